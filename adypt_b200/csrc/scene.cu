@@ -1,0 +1,332 @@
+// Scene upload, GPU Woop construction and the batch traversal entry points of the C-ABI.
+#include "scene.h"
+#include "traverse.cuh"
+#include <cstring>
+#include <mutex>
+
+namespace adypt {
+
+static thread_local std::string t_error;
+std::atomic<uint64_t> g_launches{0};
+
+void set_error(const std::string &msg) { t_error = msg; }
+int fail(int code, const std::string &msg)
+{
+	t_error = msg;
+	return code;
+}
+
+// ------------------------------------------------------------------------------------------------
+// OglScene::init_triangles (OglScene.cpp:93-116) on the GPU, one thread per leaf reference. The 4x4
+// inverse follows glm::inverse's cofactor expansion (dep/glm/detail/func_matrix.inl:294-351) operation by
+// operation; the library is built with -fmad=false so nothing is contracted and the rows are
+// bit-identical to the host build of the reference.
+__device__ void mat4_inverse_glm(const float m[4][4], float out[4][4])
+{
+	const float Coef00 = m[2][2] * m[3][3] - m[3][2] * m[2][3];
+	const float Coef02 = m[1][2] * m[3][3] - m[3][2] * m[1][3];
+	const float Coef03 = m[1][2] * m[2][3] - m[2][2] * m[1][3];
+	const float Coef04 = m[2][1] * m[3][3] - m[3][1] * m[2][3];
+	const float Coef06 = m[1][1] * m[3][3] - m[3][1] * m[1][3];
+	const float Coef07 = m[1][1] * m[2][3] - m[2][1] * m[1][3];
+	const float Coef08 = m[2][1] * m[3][2] - m[3][1] * m[2][2];
+	const float Coef10 = m[1][1] * m[3][2] - m[3][1] * m[1][2];
+	const float Coef11 = m[1][1] * m[2][2] - m[2][1] * m[1][2];
+	const float Coef12 = m[2][0] * m[3][3] - m[3][0] * m[2][3];
+	const float Coef14 = m[1][0] * m[3][3] - m[3][0] * m[1][3];
+	const float Coef15 = m[1][0] * m[2][3] - m[2][0] * m[1][3];
+	const float Coef16 = m[2][0] * m[3][2] - m[3][0] * m[2][2];
+	const float Coef18 = m[1][0] * m[3][2] - m[3][0] * m[1][2];
+	const float Coef19 = m[1][0] * m[2][2] - m[2][0] * m[1][2];
+	const float Coef20 = m[2][0] * m[3][1] - m[3][0] * m[2][1];
+	const float Coef22 = m[1][0] * m[3][1] - m[3][0] * m[1][1];
+	const float Coef23 = m[1][0] * m[2][1] - m[2][0] * m[1][1];
+	const float Fac0[4] = {Coef00, Coef00, Coef02, Coef03}, Fac1[4] = {Coef04, Coef04, Coef06, Coef07};
+	const float Fac2[4] = {Coef08, Coef08, Coef10, Coef11}, Fac3[4] = {Coef12, Coef12, Coef14, Coef15};
+	const float Fac4[4] = {Coef16, Coef16, Coef18, Coef19}, Fac5[4] = {Coef20, Coef20, Coef22, Coef23};
+	const float V0[4] = {m[1][0], m[0][0], m[0][0], m[0][0]}, V1[4] = {m[1][1], m[0][1], m[0][1], m[0][1]};
+	const float V2[4] = {m[1][2], m[0][2], m[0][2], m[0][2]}, V3[4] = {m[1][3], m[0][3], m[0][3], m[0][3]};
+	const float SignA[4] = {+1.f, -1.f, +1.f, -1.f}, SignB[4] = {-1.f, +1.f, -1.f, +1.f};
+	float inv[4][4];
+#pragma unroll
+	for (int i = 0; i < 4; ++i) {
+		const float Inv0 = V1[i] * Fac0[i] - V2[i] * Fac1[i] + V3[i] * Fac2[i];
+		const float Inv1 = V0[i] * Fac0[i] - V2[i] * Fac3[i] + V3[i] * Fac4[i];
+		const float Inv2 = V0[i] * Fac1[i] - V1[i] * Fac3[i] + V3[i] * Fac5[i];
+		const float Inv3 = V0[i] * Fac2[i] - V1[i] * Fac4[i] + V2[i] * Fac5[i];
+		inv[0][i] = Inv0 * SignA[i];
+		inv[1][i] = Inv1 * SignB[i];
+		inv[2][i] = Inv2 * SignA[i];
+		inv[3][i] = Inv3 * SignB[i];
+	}
+	const float d0 = m[0][0] * inv[0][0], d1 = m[0][1] * inv[1][0], d2 = m[0][2] * inv[2][0], d3 = m[0][3] * inv[3][0];
+	const float Dot1 = (d0 + d1) + (d2 + d3);
+	const float OneOverDeterminant = __fdiv_rn(1.0f, Dot1);
+#pragma unroll
+	for (int c = 0; c < 4; ++c)
+#pragma unroll
+		for (int r = 0; r < 4; ++r) out[c][r] = inv[c][r] * OneOverDeterminant;
+}
+
+__global__ void build_woop_kernel(const uint8_t *__restrict__ tris, const int32_t *__restrict__ tri_indices, uint32_t n_refs,
+                                  float4 *__restrict__ woop)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_refs) return;
+	const float *p = (const float *)(tris + (size_t)tri_indices[i] * 100u); // 100-byte stride: 4-byte aligned
+	const float v0[3] = {p[0], p[1], p[2]}, v1[3] = {p[3], p[4], p[5]}, v2[3] = {p[6], p[7], p[8]};
+	const float e0[3] = {v0[0] - v2[0], v0[1] - v2[1], v0[2] - v2[2]};
+	const float e1[3] = {v1[0] - v2[0], v1[1] - v2[1], v1[2] - v2[2]};
+	// glm::cross: (x.y*y.z - y.y*x.z, x.z*y.x - y.z*x.x, x.x*y.y - y.x*x.y)
+	const float cr[3] = {e0[1] * e1[2] - e1[1] * e0[2], e0[2] * e1[0] - e1[2] * e0[0], e0[0] * e1[1] - e1[0] * e0[1]};
+	// the mat4 constructor of OglScene.cpp:104-109 takes column-major scalars
+	const float m[4][4] = {{e0[0], e1[0], cr[0], v2[0]}, {e0[1], e1[1], cr[1], v2[1]}, {e0[2], e1[2], cr[2], v2[2]}, {0.f, 0.f, 0.f, 1.f}};
+	float inv[4][4];
+	mat4_inverse_glm(m, inv);
+	woop[3 * (size_t)i + 0] = make_float4(inv[2][0], inv[2][1], inv[2][2], -inv[2][3]);
+	woop[3 * (size_t)i + 1] = make_float4(inv[0][0], inv[0][1], inv[0][2], inv[0][3]);
+	woop[3 * (size_t)i + 2] = make_float4(inv[1][0], inv[1][1], inv[1][2], inv[1][3]);
+}
+
+// ------------------------------------------------------------------------------------------------
+int launch_trace(adypt_scene *s, const float4 *d_rays, uint64_t n, int32_t *d_tri, float *d_t, float2 *d_uv, uint8_t *d_occ,
+                 cudaStream_t stream, const unsigned long long *d_n)
+{
+	if (n == 0) return ADYPT_OK;
+	const bool any = d_occ != nullptr;
+	TraceParams p;
+	p.nodes = s->d_nodes;
+	p.woop = s->d_woop;
+	p.tri_indices = s->d_tri_indices;
+	p.rays = d_rays;
+	p.n = n;
+	p.n_ptr = d_n;
+	p.out_tri = d_tri;
+	p.out_t = d_t;
+	p.out_uv = d_uv;
+	p.out_occ = d_occ;
+	p.counter = s->d_counters + (s->counter_cursor++ % kCounterRing);
+	p.refill_threshold = s->refill_threshold > 0 ? s->refill_threshold : 28;
+	int per_sm = s->ctas_per_sm > 0 ? s->ctas_per_sm : (any ? s->occ_any : s->occ_closest);
+	if (per_sm < 1) per_sm = 1;
+	unsigned long long warps_needed = (n + 31) / 32;
+	unsigned long long ctas_needed = (warps_needed + (kTraceBlock / 32) - 1) / (kTraceBlock / 32);
+	unsigned grid = (unsigned)s->sm_count * (unsigned)per_sm;
+	if (ctas_needed < grid) grid = (unsigned)ctas_needed;
+	ADYPT_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned long long), stream));
+	if (any) trace_kernel<true><<<grid, kTraceBlock, 0, stream>>>(p);
+	else trace_kernel<false><<<grid, kTraceBlock, 0, stream>>>(p);
+	count_launch();
+	ADYPT_CUDA(cudaGetLastError());
+	return ADYPT_OK;
+}
+
+static int upload(void **dst, const void *src, size_t bytes, uint64_t *total)
+{
+	*dst = nullptr;
+	if (bytes == 0) return ADYPT_OK;
+	ADYPT_CUDA(cudaMalloc(dst, bytes));
+	ADYPT_CUDA(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
+	*total += bytes;
+	return ADYPT_OK;
+}
+
+static void free_scene(adypt_scene *s)
+{
+	DeviceGuard g(s->device);
+	cudaFree(s->d_nodes);
+	cudaFree(s->d_woop);
+	cudaFree(s->d_tri_indices);
+	cudaFree(s->d_tris);
+	cudaFree(s->d_mats);
+	cudaFree(s->d_counters);
+	s->stage_in.release();
+	s->stage_out.release();
+	delete s;
+}
+
+} // namespace adypt
+
+using namespace adypt;
+
+extern "C" {
+
+const char *adypt_last_error(void) { return t_error.c_str(); }
+int adypt_version(void) { return ADYPT_B200_VERSION; }
+
+int adypt_device_count(int *count)
+{
+	if (!count) return fail(ADYPT_EINVAL, "count is NULL");
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess) {
+		*count = 0;
+		return fail(ADYPT_ENODEV, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+	}
+	*count = n;
+	return ADYPT_OK;
+}
+
+int adypt_launch_count(uint64_t *launches)
+{
+	if (!launches) return fail(ADYPT_EINVAL, "launches is NULL");
+	*launches = g_launches.load();
+	return ADYPT_OK;
+}
+
+int adypt_scene_create(const adypt_scene_desc *d, adypt_scene **out)
+{
+	if (!d || !out) return fail(ADYPT_EINVAL, "desc/out is NULL");
+	*out = nullptr;
+	if (!d->nodes || d->n_nodes == 0) return fail(ADYPT_EINVAL, "scene needs at least the root node");
+	if (d->n_refs && !d->tri_indices) return fail(ADYPT_EINVAL, "tri_indices is NULL");
+	if (d->n_refs && !d->woop && !d->triangles) return fail(ADYPT_EINVAL, "need woop or triangles to build it from");
+	if (d->n_tris && !d->triangles) return fail(ADYPT_EINVAL, "triangles is NULL");
+	if (d->n_mats && !d->materials) return fail(ADYPT_EINVAL, "materials is NULL");
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+		return fail(ADYPT_ENODEV, "no CUDA device: adypt_b200 has no CPU fallback");
+	if (d->device < 0 || d->device >= ndev) return fail(ADYPT_ENODEV, "device ordinal out of range");
+	// validate what traversal dereferences so a bad array cannot read out of bounds on the device
+	for (uint32_t i = 0; i < d->n_refs; ++i)
+		if (d->triangles && (d->tri_indices[i] < 0 || (uint32_t)d->tri_indices[i] >= d->n_tris))
+			return fail(ADYPT_EINVAL, "tri_indices entry out of range");
+	{
+		const Node *nodes = (const Node *)d->nodes;
+		for (uint32_t i = 0; i < d->n_nodes; ++i) {
+			const Node &n = nodes[i];
+			uint32_t n_inner = 0, max_tri = 0;
+			const uint32_t metas[2] = {n.meta_lo, n.meta_hi};
+			for (int k = 0; k < 8; ++k) {
+				const uint32_t m = (metas[k >> 2] >> (8 * (k & 3))) & 0xffu;
+				if (m == 0) continue;
+				if ((m & 0x1fu) >= 24u) ++n_inner;
+				else {
+					const uint32_t cnt = __builtin_popcount(m >> 5), end = (m & 0x1fu) + cnt;
+					if (end > max_tri) max_tri = end;
+				}
+			}
+			if (n_inner && (uint64_t)n.child_base + n_inner > d->n_nodes) return fail(ADYPT_EINVAL, "node child index out of range");
+			if (max_tri && (uint64_t)n.tri_base + max_tri > d->n_refs) return fail(ADYPT_EINVAL, "node triangle index out of range");
+		}
+	}
+
+	DeviceGuard g(d->device);
+	if (!g.ok) return fail(ADYPT_ENODEV, "cudaSetDevice failed");
+	adypt_scene *s = new adypt_scene;
+	s->device = d->device;
+	s->n_nodes = d->n_nodes;
+	s->n_refs = d->n_refs;
+	s->n_tris = d->n_tris;
+	s->n_mats = d->n_mats;
+	cudaDeviceProp prop;
+	if (cudaGetDeviceProperties(&prop, d->device) != cudaSuccess) { delete s; return fail(ADYPT_ECUDA, "cudaGetDeviceProperties failed"); }
+	s->sm_count = prop.multiProcessorCount;
+	int rc;
+#define UP(dst, src, bytes)                                                          \
+	if ((rc = upload((void **)&(dst), (src), (bytes), &s->device_bytes)) != ADYPT_OK) { \
+		free_scene(s);                                                               \
+		return rc;                                                                   \
+	}
+	UP(s->d_nodes, d->nodes, (size_t)d->n_nodes * 80u);
+	UP(s->d_tri_indices, d->tri_indices, (size_t)d->n_refs * 4u);
+	UP(s->d_tris, d->triangles, (size_t)d->n_tris * 100u);
+	UP(s->d_mats, d->materials, (size_t)d->n_mats * 64u);
+	if (d->woop) {
+		UP(s->d_woop, d->woop, (size_t)d->n_refs * 48u);
+	} else if (d->n_refs) {
+		if (cudaMalloc((void **)&s->d_woop, (size_t)d->n_refs * 48u) != cudaSuccess) { free_scene(s); return fail(ADYPT_ENOMEM, "cudaMalloc woop"); }
+		s->device_bytes += (size_t)d->n_refs * 48u;
+		build_woop_kernel<<<(d->n_refs + 255) / 256, 256>>>(s->d_tris, s->d_tri_indices, d->n_refs, s->d_woop);
+		count_launch();
+		cudaError_t e = cudaDeviceSynchronize();
+		if (e != cudaSuccess) { free_scene(s); return fail(ADYPT_ECUDA, std::string("build_woop_kernel: ") + cudaGetErrorString(e)); }
+	}
+#undef UP
+	if (cudaMalloc((void **)&s->d_counters, kCounterRing * sizeof(unsigned long long)) != cudaSuccess) { free_scene(s); return fail(ADYPT_ENOMEM, "cudaMalloc counters"); }
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->occ_closest, trace_kernel<false>, kTraceBlock, 0);
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->occ_any, trace_kernel<true>, kTraceBlock, 0);
+	*out = s;
+	return ADYPT_OK;
+}
+
+int adypt_scene_destroy(adypt_scene *scene)
+{
+	if (!scene) return ADYPT_OK;
+	free_scene(scene);
+	return ADYPT_OK;
+}
+
+int adypt_scene_read_woop(adypt_scene *s, float *out)
+{
+	if (!s || !out) return fail(ADYPT_EINVAL, "scene/out is NULL");
+	DeviceGuard g(s->device);
+	ADYPT_CUDA(cudaMemcpy(out, s->d_woop, (size_t)s->n_refs * 48u, cudaMemcpyDeviceToHost));
+	return ADYPT_OK;
+}
+
+int adypt_scene_device_bytes(adypt_scene *s, uint64_t *bytes)
+{
+	if (!s || !bytes) return fail(ADYPT_EINVAL, "scene/bytes is NULL");
+	*bytes = s->device_bytes;
+	return ADYPT_OK;
+}
+
+int adypt_trace_configure(adypt_scene *s, int ctas_per_sm, int refill_threshold)
+{
+	if (!s) return fail(ADYPT_EINVAL, "scene is NULL");
+	if (ctas_per_sm < 0 || refill_threshold < 0 || refill_threshold > 32) return fail(ADYPT_EINVAL, "bad tuning value");
+	s->ctas_per_sm = ctas_per_sm;
+	s->refill_threshold = refill_threshold;
+	return ADYPT_OK;
+}
+
+static int trace_host(adypt_scene *s, const float *rays, uint64_t n, int32_t *tri, float *t, float *uv, uint8_t *occ, cudaStream_t stream)
+{
+	// host arrays: stage through device buffers owned by the scene; returns with results in place
+	const size_t in_bytes = (size_t)n * 32u;
+	const size_t o_tri = 0, o_t = o_tri + (size_t)n * 4u, o_uv = o_t + (size_t)n * 4u, o_occ = o_uv + (size_t)n * 8u;
+	const size_t out_bytes = o_occ + (size_t)n;
+	ADYPT_TRY(s->stage_in.reserve(in_bytes));
+	ADYPT_TRY(s->stage_out.reserve(out_bytes));
+	uint8_t *o = s->stage_out.as<uint8_t>();
+	ADYPT_CUDA(cudaMemcpyAsync(s->stage_in.ptr, rays, in_bytes, cudaMemcpyHostToDevice, stream));
+	if (occ) {
+		ADYPT_TRY(launch_trace(s, s->stage_in.as<float4>(), n, nullptr, nullptr, nullptr, o + o_occ, stream));
+		ADYPT_CUDA(cudaMemcpyAsync(occ, o + o_occ, (size_t)n, cudaMemcpyDeviceToHost, stream));
+	} else {
+		ADYPT_TRY(launch_trace(s, s->stage_in.as<float4>(), n, (int32_t *)(o + o_tri), t ? (float *)(o + o_t) : nullptr,
+		                       uv ? (float2 *)(o + o_uv) : nullptr, nullptr, stream));
+		ADYPT_CUDA(cudaMemcpyAsync(tri, o + o_tri, (size_t)n * 4u, cudaMemcpyDeviceToHost, stream));
+		if (t) ADYPT_CUDA(cudaMemcpyAsync(t, o + o_t, (size_t)n * 4u, cudaMemcpyDeviceToHost, stream));
+		if (uv) ADYPT_CUDA(cudaMemcpyAsync(uv, o + o_uv, (size_t)n * 8u, cudaMemcpyDeviceToHost, stream));
+	}
+	ADYPT_CUDA(cudaStreamSynchronize(stream));
+	return ADYPT_OK;
+}
+
+int adypt_trace_closest(adypt_scene *s, const float *rays, uint64_t n, int32_t *tri, float *t, float *uv, int memspace, void *stream)
+{
+	if (!s) return fail(ADYPT_EINVAL, "scene is NULL");
+	if (n == 0) return ADYPT_OK;
+	if (!rays || !tri) return fail(ADYPT_EINVAL, "rays/tri is NULL");
+	if (memspace != ADYPT_MEM_HOST && memspace != ADYPT_MEM_DEVICE) return fail(ADYPT_EINVAL, "bad memspace");
+	DeviceGuard g(s->device);
+	if (memspace == ADYPT_MEM_DEVICE)
+		return launch_trace(s, (const float4 *)rays, n, tri, t, (float2 *)uv, nullptr, (cudaStream_t)stream);
+	return trace_host(s, rays, n, tri, t, uv, nullptr, (cudaStream_t)stream);
+}
+
+int adypt_trace_any(adypt_scene *s, const float *rays, uint64_t n, uint8_t *occluded, int memspace, void *stream)
+{
+	if (!s) return fail(ADYPT_EINVAL, "scene is NULL");
+	if (n == 0) return ADYPT_OK;
+	if (!rays || !occluded) return fail(ADYPT_EINVAL, "rays/occluded is NULL");
+	if (memspace != ADYPT_MEM_HOST && memspace != ADYPT_MEM_DEVICE) return fail(ADYPT_EINVAL, "bad memspace");
+	DeviceGuard g(s->device);
+	if (memspace == ADYPT_MEM_DEVICE)
+		return launch_trace(s, (const float4 *)rays, n, nullptr, nullptr, nullptr, occluded, (cudaStream_t)stream);
+	return trace_host(s, rays, n, nullptr, nullptr, nullptr, occluded, (cudaStream_t)stream);
+}
+
+} // extern "C"

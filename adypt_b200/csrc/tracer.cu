@@ -1,0 +1,799 @@
+// Wavefront path tracer + AOV viewer: the CUDA stand-in for OglPathTracer (src/Tracer/OglPathTracer.*)
+// and for the two GLSL programs it dispatches (shaders/primaryray.glsl, shaders/pathtracer.glsl).
+//
+// The reference runs one megakernel thread per pixel per sample (pathtracer.glsl:220-227). Here one
+// "batch" is S consecutive samples of every pixel (S <= tmpLifetime, all sharing one primary hit and one
+// sub-pixel stratum, pathtracer.glsl:113-127,206-211) and the integrator is split into queue-driven
+// stages so that every traversal launch sees a dense array of live rays:
+//   generate  : camera rays for the batch's stratum                      (Camera(), SubPixel())
+//   extend    : closest-hit traversal of a ray queue (trace_kernel, traverse.cuh)
+//   shade     : FetchInfo + material switch + next-ray sampling, appends survivors to the next queue
+//   accumulate: clamp + running mean in sample order                      (main(), :224-226)
+// Queue lengths stay on the device (kernels read them through pointers), so a whole batch is enqueued
+// without a host round trip. Per-path results are independent of queue order, and the accumulate stage
+// applies samples in ascending spp, so images are bit-reproducible run to run and identical to
+// dispatching the reference's megakernel once per sample.
+//
+// FP policy: every GLSL expression is evaluated un-fused, left to right in IEEE fp32
+// (the library is built with -fmad=false); sin/cos/pow come from CUDA's libdevice, which is why image
+// parity against the CPU oracle is an RMSE bound rather than bit equality.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+#include "hostmath.h"
+#include "scene.h"
+#include "traverse.cuh"
+
+namespace adypt {
+
+struct CameraArgs { // uuCamera (pathtracer.glsl:27-32), by value
+	float origin[3], tmin;
+	float inv_proj[16], inv_view[16];
+};
+
+struct PTArgs { // uuPT (pathtracer.glsl:34-38) + batch bookkeeping
+	int32_t max_bounce, subpixel, tmp_lifetime;
+	float clamp, sun[3];
+	int32_t width, height;
+	int32_t first_spp; // spp of the batch's first sample
+	int32_t n_samples; // S
+};
+
+// ---------------------------------------------------------------------------------------------
+// GLSL-shaped helpers
+struct V3 { float x, y, z; };
+__device__ __forceinline__ V3 v3(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ V3 operator*(V3 a, V3 b) { return v3(a.x * b.x, a.y * b.y, a.z * b.z); }
+__device__ __forceinline__ V3 operator*(V3 a, float s) { return v3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ V3 operator-(V3 a) { return v3(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ V3 cross(V3 x, V3 y) { return v3(x.y * y.z - y.y * x.z, x.z * y.x - y.z * x.x, x.x * y.y - y.x * x.y); }
+__device__ __forceinline__ V3 normalize(V3 v)
+{
+	const float inv = __fdiv_rn(1.0f, __fsqrt_rn(dot(v, v)));
+	return v * inv;
+}
+__device__ __forceinline__ V3 reflect(V3 I, V3 N) { return I - N * (2.0f * dot(N, I)); }
+__device__ __forceinline__ float glsl_min(float x, float y) { return y < x ? y : x; }
+__device__ __forceinline__ float glsl_max(float x, float y) { return x < y ? y : x; }
+__device__ __forceinline__ float fract(float x) { return x - floorf(x); }
+
+// Camera(bias): primaryray.glsl:39-44 (bias 0) / pathtracer.glsl:213-218
+__device__ __forceinline__ V3 camera_dir(const CameraArgs &c, int w, int h, int px, int py, float bx, float by)
+{
+	const float sx = 2.0f * ((float)px + bx) / (float)w - 1.0f;
+	const float sy = -(2.0f * ((float)py + by) / (float)h - 1.0f);
+	const float *ip = c.inv_proj, *iv = c.inv_view;
+	const float vx = ip[0] * sx + ip[4] * sy + ip[8] * 1.0f + ip[12] * 1.0f;
+	const float vy = ip[1] * sx + ip[5] * sy + ip[9] * 1.0f + ip[13] * 1.0f;
+	const float vz = ip[2] * sx + ip[6] * sy + ip[10] * 1.0f + ip[14] * 1.0f;
+	return normalize(v3(iv[0] * vx + iv[4] * vy + iv[8] * vz, iv[1] * vx + iv[5] * vy + iv[9] * vz, iv[2] * vx + iv[6] * vy + iv[10] * vz));
+}
+
+__device__ __forceinline__ void subpixel_bias(int subpixel, int tmp_lifetime, int spp, float *bx, float *by) // SubPixel(), :206-211
+{
+	const int idx = (spp / tmp_lifetime) % (subpixel * subpixel);
+	const float unit = 1.0f / (float)subpixel;
+	*bx = (float)(idx / subpixel) * unit;
+	*by = (float)(idx % subpixel) * unit;
+}
+
+__global__ void k_generate(CameraArgs cam, int w, int h, float bx, float by, float4 *__restrict__ rays)
+{
+	const unsigned npix = (unsigned)w * (unsigned)h;
+	for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x) {
+		const V3 d = camera_dir(cam, w, h, (int)(i % (unsigned)w), (int)(i / (unsigned)w), bx, by);
+		rays[2 * (size_t)i] = make_float4(cam.origin[0], cam.origin[1], cam.origin[2], cam.tmin);
+		rays[2 * (size_t)i + 1] = make_float4(d.x, d.y, d.z, 0.0f);
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sobol: uSobol for every sample of the batch, computed on the device from the direction numbers
+// (Sobol.cpp:16-21 in closed form: state after n calls = XOR of columns selected by gray(n)).
+__global__ void k_sobol(const uint32_t *__restrict__ dirs, int dims, int first_spp, int n_samples, float *__restrict__ out)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= dims * n_samples) return;
+	const int s = i / dims, j = i % dims;
+	const uint32_t n = (uint32_t)(first_spp + s) + 1u;
+	uint32_t gray = n ^ (n >> 1), x = 0;
+	for (int k = 0; gray; gray >>= 1, ++k)
+		if (gray & 1u) x ^= dirs[j * 32 + k];
+	out[i] = (float)((double)x / 4294967296.0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// shading
+
+struct ShadeBuffers {
+	const uint8_t *__restrict__ tris;        // 100-byte records
+	const Material *__restrict__ mats;
+	const uchar2 *__restrict__ bias;         // uSobolBiasImg
+	const float *__restrict__ sobol;         // [S][2*max_bounce]
+	// primary hit cache (uPrimaryTmpImg): x = tri id bits, zw = uv
+	const int32_t *__restrict__ prim_tri;
+	const float2 *__restrict__ prim_uv;
+	// current queue (bounce >= 1)
+	const float4 *__restrict__ in_rays;      // 2 per entry; .w of the 2nd = path id bits
+	const int32_t *__restrict__ in_tri;
+	const float2 *__restrict__ in_uv;
+	const unsigned long long *in_count;
+	// next queue
+	float4 *__restrict__ out_rays;
+	unsigned long long *out_count;
+	// per-path state
+	float4 *__restrict__ color;              // throughput
+	float4 *__restrict__ ret;                // radiance so far; final value once the path ends
+	unsigned long long *segments;            // statistics
+};
+
+__device__ __forceinline__ V3 load3(const float *p) { return v3(p[0], p[1], p[2]); }
+
+__device__ __forceinline__ V3 bary(const float *a, const float *b, const float *c, float u, float v) // :77-85
+{
+	const float w = 1.0f - u - v;
+	return v3(a[0] * u + b[0] * v + c[0] * w, a[1] * u + b[1] * v + c[1] * w, a[2] * u + b[2] * v + c[2] * w);
+}
+
+__device__ __forceinline__ V3 sample_hemisphere(float rx, float ry, float e) // :52-64
+{
+	rx *= 6.28318530718f;
+	const float cos_phi = cosf(rx), sin_phi = sinf(rx);
+	const float cos_theta = powf(1.0f - ry, 1.0f / (e + 1.0f));
+	const float sin_theta = __fsqrt_rn(1.0f - cos_theta * cos_theta);
+	return normalize(v3(sin_theta * cos_phi, sin_theta * sin_phi, cos_theta));
+}
+
+__device__ __forceinline__ V3 align_direction(V3 dir, V3 target) // :66-71
+{
+	const V3 a = fabsf(target.x) > .01f ? v3(0.f, 1.f, 0.f) : v3(1.f, 0.f, 0.f);
+	const V3 u = normalize(cross(a, target));
+	const V3 v = cross(target, u);
+	return u * dir.x + v * dir.y + target * dir.z;
+}
+
+// One segment of Render's loop body after the intersection (pathtracer.glsl:130-201).
+// Returns true when the path continues with (origin, dir); false when it has ended (ret is final).
+__device__ __forceinline__ bool shade_segment(const ShadeBuffers &B, const PTArgs &A, int b, int32_t tri_idx, float u, float v, float rx,
+                                              float ry, V3 &origin, V3 &dir, V3 &color, V3 &ret)
+{
+	if (tri_idx == -1) { // :130-135
+		ret = ret + color * v3(A.sun[0], A.sun[1], A.sun[2]);
+		return false;
+	}
+	const float *t = (const float *)(B.tris + (size_t)tri_idx * 100u);
+	const int32_t matid = *(const int32_t *)(t + 24);
+	const Material m = B.mats[matid];
+	V3 normal = normalize(bary(t + 9, t + 12, t + 15, u, v));
+	origin = bary(t, t + 3, t + 6, u, v); // :138
+	const V3 emissive = v3(m.er, m.eg, m.eb), diffuse = v3(m.dr, m.dg, m.db), specular = v3(m.sr, m.sg, m.sb);
+	ret = ret + color * emissive;
+	if (b == A.max_bounce - 1) return false; // the loop ends here; the sampled direction would never be used
+	if (m.illum < 6 && dot(dir, normal) > 0.0f) normal = -normal; // :141-142
+
+	bool do_diffuse = false;
+	switch (m.illum) { // :144-201
+	case 2: {
+		const float e = m.shininess * 0.01f;
+		if (e > 0.3f) {
+			const V3 r = reflect(dir, normal), s = sample_hemisphere(rx, ry, e);
+			dir = align_direction(s, r);
+			if (dot(dir, normal) < 0.0f) return false;
+			color = color * (diffuse + specular * powf(dot(dir, r), e));
+		} else
+			do_diffuse = true;
+		break;
+	}
+	case 1:
+		do_diffuse = true;
+		break;
+	case 3: case 4: case 5:
+		color = color * specular;
+		dir = reflect(dir, normal);
+		break;
+	case 6: case 7: {
+		float eta = m.ior;
+		float cosi = dot(dir, normal);
+		float fresnel, etai, etat;
+		if (cosi > 0.0f) { etai = eta; etat = 1.0f; }
+		else { etai = 1.0f; etat = eta; normal = -normal; cosi = -cosi; }
+		eta = etai / etat;
+		const float sint = etai / etat * __fsqrt_rn(glsl_max(0.f, 1.0f - cosi * cosi));
+		if (sint >= 1.0f) fresnel = 1.0f;
+		else {
+			const float cost = __fsqrt_rn(glsl_max(0.f, 1.0f - sint * sint));
+			const float Rs = ((etat * cosi) - (etai * cost)) / ((etat * cosi) + (etai * cost));
+			const float Rp = ((etai * cosi) - (etat * cost)) / ((etai * cosi) + (etat * cost));
+			fresnel = (Rs * Rs + Rp * Rp) * 0.5f;
+		}
+		const float cos2 = 1.0f - eta * eta * (1.0f - cosi * cosi);
+		if (cos2 > 0.0f && rx >= fresnel) {
+			dir = normalize(dir * eta + normal * (eta * cosi + __fsqrt_rn(cos2)));
+			normal = -normal;
+		} else
+			dir = reflect(dir, normal);
+		break;
+	}
+	default: break; // any other illum passes straight through
+	}
+	if (do_diffuse) { // :156-159
+		dir = align_direction(sample_hemisphere(rx, ry, 0.0f), normal);
+		color = color * diffuse;
+	}
+	return true;
+}
+
+// warp-aggregated append: returns this lane's slot in the output queue (valid when `keep`)
+__device__ __forceinline__ unsigned long long queue_append(bool keep, unsigned long long *counter)
+{
+	const unsigned m = __ballot_sync(kFullMask, keep);
+	if (m == 0u) return 0ull;
+	const unsigned lane = threadIdx.x & 31u, leader = (unsigned)__ffs((int)m) - 1u;
+	unsigned long long base = 0;
+	if (lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(m));
+	base = __shfl_sync(kFullMask, base, (int)leader);
+	return base + (unsigned long long)__popc(m & ((1u << lane) - 1u));
+}
+
+// bounce 0 for every (sample, pixel) of the batch: reads the cached primary hit
+__global__ void __launch_bounds__(256) k_shade_primary(ShadeBuffers B, PTArgs A, CameraArgs cam)
+{
+	const unsigned long long npix = (unsigned long long)A.width * (unsigned long long)A.height;
+	const unsigned long long total = npix * (unsigned long long)A.n_samples;
+	const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+	const unsigned long long rounds = (total + stride - 1) / stride;
+	float bx, by;
+	subpixel_bias(A.subpixel, A.tmp_lifetime, A.first_spp, &bx, &by);
+	const int dims = 2 * A.max_bounce;
+	for (unsigned long long r = 0; r < rounds; ++r) {
+		const unsigned long long id = r * stride + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+		bool keep = false;
+		V3 origin = v3(cam.origin[0], cam.origin[1], cam.origin[2]), dir = v3(0, 0, 0), color = v3(1.f, 1.f, 1.f), ret = v3(0.f, 0.f, 0.f);
+		if (id < total) {
+			const unsigned pix = (unsigned)(id % npix), s = (unsigned)(id / npix);
+			dir = camera_dir(cam, A.width, A.height, (int)(pix % (unsigned)A.width), (int)(pix / (unsigned)A.width), bx, by);
+			const uchar2 bb = B.bias[pix];
+			const float rx = fract(B.sobol[s * dims + 0] + (float)bb.x / 255.0f);
+			const float ry = fract(B.sobol[s * dims + 1] + (float)bb.y / 255.0f);
+			const float2 uv = B.prim_uv[pix];
+			keep = shade_segment(B, A, 0, B.prim_tri[pix], uv.x, uv.y, rx, ry, origin, dir, color, ret);
+			B.ret[id] = make_float4(ret.x, ret.y, ret.z, 0.0f);
+			if (keep) B.color[id] = make_float4(color.x, color.y, color.z, 0.0f);
+		}
+		const unsigned long long slot = queue_append(keep, B.out_count);
+		if (keep) {
+			B.out_rays[2 * slot] = make_float4(origin.x, origin.y, origin.z, cam.tmin);
+			B.out_rays[2 * slot + 1] = make_float4(dir.x, dir.y, dir.z, __uint_as_float((unsigned)id));
+		}
+	}
+}
+
+// bounce b >= 1 over the current queue
+__global__ void __launch_bounds__(256) k_shade_bounce(ShadeBuffers B, PTArgs A, int b, float tmin)
+{
+	const unsigned long long npix = (unsigned long long)A.width * (unsigned long long)A.height;
+	const unsigned long long total = *B.in_count;
+	const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+	const unsigned long long rounds = (total + stride - 1) / stride;
+	const int dims = 2 * A.max_bounce;
+	if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(B.segments, total);
+	for (unsigned long long r = 0; r < rounds; ++r) {
+		const unsigned long long q = r * stride + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+		bool keep = false;
+		V3 origin = v3(0, 0, 0), dir = v3(0, 0, 0), color = v3(0, 0, 0), ret = v3(0, 0, 0);
+		unsigned id = 0;
+		if (q < total) {
+			const float4 r1 = B.in_rays[2 * q + 1];
+			dir = v3(r1.x, r1.y, r1.z);
+			id = __float_as_uint(r1.w);
+			const unsigned pix = (unsigned)(id % npix), s = (unsigned)(id / npix);
+			const uchar2 bb = B.bias[pix];
+			const float rx = fract(B.sobol[s * dims + 2 * b] + (float)bb.x / 255.0f);
+			const float ry = fract(B.sobol[s * dims + 2 * b + 1] + (float)bb.y / 255.0f);
+			const float4 c4 = B.color[id], r4 = B.ret[id];
+			color = v3(c4.x, c4.y, c4.z);
+			ret = v3(r4.x, r4.y, r4.z);
+			const float2 uv = B.in_uv[q];
+			keep = shade_segment(B, A, b, B.in_tri[q], uv.x, uv.y, rx, ry, origin, dir, color, ret);
+			B.ret[id] = make_float4(ret.x, ret.y, ret.z, 0.0f);
+			if (keep) B.color[id] = make_float4(color.x, color.y, color.z, 0.0f);
+		}
+		const unsigned long long slot = queue_append(keep, B.out_count);
+		if (keep) {
+			B.out_rays[2 * slot] = make_float4(origin.x, origin.y, origin.z, tmin);
+			B.out_rays[2 * slot + 1] = make_float4(dir.x, dir.y, dir.z, __uint_as_float(id));
+		}
+	}
+}
+
+// main() :224-226 for the S samples of the batch, in ascending spp
+__global__ void k_accumulate_mean(const float4 *__restrict__ ret, float4 *__restrict__ out, unsigned npix, int first_spp, int n_samples, float clamp)
+{
+	for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x) {
+		float4 o = out[i];
+		for (int s = 0; s < n_samples; ++s) {
+			const float4 r = ret[(size_t)s * npix + i];
+			const float fs = (float)(first_spp + s), fs1 = (float)(first_spp + s + 1);
+			o.x = (o.x * fs + glsl_min(r.x, clamp)) / fs1;
+			o.y = (o.y * fs + glsl_min(r.y, clamp)) / fs1;
+			o.z = (o.z * fs + glsl_min(r.z, clamp)) / fs1;
+			o.w = 1.0f;
+		}
+		out[i] = o;
+	}
+}
+
+// sharded mode: clamped radiance added to a sum accumulator in ascending spp; .w counts samples
+__global__ void k_accumulate_sum(const float4 *__restrict__ ret, float4 *__restrict__ sum, unsigned npix, int n_samples, float clamp)
+{
+	for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x) {
+		float4 o = sum[i];
+		for (int s = 0; s < n_samples; ++s) {
+			const float4 r = ret[(size_t)s * npix + i];
+			o.x += glsl_min(r.x, clamp);
+			o.y += glsl_min(r.y, clamp);
+			o.z += glsl_min(r.z, clamp);
+			o.w += 1.0f;
+		}
+		sum[i] = o;
+	}
+}
+
+__global__ void k_resolve_sum(const float4 *__restrict__ sum, float4 *__restrict__ out, unsigned npix)
+{
+	for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x) {
+		const float4 s = sum[i];
+		out[i] = s.w > 0.0f ? make_float4(s.x / s.w, s.y / s.w, s.z / s.w, 1.0f) : make_float4(0.f, 0.f, 0.f, 1.0f);
+	}
+}
+
+// primaryray.glsl main() :46-94 after the intersection (TEXTURE_COUNT == 0)
+__global__ void k_view(const uint8_t *__restrict__ tris, const Material *__restrict__ mats, const int32_t *__restrict__ hit_tri,
+                       const float2 *__restrict__ hit_uv, int type, unsigned npix, float4 *__restrict__ out)
+{
+	for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x) {
+		const int32_t tri = hit_tri[i];
+		V3 c = v3(0.f, 0.f, 0.f);
+		if (tri != -1) {
+			const float *t = (const float *)(tris + (size_t)tri * 100u);
+			const Material m = mats[*(const int32_t *)(t + 24)];
+			const float2 uv = hit_uv[i];
+			if (type == 0) c = v3(m.dr, m.dg, m.db);
+			else if (type == 1) c = v3(m.sr, m.sg, m.sb);
+			else if (type == 2) c = v3(m.er, m.eg, m.eb);
+			else if (type == 4) c = normalize(bary(t + 9, t + 12, t + 15, uv.x, uv.y));
+			else if (type == 5) c = bary(t, t + 3, t + 6, uv.x, uv.y);
+		}
+		out[i] = make_float4(c.x, c.y, c.z, 1.0f);
+	}
+}
+
+} // namespace adypt
+
+using namespace adypt;
+
+// ================================================================================================
+struct adypt_tracer {
+	adypt_scene *scene = nullptr;
+	adypt_pt_config cfg{};
+	int width = 0, height = 0;
+	unsigned npix = 0;
+	cudaStream_t stream = nullptr;
+	CameraArgs cam{};
+	int spp = 0;                 // m_pt_local_spp
+	bool prim_valid = false;     // primary cache holds the hit of the current block/stratum
+	int prim_block = -1;
+	// images
+	float4 *d_result = nullptr, *d_sum = nullptr;
+	int32_t *d_prim_tri = nullptr;
+	float2 *d_prim_uv = nullptr;
+	uchar2 *d_bias = nullptr;
+	std::vector<uint8_t> h_bias;
+	// Sobol
+	uint32_t *d_dirs = nullptr;
+	float *d_sobol = nullptr;
+	// wavefront
+	int batch_samples = 0;       // S
+	unsigned long long capacity = 0; // paths per batch = S * npix
+	float4 *d_rays[2] = {nullptr, nullptr};
+	int32_t *d_hit_tri = nullptr;
+	float2 *d_hit_uv = nullptr;
+	float4 *d_color = nullptr, *d_ret = nullptr;
+	unsigned long long *d_counts = nullptr; // [max_bounce + 1] queue lengths, [kCountSlots-1] = segments
+	uint64_t launches_at_create = 0;
+	uint64_t host_segments = 0;  // primary segments (known on the host)
+};
+
+namespace {
+
+constexpr int kCountSlots = 72;
+constexpr unsigned long long kDefaultMaxPaths = 48ull << 20;
+
+void free_tracer(adypt_tracer *t)
+{
+	DeviceGuard g(t->scene->device);
+	if (t->stream) cudaStreamSynchronize(t->stream);
+	cudaFree(t->d_result); cudaFree(t->d_sum); cudaFree(t->d_prim_tri); cudaFree(t->d_prim_uv); cudaFree(t->d_bias);
+	cudaFree(t->d_dirs); cudaFree(t->d_sobol); cudaFree(t->d_rays[0]); cudaFree(t->d_rays[1]); cudaFree(t->d_hit_tri);
+	cudaFree(t->d_hit_uv); cudaFree(t->d_color); cudaFree(t->d_ret); cudaFree(t->d_counts);
+	if (t->stream) cudaStreamDestroy(t->stream);
+	delete t;
+}
+
+int check_config(const adypt_pt_config *c)
+{
+	if (c->max_bounce < 1) return fail(ADYPT_EINVAL, "maxBounce must be >= 1");
+	if (2 * c->max_bounce > sobol_max_dim()) return fail(ADYPT_ERANGE, "maxBounce needs more Sobol dimensions than are built in (2*maxBounce <= 64)");
+	if (c->subpixel < 1 || c->tmp_lifetime < 1) return fail(ADYPT_EINVAL, "subpixel and tmpLifetime must be >= 1");
+	return ADYPT_OK;
+}
+
+int grid_for(unsigned long long n, int block, int sm_count)
+{
+	unsigned long long g = (n + block - 1) / block;
+	const unsigned long long cap = (unsigned long long)sm_count * 16ull;
+	if (g > cap) g = cap;
+	return g < 1 ? 1 : (int)g;
+}
+
+int alloc_wavefront(adypt_tracer *t)
+{
+	int S = t->cfg.tmp_lifetime;
+	const unsigned long long by_mem = std::max(1ull, kDefaultMaxPaths / (unsigned long long)t->npix);
+	if ((unsigned long long)S > by_mem) S = (int)by_mem;
+	if (S > 4096) S = 4096; // d_sobol holds 4096 sample vectors
+	const unsigned long long cap = (unsigned long long)S * t->npix;
+	if (cap >= (1ull << 32)) return fail(ADYPT_ERANGE, "batch too large for 32-bit path ids");
+	if (cap == t->capacity && S == t->batch_samples) return ADYPT_OK;
+	cudaFree(t->d_rays[0]); cudaFree(t->d_rays[1]); cudaFree(t->d_hit_tri); cudaFree(t->d_hit_uv); cudaFree(t->d_color); cudaFree(t->d_ret);
+	t->d_rays[0] = t->d_rays[1] = nullptr; t->d_hit_tri = nullptr; t->d_hit_uv = nullptr; t->d_color = t->d_ret = nullptr;
+	t->capacity = 0;
+	ADYPT_CUDA(cudaMalloc((void **)&t->d_rays[0], cap * 32u));
+	ADYPT_CUDA(cudaMalloc((void **)&t->d_rays[1], cap * 32u));
+	ADYPT_CUDA(cudaMalloc((void **)&t->d_hit_tri, cap * 4u));
+	ADYPT_CUDA(cudaMalloc((void **)&t->d_hit_uv, cap * 8u));
+	ADYPT_CUDA(cudaMalloc((void **)&t->d_color, cap * 16u));
+	ADYPT_CUDA(cudaMalloc((void **)&t->d_ret, cap * 16u));
+	t->capacity = cap;
+	t->batch_samples = S;
+	return ADYPT_OK;
+}
+
+// trace the primary rays of the stratum `spp` belongs to and store them in the primary cache
+int trace_primary(adypt_tracer *t, float bx, float by)
+{
+	adypt_scene *s = t->scene;
+	k_generate<<<grid_for(t->npix, 256, s->sm_count), 256, 0, t->stream>>>(t->cam, t->width, t->height, bx, by, t->d_rays[0]);
+	count_launch();
+	ADYPT_CUDA(cudaGetLastError());
+	ADYPT_TRY(launch_trace(s, t->d_rays[0], t->npix, t->d_prim_tri, nullptr, t->d_prim_uv, nullptr, t->stream));
+	t->host_segments += t->npix;
+	return ADYPT_OK;
+}
+
+// one batch: samples [first, first+n) of every pixel, all inside one tmpLifetime block
+int run_batch(adypt_tracer *t, int first, int n, bool sum_mode)
+{
+	adypt_scene *s = t->scene;
+	const adypt_pt_config &c = t->cfg;
+	const int block = first / c.tmp_lifetime;
+	PTArgs A;
+	A.max_bounce = c.max_bounce; A.subpixel = c.subpixel; A.tmp_lifetime = c.tmp_lifetime;
+	A.clamp = c.clamp; A.sun[0] = c.sun[0]; A.sun[1] = c.sun[1]; A.sun[2] = c.sun[2];
+	A.width = t->width; A.height = t->height; A.first_spp = first; A.n_samples = n;
+	// uSpp % uTmpLife == 0 -> trace and store the primary hit; otherwise reuse it (pathtracer.glsl:113-127)
+	if (first % c.tmp_lifetime == 0 || !t->prim_valid || t->prim_block != block) {
+		float bx, by;
+		const int idx = (first / c.tmp_lifetime) % (c.subpixel * c.subpixel);
+		const float unit = 1.0f / (float)c.subpixel;
+		bx = (float)(idx / c.subpixel) * unit;
+		by = (float)(idx % c.subpixel) * unit;
+		ADYPT_TRY(trace_primary(t, bx, by));
+		t->prim_valid = true;
+		t->prim_block = block;
+	}
+	const int dims = 2 * c.max_bounce;
+	k_sobol<<<(dims * n + 127) / 128, 128, 0, t->stream>>>(t->d_dirs, dims, first, n, t->d_sobol);
+	count_launch();
+	ADYPT_CUDA(cudaMemsetAsync(t->d_counts, 0, (size_t)(c.max_bounce + 1) * sizeof(unsigned long long), t->stream));
+	ShadeBuffers B;
+	B.tris = s->d_tris; B.mats = s->d_mats; B.bias = t->d_bias; B.sobol = t->d_sobol;
+	B.prim_tri = t->d_prim_tri; B.prim_uv = t->d_prim_uv;
+	B.in_rays = nullptr; B.in_tri = t->d_hit_tri; B.in_uv = t->d_hit_uv; B.in_count = nullptr;
+	B.out_rays = t->d_rays[1]; B.out_count = t->d_counts + 1;
+	B.color = t->d_color; B.ret = t->d_ret; B.segments = t->d_counts + (kCountSlots - 1);
+	const unsigned long long total = (unsigned long long)n * t->npix;
+	k_shade_primary<<<grid_for(total, 256, s->sm_count), 256, 0, t->stream>>>(B, A, t->cam);
+	count_launch();
+	ADYPT_CUDA(cudaGetLastError());
+	int cur = 1;
+	for (int b = 1; b < c.max_bounce; ++b) {
+		// extend: queue length is read on the device
+		ADYPT_TRY(launch_trace(s, t->d_rays[cur], total, t->d_hit_tri, nullptr, t->d_hit_uv, nullptr, t->stream, t->d_counts + b));
+		B.in_rays = t->d_rays[cur];
+		B.in_count = t->d_counts + b;
+		B.out_rays = t->d_rays[cur ^ 1];
+		B.out_count = t->d_counts + b + 1;
+		k_shade_bounce<<<grid_for(total, 256, s->sm_count), 256, 0, t->stream>>>(B, A, b, c.ray_tmin);
+		count_launch();
+		ADYPT_CUDA(cudaGetLastError());
+		cur ^= 1;
+	}
+	const int g = grid_for(t->npix, 256, s->sm_count);
+	if (sum_mode) k_accumulate_sum<<<g, 256, 0, t->stream>>>(t->d_ret, t->d_sum, t->npix, n, c.clamp);
+	else k_accumulate_mean<<<g, 256, 0, t->stream>>>(t->d_ret, t->d_result, t->npix, first, n, c.clamp);
+	count_launch();
+	ADYPT_CUDA(cudaGetLastError());
+	return ADYPT_OK;
+}
+
+// split [first, first+n) into batches that do not cross tmpLifetime blocks nor exceed S samples
+int run_range(adypt_tracer *t, int first, int n, bool sum_mode)
+{
+	ADYPT_TRY(alloc_wavefront(t));
+	const int L = t->cfg.tmp_lifetime;
+	int s = first;
+	const int end = first + n;
+	while (s < end) {
+		const int block_end = (s / L + 1) * L;
+		const int m = std::min(std::min(end, block_end) - s, t->batch_samples);
+		ADYPT_TRY(run_batch(t, s, m, sum_mode));
+		s += m;
+	}
+	return ADYPT_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int adypt_tracer_create(adypt_scene *scene, const adypt_pt_config *config, int32_t width, int32_t height, uint64_t bias_seed,
+                        adypt_tracer **out)
+{
+	if (!scene || !config || !out) return fail(ADYPT_EINVAL, "scene/config/out is NULL");
+	*out = nullptr;
+	if (width <= 0 || height <= 0 || (uint64_t)width * (uint64_t)height >= (1ull << 31)) return fail(ADYPT_EINVAL, "bad image size");
+	if (!scene->d_tris || !scene->d_mats) return fail(ADYPT_EINVAL, "scene has no triangles/materials: traversal-only scenes cannot shade");
+	ADYPT_TRY(check_config(config));
+	DeviceGuard g(scene->device);
+	adypt_tracer *t = new adypt_tracer;
+	t->scene = scene;
+	t->cfg = *config;
+	t->width = width;
+	t->height = height;
+	t->npix = (unsigned)width * (unsigned)height;
+	cudaError_t e = cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking);
+	const size_t np = t->npix;
+	if (e == cudaSuccess) e = cudaMalloc((void **)&t->d_result, np * 16u);
+	if (e == cudaSuccess) e = cudaMalloc((void **)&t->d_sum, np * 16u);
+	if (e == cudaSuccess) e = cudaMalloc((void **)&t->d_prim_tri, np * 4u);
+	if (e == cudaSuccess) e = cudaMalloc((void **)&t->d_prim_uv, np * 8u);
+	if (e == cudaSuccess) e = cudaMalloc((void **)&t->d_bias, np * 2u);
+	if (e == cudaSuccess) e = cudaMalloc((void **)&t->d_dirs, (size_t)sobol_max_dim() * 32u * 4u);
+	if (e == cudaSuccess) e = cudaMalloc((void **)&t->d_sobol, (size_t)sobol_max_dim() * 4u * 4096u);
+	if (e == cudaSuccess) e = cudaMalloc((void **)&t->d_counts, kCountSlots * sizeof(unsigned long long));
+	if (e == cudaSuccess) e = cudaMemset(t->d_result, 0, np * 16u);
+	if (e == cudaSuccess) e = cudaMemset(t->d_sum, 0, np * 16u);
+	if (e == cudaSuccess) e = cudaMemset(t->d_counts, 0, kCountSlots * sizeof(unsigned long long));
+	if (e == cudaSuccess) e = cudaMemcpy(t->d_dirs, sobol_directions(), (size_t)sobol_max_dim() * 32u * 4u, cudaMemcpyHostToDevice);
+	if (e == cudaSuccess) {
+		t->h_bias.resize(np * 2u);
+		fill_bias(bias_seed, np * 2u, t->h_bias.data());
+		e = cudaMemcpy(t->d_bias, t->h_bias.data(), np * 2u, cudaMemcpyHostToDevice);
+	}
+	if (e != cudaSuccess) {
+		free_tracer(t);
+		return fail(e == cudaErrorMemoryAllocation ? ADYPT_ENOMEM : ADYPT_ECUDA, std::string("tracer allocation: ") + cudaGetErrorString(e));
+	}
+	t->cam.tmin = config->ray_tmin;
+	const float ident[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+	memcpy(t->cam.inv_proj, ident, 64);
+	memcpy(t->cam.inv_view, ident, 64);
+	t->launches_at_create = g_launches.load();
+	*out = t;
+	return ADYPT_OK;
+}
+
+int adypt_tracer_destroy(adypt_tracer *t)
+{
+	if (t) free_tracer(t);
+	return ADYPT_OK;
+}
+
+int adypt_tracer_set_config(adypt_tracer *t, const adypt_pt_config *config)
+{
+	if (!t || !config) return fail(ADYPT_EINVAL, "tracer/config is NULL");
+	ADYPT_TRY(check_config(config));
+	t->cfg = *config;
+	t->cam.tmin = config->ray_tmin; // update_config_args, OglPathTracer.cpp:216
+	t->prim_valid = false;
+	return ADYPT_OK;
+}
+
+int adypt_tracer_set_bias(adypt_tracer *t, const uint8_t *rg8)
+{
+	if (!t || !rg8) return fail(ADYPT_EINVAL, "tracer/rg8 is NULL");
+	DeviceGuard g(t->scene->device);
+	memcpy(t->h_bias.data(), rg8, t->h_bias.size());
+	ADYPT_CUDA(cudaStreamSynchronize(t->stream));
+	ADYPT_CUDA(cudaMemcpy(t->d_bias, rg8, t->h_bias.size(), cudaMemcpyHostToDevice));
+	return ADYPT_OK;
+}
+
+int adypt_tracer_get_bias(adypt_tracer *t, uint8_t *rg8)
+{
+	if (!t || !rg8) return fail(ADYPT_EINVAL, "tracer/rg8 is NULL");
+	memcpy(rg8, t->h_bias.data(), t->h_bias.size());
+	return ADYPT_OK;
+}
+
+int adypt_tracer_set_camera(adypt_tracer *t, const float projection[16], const float view[16], const float position[3])
+{
+	if (!t || !projection || !view || !position) return fail(ADYPT_EINVAL, "NULL argument");
+	t->cam.origin[0] = position[0]; t->cam.origin[1] = position[1]; t->cam.origin[2] = position[2];
+	mat4_inverse(projection, t->cam.inv_proj); // OglPathTracer.cpp:30-31
+	mat4_inverse(view, t->cam.inv_view);
+	t->prim_valid = false;
+	return ADYPT_OK;
+}
+
+int adypt_tracer_primary(adypt_tracer *t, int32_t viewer_type)
+{
+	if (!t) return fail(ADYPT_EINVAL, "tracer is NULL");
+	DeviceGuard g(t->scene->device);
+	ADYPT_TRY(alloc_wavefront(t));
+	t->spp = 0; // OglPathTracer.cpp:55
+	t->cam.tmin = t->cfg.ray_tmin;
+	adypt_scene *s = t->scene;
+	k_generate<<<grid_for(t->npix, 256, s->sm_count), 256, 0, t->stream>>>(t->cam, t->width, t->height, 0.0f, 0.0f, t->d_rays[0]);
+	count_launch();
+	ADYPT_TRY(launch_trace(s, t->d_rays[0], t->npix, t->d_hit_tri, nullptr, t->d_hit_uv, nullptr, t->stream));
+	k_view<<<grid_for(t->npix, 256, s->sm_count), 256, 0, t->stream>>>(s->d_tris, s->d_mats, t->d_hit_tri, t->d_hit_uv, viewer_type, t->npix, t->d_result);
+	count_launch();
+	ADYPT_CUDA(cudaGetLastError());
+	t->host_segments += t->npix;
+	t->prim_valid = false;
+	return ADYPT_OK;
+}
+
+int adypt_tracer_sample(adypt_tracer *t, int32_t n_spp)
+{
+	if (!t) return fail(ADYPT_EINVAL, "tracer is NULL");
+	if (n_spp <= 0) return ADYPT_OK;
+	DeviceGuard g(t->scene->device);
+	if (t->spp == 0) { // OglPathTracer.cpp:39-46
+		t->cam.tmin = t->cfg.ray_tmin;
+		ADYPT_CUDA(cudaMemsetAsync(t->d_result, 0, (size_t)t->npix * 16u, t->stream));
+		t->prim_valid = false;
+	}
+	ADYPT_TRY(run_range(t, t->spp, n_spp, false));
+	t->spp += n_spp;
+	return ADYPT_OK;
+}
+
+int adypt_tracer_accumulate(adypt_tracer *t, int32_t first_spp, int32_t n_spp)
+{
+	if (!t) return fail(ADYPT_EINVAL, "tracer is NULL");
+	if (n_spp <= 0) return ADYPT_OK;
+	if (first_spp < 0 || first_spp % t->cfg.tmp_lifetime != 0) return fail(ADYPT_EINVAL, "first_spp must be a non-negative multiple of tmpLifetime");
+	DeviceGuard g(t->scene->device);
+	t->cam.tmin = t->cfg.ray_tmin;
+	t->prim_valid = false;
+	return run_range(t, first_spp, n_spp, true);
+}
+
+int adypt_tracer_sum_buffer(adypt_tracer *t, float **device_ptr, uint64_t *n_floats)
+{
+	if (!t || !device_ptr) return fail(ADYPT_EINVAL, "NULL argument");
+	*device_ptr = (float *)t->d_sum;
+	if (n_floats) *n_floats = (uint64_t)t->npix * 4u;
+	return ADYPT_OK;
+}
+
+int adypt_tracer_result_buffer(adypt_tracer *t, float **device_ptr, uint64_t *n_floats)
+{
+	if (!t || !device_ptr) return fail(ADYPT_EINVAL, "NULL argument");
+	*device_ptr = (float *)t->d_result;
+	if (n_floats) *n_floats = (uint64_t)t->npix * 4u;
+	return ADYPT_OK;
+}
+
+int adypt_tracer_clear_sum(adypt_tracer *t)
+{
+	if (!t) return fail(ADYPT_EINVAL, "tracer is NULL");
+	DeviceGuard g(t->scene->device);
+	ADYPT_CUDA(cudaMemsetAsync(t->d_sum, 0, (size_t)t->npix * 16u, t->stream));
+	return ADYPT_OK;
+}
+
+int adypt_tracer_resolve_sum(adypt_tracer *t)
+{
+	if (!t) return fail(ADYPT_EINVAL, "tracer is NULL");
+	DeviceGuard g(t->scene->device);
+	k_resolve_sum<<<grid_for(t->npix, 256, t->scene->sm_count), 256, 0, t->stream>>>(t->d_sum, t->d_result, t->npix);
+	count_launch();
+	ADYPT_CUDA(cudaGetLastError());
+	return ADYPT_OK;
+}
+
+int adypt_tracer_spp(adypt_tracer *t, int32_t *spp)
+{
+	if (!t || !spp) return fail(ADYPT_EINVAL, "NULL argument");
+	*spp = t->spp;
+	return ADYPT_OK;
+}
+
+int adypt_tracer_sync(adypt_tracer *t)
+{
+	if (!t) return fail(ADYPT_EINVAL, "tracer is NULL");
+	DeviceGuard g(t->scene->device);
+	ADYPT_CUDA(cudaStreamSynchronize(t->stream));
+	return ADYPT_OK;
+}
+
+int adypt_tracer_read(adypt_tracer *t, float *out, int32_t channels)
+{
+	if (!t || !out) return fail(ADYPT_EINVAL, "NULL argument");
+	if (channels != 3 && channels != 4) return fail(ADYPT_EINVAL, "channels must be 3 or 4");
+	DeviceGuard g(t->scene->device);
+	if (channels == 4) {
+		ADYPT_CUDA(cudaMemcpyAsync(out, t->d_result, (size_t)t->npix * 16u, cudaMemcpyDeviceToHost, t->stream));
+		ADYPT_CUDA(cudaStreamSynchronize(t->stream));
+		return ADYPT_OK;
+	}
+	std::vector<float> tmp((size_t)t->npix * 4u);
+	ADYPT_CUDA(cudaMemcpyAsync(tmp.data(), t->d_result, (size_t)t->npix * 16u, cudaMemcpyDeviceToHost, t->stream));
+	ADYPT_CUDA(cudaStreamSynchronize(t->stream));
+	for (size_t i = 0; i < t->npix; ++i) {
+		out[3 * i] = tmp[4 * i];
+		out[3 * i + 1] = tmp[4 * i + 1];
+		out[3 * i + 2] = tmp[4 * i + 2];
+	}
+	return ADYPT_OK;
+}
+
+int adypt_tracer_save_exr(adypt_tracer *t, const char *filename, int32_t save_as_fp16)
+{
+	if (!t || !filename) return fail(ADYPT_EINVAL, "NULL argument");
+	std::vector<float> rgb((size_t)t->npix * 3u);
+	ADYPT_TRY(adypt_tracer_read(t, rgb.data(), 3));
+	const int rc = adypt_write_exr(filename, rgb.data(), t->width, t->height, save_as_fp16);
+	if (rc != ADYPT_OK) return fail(rc, std::string("cannot write ") + filename);
+	return ADYPT_OK;
+}
+
+int adypt_tracer_primary_rays(adypt_tracer *t, float *rays, int memspace)
+{
+	if (!t || !rays) return fail(ADYPT_EINVAL, "NULL argument");
+	DeviceGuard g(t->scene->device);
+	t->cam.tmin = t->cfg.ray_tmin;
+	float4 *dst = (float4 *)rays;
+	if (memspace == ADYPT_MEM_HOST) {
+		ADYPT_TRY(alloc_wavefront(t));
+		dst = t->d_rays[0];
+	} else if (memspace != ADYPT_MEM_DEVICE)
+		return fail(ADYPT_EINVAL, "bad memspace");
+	k_generate<<<grid_for(t->npix, 256, t->scene->sm_count), 256, 0, t->stream>>>(t->cam, t->width, t->height, 0.0f, 0.0f, dst);
+	count_launch();
+	ADYPT_CUDA(cudaGetLastError());
+	if (memspace == ADYPT_MEM_HOST) ADYPT_CUDA(cudaMemcpyAsync(rays, dst, (size_t)t->npix * 32u, cudaMemcpyDeviceToHost, t->stream));
+	ADYPT_CUDA(cudaStreamSynchronize(t->stream));
+	return ADYPT_OK;
+}
+
+int adypt_tracer_stats(adypt_tracer *t, uint64_t *segments, uint64_t *launches)
+{
+	if (!t) return fail(ADYPT_EINVAL, "tracer is NULL");
+	DeviceGuard g(t->scene->device);
+	unsigned long long dev = 0;
+	ADYPT_CUDA(cudaStreamSynchronize(t->stream));
+	ADYPT_CUDA(cudaMemcpy(&dev, t->d_counts + (kCountSlots - 1), sizeof(dev), cudaMemcpyDeviceToHost));
+	if (segments) *segments = t->host_segments + dev;
+	if (launches) *launches = g_launches.load() - t->launches_at_create;
+	return ADYPT_OK;
+}
+
+} // extern "C"

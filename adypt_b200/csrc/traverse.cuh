@@ -1,0 +1,246 @@
+// CWBVH traversal for sm_100a: closest-hit and any-hit, one ray per lane, persistent warps.
+//
+// Semantics are those of BVHIntersection in shaders/traversal.glsl:14-255 (closest) and :257-494 (any),
+// ray by ray: children are visited in descending hit-bit order (findMSB, :52), triangles in ascending
+// order (findLSB, :215), deferred groups LIFO (:59-60, :245-250), strict t comparisons (:235). Lanes never
+// share a ray, so the per-ray visit order -- and with it every tie-break -- is the reference's. The warp
+// cooperates on SCHEDULING only: lanes whose ray has finished are refilled from a warp-local pool of ray
+// indices (ballot + popc ranking), and the pool is topped up with one atomicAdd per CHUNK rays.
+//
+// FP policy: IEEE fp32, round-to-nearest, no implicit contraction (explicit __f*_rn
+// intrinsics), with fused multiply-add exactly where the oracle has fmaf(): the 48 slab evaluations per
+// node and the Woop dot chains.
+//
+// Memory: node = 5 x LDG.128 and Woop = 3 x LDG.128 through the read-only path (L1 + L2; C1/C2 BVHs are
+// L2-resident on B200), traversal stack = SSTACK entries per lane in shared memory ([entry][thread], so a
+// warp's 8-byte accesses are conflict-free) with a local-memory overflow that real scenes never reach.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "layouts.h"
+
+namespace adypt {
+
+struct TraceParams {
+	const uint4 *__restrict__ nodes;        // 5 per node
+	const float4 *__restrict__ woop;        // 3 per leaf reference
+	const int32_t *__restrict__ tri_indices;
+	const float4 *__restrict__ rays;        // 2 per ray
+	unsigned long long n;
+	const unsigned long long *n_ptr;        // when non-null the ray count is read from device memory (wavefront queues)
+	int32_t *__restrict__ out_tri;          // closest
+	float *__restrict__ out_t;              // closest, nullable
+	float2 *__restrict__ out_uv;            // closest, nullable
+	uint8_t *__restrict__ out_occ;          // any
+	unsigned long long *counter;            // zeroed before launch
+	int refill_threshold;                   // leave the traversal loop when fewer lanes than this are busy
+};
+
+constexpr int kTraceBlock = 128;      // threads per CTA
+constexpr int kSmemStack = 8;         // stack entries per lane kept in shared memory
+constexpr int kLocalStack = 56;       // overflow entries (local memory); total 64 like the oracle
+constexpr unsigned kPoolChunk = 256;  // ray indices a warp takes per atomicAdd
+constexpr unsigned kFullMask = 0xffffffffu;
+
+__device__ __forceinline__ float dot3_fma(float ax, float ay, float az, const float4 m)
+{
+	return __fmaf_rn(az, m.z, __fmaf_rn(ay, m.y, __fmul_rn(ax, m.x)));
+}
+
+// exact uint8 -> float: splice the byte into the mantissa of 2^23 and subtract 2^23 (one PRMT + one FADD,
+// no conversion-pipe instruction); identical to (float)byte
+__device__ __forceinline__ float byte_to_float(uint32_t word, uint32_t selector)
+{
+	return __fsub_rn(__uint_as_float(__byte_perm(word, 0x4B000000u, selector)), 8388608.0f);
+}
+
+// one group of four children (one 32-bit lane of each quantised plane), traversal.glsl:86-143 / :145-202
+__device__ __forceinline__ uint32_t test_children4(uint32_t meta4, uint32_t octinv4, uint32_t s_lox, uint32_t s_loy,
+                                                   uint32_t s_loz, uint32_t s_hix, uint32_t s_hiy, uint32_t s_hiz,
+                                                   float aix, float aiy, float aiz, float aox, float aoy, float aoz,
+                                                   float tmin, float hit_t)
+{
+	const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+	const uint32_t bit_index4 = (meta4 ^ (octinv4 & ((is_inner4 >> 4) * 0xffu))) & 0x1f1f1f1fu;
+	const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+	uint32_t hitmask = 0;
+#pragma unroll
+	for (int k = 0; k < 4; ++k) {
+		const uint32_t sel = 0x7540u | (uint32_t)k;
+		const float txmin = __fmaf_rn(byte_to_float(s_lox, sel), aix, aox);
+		const float tymin = __fmaf_rn(byte_to_float(s_loy, sel), aiy, aoy);
+		const float tzmin = __fmaf_rn(byte_to_float(s_loz, sel), aiz, aoz);
+		const float txmax = __fmaf_rn(byte_to_float(s_hix, sel), aix, aox);
+		const float tymax = __fmaf_rn(byte_to_float(s_hiy, sel), aiy, aoy);
+		const float tzmax = __fmaf_rn(byte_to_float(s_hiz, sel), aiz, aoz);
+		const float ctmin = fmaxf(fmaxf(txmin, tymin), fmaxf(tzmin, tmin));
+		const float ctmax = fminf(fminf(txmax, tymax), fminf(tzmax, hit_t));
+		if (ctmin <= ctmax) {
+			const uint32_t bits = (child_bits4 >> (8 * k)) & 0xffu;
+			const uint32_t idx = (bit_index4 >> (8 * k)) & 0xffu;
+			hitmask |= bits << idx;
+		}
+	}
+	return hitmask;
+}
+
+template <bool ANY>
+__global__ void __launch_bounds__(kTraceBlock, 6) trace_kernel(const TraceParams p)
+{
+	__shared__ uint2 s_stack[kSmemStack][kTraceBlock];
+	uint2 l_stack[kLocalStack];
+
+	const unsigned tid = threadIdx.x;
+	const unsigned lane = tid & 31u;
+	const unsigned lt_mask = (1u << lane) - 1u;
+	const unsigned long long n_rays = p.n_ptr ? *p.n_ptr : p.n;
+
+	// warp-uniform pool of ray indices
+	unsigned long long pool_next = 0, pool_end = 0;
+	bool exhausted = false;
+
+	// per-lane ray state
+	bool active = false;
+	unsigned long long ray_idx = 0;
+	float ox = 0, oy = 0, oz = 0, tmin = 0, dx = 0, dy = 0, dz = 0, idx = 0, idy = 0, idz = 0;
+	uint32_t octinv = 0;
+	float hit_t = 0, hit_u = 0, hit_v = 0;
+	int32_t hit_idx = -1;
+	uint2 ng = make_uint2(0, 0), tg = make_uint2(0, 0);
+	int sp = 0;
+
+	for (;;) {
+		// ---------------------------------------------------------------- refill idle lanes
+		unsigned idle = __ballot_sync(kFullMask, !active);
+		while (idle != 0 && !exhausted) {
+			if (pool_next >= pool_end) {
+				unsigned long long b = 0;
+				if (lane == 0) b = atomicAdd(p.counter, (unsigned long long)kPoolChunk);
+				b = __shfl_sync(kFullMask, b, 0);
+				if (b >= n_rays) { exhausted = true; break; }
+				pool_next = b;
+				pool_end = (b + kPoolChunk < n_rays) ? b + kPoolChunk : n_rays;
+			}
+			const unsigned long long cand = pool_next + __popc(idle & lt_mask);
+			const bool take = !active && cand < pool_end;
+			if (take) {
+				// ray setup, traversal.glsl:16-35
+				ray_idx = cand;
+				const float4 r0 = __ldg(p.rays + 2 * cand), r1 = __ldg(p.rays + 2 * cand + 1);
+				ox = r0.x; oy = r0.y; oz = r0.z; tmin = r0.w;
+				const float ooeps = 5.42101086242752217e-20f; // exp2(-64)
+				dx = fabsf(r1.x) > ooeps ? r1.x : (r1.x >= 0.0f ? ooeps : -ooeps);
+				dy = fabsf(r1.y) > ooeps ? r1.y : (r1.y >= 0.0f ? ooeps : -ooeps);
+				dz = fabsf(r1.z) > ooeps ? r1.z : (r1.z >= 0.0f ? ooeps : -ooeps);
+				const float len2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+				const float inv = __fdiv_rn(1.0f, __fsqrt_rn(len2));
+				dx = __fmul_rn(dx, inv); dy = __fmul_rn(dy, inv); dz = __fmul_rn(dz, inv);
+				idx = __fdiv_rn(1.0f, dx); idy = __fdiv_rn(1.0f, dy); idz = __fdiv_rn(1.0f, dz);
+				octinv = 7u - ((dx < 0.0f ? 1u : 0u) | (dy < 0.0f ? 2u : 0u) | (dz < 0.0f ? 4u : 0u));
+				hit_t = 1e9f; hit_idx = -1; hit_u = 0.0f; hit_v = 0.0f;
+				ng = make_uint2(0u, 0x80000000u);
+				tg = make_uint2(0u, 0u);
+				sp = 0;
+				active = true;
+			}
+			const unsigned took = __ballot_sync(kFullMask, take);
+			pool_next += __popc(took);
+			idle &= ~took;
+		}
+		if (!__any_sync(kFullMask, active)) break;
+
+		// ---------------------------------------------------------------- traverse
+		unsigned busy;
+		do {
+			if (active) {
+				if (ng.y > 0x00ffffffu) {
+					// n <- closest child of G (:50-67)
+					const uint32_t imask = ng.y;
+					const uint32_t bit = 31u - (uint32_t)__clz((int)ng.y);
+					const uint32_t base = ng.x;
+					ng.y &= ~(1u << bit);
+					if (ng.y > 0x00ffffffu) {
+						if (sp < kSmemStack) s_stack[sp][tid] = ng;
+						else if (sp < kSmemStack + kLocalStack) l_stack[sp - kSmemStack] = ng;
+						++sp;
+					}
+					const uint32_t slot = (bit - 24u) ^ octinv;
+					const uint32_t rel = (uint32_t)__popc(imask & ~(0xffffffffu << slot));
+					const uint4 *np = p.nodes + (size_t)(base + rel) * 5u;
+					const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+
+					const float aix = __fmul_rn(__uint_as_float((n0.w & 0xffu) << 23), idx);
+					const float aiy = __fmul_rn(__uint_as_float(((n0.w >> 8) & 0xffu) << 23), idy);
+					const float aiz = __fmul_rn(__uint_as_float(((n0.w >> 16) & 0xffu) << 23), idz);
+					const float aox = __fmul_rn(__fsub_rn(__uint_as_float(n0.x), ox), idx);
+					const float aoy = __fmul_rn(__fsub_rn(__uint_as_float(n0.y), oy), idy);
+					const float aoz = __fmul_rn(__fsub_rn(__uint_as_float(n0.z), oz), idz);
+
+					ng.x = n1.x;
+					tg.x = n1.y;
+					const uint32_t octinv4 = octinv * 0x01010101u;
+					const bool nx = idx < 0.0f, ny = idy < 0.0f, nz = idz < 0.0f;
+					// planes: n2 = (lox.lo, lox.hi, loy.lo, loy.hi) n3 = (loz.lo, loz.hi, hix.lo, hix.hi)
+					//         n4 = (hiy.lo, hiy.hi, hiz.lo, hiz.hi)
+					uint32_t hitmask = test_children4(n1.z, octinv4,
+						nx ? n3.z : n2.x, ny ? n4.x : n2.z, nz ? n4.z : n3.x,
+						nx ? n2.x : n3.z, ny ? n2.z : n4.x, nz ? n3.x : n4.z,
+						aix, aiy, aiz, aox, aoy, aoz, tmin, hit_t);
+					hitmask |= test_children4(n1.w, octinv4,
+						nx ? n3.w : n2.y, ny ? n4.y : n2.w, nz ? n4.w : n3.y,
+						nx ? n2.y : n3.w, ny ? n2.w : n4.y, nz ? n3.y : n4.w,
+						aix, aiy, aiz, aox, aoy, aoz, tmin, hit_t);
+					ng.y = (hitmask & 0xff000000u) | (n0.w >> 24);
+					tg.y = hitmask & 0x00ffffffu;
+				} else { // :207-211
+					tg = ng;
+					ng = make_uint2(0u, 0u);
+				}
+
+				bool finished = false;
+				while (tg.y != 0u) { // :213-243
+					const uint32_t tr = tg.x + (uint32_t)(__ffs((int)tg.y) - 1);
+					tg.y &= tg.y - 1u;
+					const float4 *wp = p.woop + (size_t)tr * 3u;
+					const float4 m0 = __ldg(wp), m1 = __ldg(wp + 1), m2 = __ldg(wp + 2);
+					const float toz = __fsub_rn(m0.w, dot3_fma(ox, oy, oz, m0));
+					const float tidz = __frcp_rn(dot3_fma(dx, dy, dz, m0));
+					const float tt = __fmul_rn(toz, tidz);
+					const float tox = __fadd_rn(m1.w, dot3_fma(ox, oy, oz, m1));
+					const float tu = __fmaf_rn(tt, dot3_fma(dx, dy, dz, m1), tox);
+					const float toy = __fadd_rn(m2.w, dot3_fma(ox, oy, oz, m2));
+					const float tv = __fmaf_rn(tt, dot3_fma(dx, dy, dz, m2), toy);
+					if (tt > tmin && tt < hit_t && tu >= 0.0f && tu <= 1.0f && tv >= 0.0f && __fadd_rn(tu, tv) <= 1.0f) {
+						hit_t = tt;
+						if (ANY) { finished = true; break; } // :480-483
+						hit_u = tu;
+						hit_v = tv;
+						hit_idx = (int32_t)tr;
+					}
+				}
+
+				if (!finished && ng.y <= 0x00ffffffu) { // :245-250
+					if (sp == 0) finished = true;
+					else {
+						--sp;
+						ng = (sp < kSmemStack) ? s_stack[sp][tid] : l_stack[(sp - kSmemStack) < kLocalStack ? (sp - kSmemStack) : (kLocalStack - 1)];
+					}
+				}
+
+				if (finished) {
+					active = false;
+					if (ANY) {
+						p.out_occ[ray_idx] = (hit_t < 1e9f) ? 1 : 0;
+					} else {
+						p.out_tri[ray_idx] = hit_idx >= 0 ? __ldg(p.tri_indices + hit_idx) : -1; // :253-254
+						if (p.out_t) p.out_t[ray_idx] = hit_t;
+						if (p.out_uv) p.out_uv[ray_idx] = make_float2(hit_u, hit_v);
+					}
+				}
+			}
+			busy = __ballot_sync(kFullMask, active);
+		} while (busy != 0u && (exhausted || __popc(busy) >= p.refill_threshold));
+	}
+}
+
+} // namespace adypt

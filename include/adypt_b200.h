@@ -1,0 +1,178 @@
+/*
+ * adypt_b200 -- C-ABI of the B200-native ray-traversal / path-tracing core for AdamYuan/Adypt.
+ *
+ * This library replaces the reference's OpenGL 4.5 compute path (src/Tracer/OglScene.*,
+ * src/Tracer/OglPathTracer.*, shaders/{traversal,primaryray,pathtracer}.glsl) and nothing else.
+ * Adypt has no FFI of its own; the seam is the C++ class surface Instance uses. Each
+ * entry point below names the reference member it stands in for (paths relative to the reference
+ * root). INTEGRATION.md shows the ~60-line C++ shim that gives these the reference's class names.
+ *
+ * Conventions: every function returns 0 on success or a negative ADYPT_E* code, and
+ * adypt_last_error() returns a thread-local message for the last failure on the calling thread.
+ * Handles are opaque; one host thread per handle at a time (the reference is single-threaded on its
+ * GL-context thread). The callee copies every host input before returning (the reference's
+ * Scene/WideBVH are stack locals destroyed right after OglScene::Initialize, Instance.cpp:12-33).
+ * There is no CPU fallback: without a CUDA device every compute entry point fails with ADYPT_ENODEV.
+ *
+ * Data layouts are the reference's GPU ABI, uploaded unchanged:
+ *   node      80 B  WideBVHNode            src/BVH/WideBVH.hpp:13-26  == struct Node, traversal.glsl:1-5
+ *   woop      48 B  3 x vec4 per leaf ref  src/Tracer/OglScene.cpp:93-116 == struct Woop, traversal.glsl:6
+ *   triangle 100 B  Triangle               src/Util/Shape.hpp:70-88   == pathtracer.glsl:2-8
+ *   material  64 B  GPUMaterial            src/Tracer/OglScene.hpp:19-28 == pathtracer.glsl:9-18
+ *   ray       32 B  ox,oy,oz,tmin,dx,dy,dz,pad   (vec4 origin_tmin + vec3 dir of BVHIntersection)
+ */
+#ifndef ADYPT_B200_H
+#define ADYPT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADYPT_B200_VERSION 100
+
+enum {
+	ADYPT_OK = 0,
+	ADYPT_EINVAL = -1,  /* bad argument */
+	ADYPT_ENODEV = -2,  /* no usable CUDA device / device index out of range */
+	ADYPT_ECUDA = -3,   /* CUDA runtime error (message has the cudaError string) */
+	ADYPT_ENOMEM = -4,  /* allocation failed */
+	ADYPT_EIO = -5,     /* file could not be written */
+	ADYPT_ERANGE = -6   /* value outside what the implementation supports (e.g. Sobol dimensions) */
+};
+
+/* where the buffers of a batch call live */
+enum { ADYPT_MEM_HOST = 0, ADYPT_MEM_DEVICE = 1 };
+
+/* OglPathTracer::ViewerTypes (src/Tracer/OglPathTracer.hpp:20) */
+enum { ADYPT_VIEW_DIFFUSE = 0, ADYPT_VIEW_SPECULAR = 1, ADYPT_VIEW_EMISSIVE = 2, ADYPT_VIEW_RADIANCE = 3,
+       ADYPT_VIEW_NORMAL = 4, ADYPT_VIEW_POSITION = 5 };
+
+typedef struct adypt_scene adypt_scene;
+typedef struct adypt_tracer adypt_tracer;
+
+const char *adypt_last_error(void);
+int adypt_version(void);
+int adypt_device_count(int *count);
+
+/* ------------------------------------------------------------------------------------------------
+ * Scene: replaces OglScene::Initialize(const Scene&, const WideBVH&) (src/Tracer/OglScene.hpp:43,
+ * OglScene.cpp:46-49,118-141), called from Instance.cpp:33.
+ * nodes/tri_indices come from WideBVH::GetNodes()/GetTriIndices() (WideBVH.hpp:39-40), triangles from
+ * Scene::GetTriangles() (Scene.hpp:22), materials as OglScene::init_materials builds them
+ * (OglScene.cpp:51-91). woop may be NULL: the Woop rows are then built on the GPU from `triangles`
+ * exactly as OglScene::init_triangles does (OglScene.cpp:93-116, glm::inverse arithmetic order).
+ * triangles/materials may be NULL (n = 0) for a traversal-only scene (adypt_trace_* still work). */
+typedef struct {
+	int32_t device;              /* CUDA device ordinal */
+	const void *nodes;           /* n_nodes * 80 B */
+	uint32_t n_nodes;
+	const int32_t *tri_indices;  /* n_refs, leaf order -> scene triangle id */
+	uint32_t n_refs;
+	const float *woop;           /* n_refs * 12 floats, or NULL */
+	const void *triangles;       /* n_tris * 100 B, or NULL */
+	uint32_t n_tris;
+	const void *materials;       /* n_mats * 64 B, or NULL */
+	uint32_t n_mats;
+} adypt_scene_desc;
+
+int adypt_scene_create(const adypt_scene_desc *desc, adypt_scene **out);
+int adypt_scene_destroy(adypt_scene *scene);
+/* copies the device Woop array (n_refs * 12 floats) back to the host, for parity checks */
+int adypt_scene_read_woop(adypt_scene *scene, float *out);
+/* bytes resident on the device for this scene */
+int adypt_scene_device_bytes(adypt_scene *scene, uint64_t *bytes);
+
+/* ------------------------------------------------------------------------------------------------
+ * Batch traversal: replaces void BVHIntersection(vec4 origin_tmin, vec3 dir, inout int idx, inout vec2 uv)
+ * (shaders/traversal.glsl:14-255) and bool BVHIntersection(vec4, vec3) (traversal.glsl:257-494) as
+ * array-in / array-out calls. rays: n * 8 floats. tri: scene triangle id or -1. t: hit distance along
+ * the NORMALISED direction (1e9 on a miss; the GLSL keeps it in a local), may be NULL. uv: n * 2
+ * floats, left 0 on a miss, may be NULL. memspace says whether ALL array pointers of the call are host
+ * or device pointers (device pointers must belong to the scene's device). stream: a cudaStream_t
+ * (NULL = default stream). Device calls are asynchronous on `stream`; host calls return when the
+ * results are in the output arrays. */
+int adypt_trace_closest(adypt_scene *scene, const float *rays, uint64_t n, int32_t *tri, float *t, float *uv,
+                        int memspace, void *stream);
+int adypt_trace_any(adypt_scene *scene, const float *rays, uint64_t n, uint8_t *occluded, int memspace, void *stream);
+/* number of kernel launches adypt_* calls have issued so far on this scene's device (bench accounting) */
+int adypt_launch_count(uint64_t *launches);
+/* tuning knobs of the persistent traversal kernel (0 = default): CTAs per SM and the refill threshold */
+int adypt_trace_configure(adypt_scene *scene, int ctas_per_sm, int refill_threshold);
+
+/* ------------------------------------------------------------------------------------------------
+ * Tracer: replaces OglPathTracer (src/Tracer/OglPathTracer.hpp:66-82).
+ * adypt_pt_config has the memory layout of InstanceConfig::PT (src/InstanceConfig.hpp:22-28), so a
+ * `const InstanceConfig::PT *` can be passed as is. It is COPIED at create/set_config time; the reference
+ * borrows the pointer and re-reads it whenever spp == 0 (OglPathTracer.cpp:39-41, 214-225) -- the C++
+ * shim in INTEGRATION.md keeps that behaviour by calling adypt_tracer_set_config before the first sample. */
+typedef struct {
+	int32_t invocation_size; /* GL work-group edge; accepted and ignored */
+	int32_t stack_size;      /* reference: unchecked GLSL array size; here: must be >= scene depth or traversal spills to a slower overflow stack, never out of bounds */
+	int32_t max_bounce;      /* path segments including the primary one */
+	int32_t subpixel;
+	int32_t tmp_lifetime;
+	float ray_tmin;
+	float clamp;
+	float sun[3];
+} adypt_pt_config;
+
+/* OglPathTracer::Initialize(const InstanceConfig::PT*, const OglScene&, int w, int h) (OglPathTracer.cpp:11-25).
+ * bias_seed seeds the per-pixel Cranley-Patterson bias image the reference fills from std::random_device
+ * (OglPathTracer.cpp:154-162); use adypt_tracer_set_bias to supply explicit bytes instead. */
+int adypt_tracer_create(adypt_scene *scene, const adypt_pt_config *config, int32_t width, int32_t height,
+                        uint64_t bias_seed, adypt_tracer **out);
+int adypt_tracer_destroy(adypt_tracer *tracer);
+int adypt_tracer_set_config(adypt_tracer *tracer, const adypt_pt_config *config);
+/* width*height*2 bytes, the RG8 texels of uSobolBiasImg in row-major pixel order */
+int adypt_tracer_set_bias(adypt_tracer *tracer, const uint8_t *rg8);
+int adypt_tracer_get_bias(adypt_tracer *tracer, uint8_t *rg8);
+
+/* OglPathTracer::SetCamera(const mat4& projection, const mat4& view, const vec3& position)
+ * (OglPathTracer.cpp:27-32): column-major float[16]; the inverses are computed inside with glm::inverse's
+ * arithmetic order. */
+int adypt_tracer_set_camera(adypt_tracer *tracer, const float projection[16], const float view[16], const float position[3]);
+/* Camera::GetProjection / GetView (src/Tracer/Camera.cpp:13-23) for callers without glm */
+int adypt_camera_matrices(float fov_deg, float yaw_deg, float pitch_deg, int32_t width, int32_t height,
+                          float projection[16], float view[16]);
+
+/* OglPathTracer::Trace(false) (OglPathTracer.cpp:52-60): resets spp to 0 and renders the AOV `viewer_type`
+ * (primaryray.glsl:46-94) into the result image. */
+int adypt_tracer_primary(adypt_tracer *tracer, int32_t viewer_type);
+/* n_spp x OglPathTracer::Trace(true) (OglPathTracer.cpp:36-50): the first call after create/primary clears
+ * the result image and resets the Sobol generator; each sample advances spp by one. The result image is
+ * the reference's running mean (pathtracer.glsl:224-226). */
+int adypt_tracer_sample(adypt_tracer *tracer, int32_t n_spp);
+/* Sample-sharded rendering (not in the reference): adds the clamped radiance of samples
+ * first_spp .. first_spp+n_spp-1 into a SUM accumulator (w*h*4 floats, .w counts samples). first_spp must
+ * be a multiple of tmp_lifetime. The accumulator is exposed as a device pointer so the caller can reduce it
+ * across GPUs (NCCL) before adypt_tracer_resolve_sum divides by the sample count into the result image. */
+int adypt_tracer_accumulate(adypt_tracer *tracer, int32_t first_spp, int32_t n_spp);
+int adypt_tracer_sum_buffer(adypt_tracer *tracer, float **device_ptr, uint64_t *n_floats);
+int adypt_tracer_clear_sum(adypt_tracer *tracer);
+int adypt_tracer_resolve_sum(adypt_tracer *tracer);
+/* OglPathTracer::GetSPP (OglPathTracer.hpp:76) */
+int adypt_tracer_spp(adypt_tracer *tracer, int32_t *spp);
+/* the result image uOutImg: width*height*4 floats RGBA, row-major, top row first (glGetTextureImage order
+ * of OglPathTracer.cpp:205 is RGB; use channels = 3 for that) */
+int adypt_tracer_read(adypt_tracer *tracer, float *out, int32_t channels);
+int adypt_tracer_result_buffer(adypt_tracer *tracer, float **device_ptr, uint64_t *n_floats);
+/* OglPathTracer::SaveResult(const char*, bool save_as_fp16) (OglPathTracer.cpp:199-212): RGB scanline
+ * OpenEXR, ZIP-compressed, half or float channels */
+int adypt_tracer_save_exr(adypt_tracer *tracer, const char *filename, int32_t save_as_fp16);
+/* blocks until everything queued on the tracer's stream has finished */
+int adypt_tracer_sync(adypt_tracer *tracer);
+/* the pinhole rays of primaryray.glsl:39-44 (bias 0,0) for the current camera, written to `rays`
+ * (width*height*8 floats, row-major pixel order): the C1 benchmark's ray set */
+int adypt_tracer_primary_rays(adypt_tracer *tracer, float *rays, int memspace);
+/* per-tracer statistics since creation: traced path segments and kernel launches */
+int adypt_tracer_stats(adypt_tracer *tracer, uint64_t *segments, uint64_t *launches);
+
+/* standalone EXR writer used by adypt_tracer_save_exr (rgb: width*height*3 floats) */
+int adypt_write_exr(const char *filename, const float *rgb, int32_t width, int32_t height, int32_t save_as_fp16);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADYPT_B200_H */
