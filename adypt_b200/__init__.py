@@ -25,7 +25,7 @@ VIEW_DIFFUSE, VIEW_SPECULAR, VIEW_EMISSIVE, VIEW_RADIANCE, VIEW_NORMAL, VIEW_POS
 # every symbol include/adypt_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
     "adypt_last_error", "adypt_version", "adypt_device_count", "adypt_scene_create", "adypt_scene_destroy",
-    "adypt_scene_read_woop", "adypt_scene_device_bytes", "adypt_trace_closest", "adypt_trace_any", "adypt_launch_count",
+    "adypt_scene_read_woop", "adypt_scene_device_bytes", "adypt_trace_closest", "adypt_trace_any", "adypt_trace_stats", "adypt_launch_count",
     "adypt_trace_configure", "adypt_tracer_create", "adypt_tracer_destroy", "adypt_tracer_set_config",
     "adypt_tracer_set_bias", "adypt_tracer_get_bias", "adypt_tracer_set_camera", "adypt_camera_matrices",
     "adypt_tracer_primary", "adypt_tracer_sample", "adypt_tracer_accumulate", "adypt_tracer_sum_buffer",
@@ -81,6 +81,7 @@ def load_library():
         "adypt_trace_closest": [vp, vp, u64, vp, vp, vp, C.c_int, vp],
         "adypt_trace_any": [vp, vp, u64, vp, C.c_int, vp],
         "adypt_launch_count": [vp],
+        "adypt_trace_stats": [vp, vp, u64, C.c_int, vp],
         "adypt_trace_configure": [vp, C.c_int, C.c_int],
         "adypt_tracer_create": [vp, C.POINTER(PTConfig), i32, i32, u64, vp],
         "adypt_tracer_destroy": [vp],
@@ -230,6 +231,16 @@ class Scene:
         uv = (np.zeros((n, 2), dtype=np.float32) if want_uv else None) if uv is None else uv
         _check(lib.adypt_trace_closest(self._h, rays.ctypes.data, n, _ptr(tri), _ptr(t), _ptr(uv), MEM_HOST, stream))
         return dict(tri=tri, t=t, uv=uv)
+
+    def trace_stats(self, rays):
+        """Instrumented pass: dict(nodes, tris, hits, max_stack) totals over the batch (adypt_trace_stats)."""
+        out = (C.c_uint64 * 4)()
+        if _is_device(rays):
+            _check(load_library().adypt_trace_stats(self._h, _ptr(rays), rays.numel() // 8, MEM_DEVICE, out))
+        else:
+            rays = np.ascontiguousarray(rays, dtype=np.float32)
+            _check(load_library().adypt_trace_stats(self._h, rays.ctypes.data, rays.size // 8, MEM_HOST, out))
+        return dict(nodes=int(out[0]), tris=int(out[1]), hits=int(out[2]), max_stack=int(out[3]))
 
     def trace_any(self, rays, occluded=None, stream=None):
         lib = load_library()

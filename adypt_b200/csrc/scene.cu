@@ -105,6 +105,7 @@ int launch_trace(adypt_scene *s, const float4 *d_rays, uint64_t n, int32_t *d_tr
 	p.out_t = d_t;
 	p.out_uv = d_uv;
 	p.out_occ = d_occ;
+	p.stats = nullptr;
 	p.counter = s->d_counters + (s->counter_cursor++ % kCounterRing);
 	p.refill_threshold = s->refill_threshold > 0 ? s->refill_threshold : 28;
 	int per_sm = s->ctas_per_sm > 0 ? s->ctas_per_sm : (any ? s->occ_any : s->occ_closest);
@@ -243,7 +244,7 @@ int adypt_scene_create(const adypt_scene_desc *d, adypt_scene **out)
 		if (e != cudaSuccess) { free_scene(s); return fail(ADYPT_ECUDA, std::string("build_woop_kernel: ") + cudaGetErrorString(e)); }
 	}
 #undef UP
-	if (cudaMalloc((void **)&s->d_counters, kCounterRing * sizeof(unsigned long long)) != cudaSuccess) { free_scene(s); return fail(ADYPT_ENOMEM, "cudaMalloc counters"); }
+	if (cudaMalloc((void **)&s->d_counters, (kCounterRing + 4) * sizeof(unsigned long long)) != cudaSuccess) { free_scene(s); return fail(ADYPT_ENOMEM, "cudaMalloc counters"); }
 	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->occ_closest, trace_kernel<false>, kTraceBlock, 0);
 	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->occ_any, trace_kernel<true>, kTraceBlock, 0);
 	*out = s;
@@ -315,6 +316,40 @@ int adypt_trace_closest(adypt_scene *s, const float *rays, uint64_t n, int32_t *
 	if (memspace == ADYPT_MEM_DEVICE)
 		return launch_trace(s, (const float4 *)rays, n, tri, t, (float2 *)uv, nullptr, (cudaStream_t)stream);
 	return trace_host(s, rays, n, tri, t, uv, nullptr, (cudaStream_t)stream);
+}
+
+int adypt_trace_stats(adypt_scene *s, const float *rays, uint64_t n, int memspace, uint64_t out[4])
+{
+	if (!s || !out) return fail(ADYPT_EINVAL, "scene/out is NULL");
+	out[0] = out[1] = out[2] = out[3] = 0;
+	if (n == 0) return ADYPT_OK;
+	if (!rays) return fail(ADYPT_EINVAL, "rays is NULL");
+	DeviceGuard g(s->device);
+	const float4 *d_rays = (const float4 *)rays;
+	if (memspace == ADYPT_MEM_HOST) {
+		ADYPT_TRY(s->stage_in.reserve((size_t)n * 32u));
+		ADYPT_CUDA(cudaMemcpy(s->stage_in.ptr, rays, (size_t)n * 32u, cudaMemcpyHostToDevice));
+		d_rays = s->stage_in.as<float4>();
+	} else if (memspace != ADYPT_MEM_DEVICE)
+		return fail(ADYPT_EINVAL, "bad memspace");
+	ADYPT_TRY(s->stage_out.reserve((size_t)n * 4u + 64u));
+	unsigned long long *d_stats = s->d_counters + kCounterRing; // 4 extra slots behind the ring
+	ADYPT_CUDA(cudaMemset(d_stats, 0, 4 * sizeof(unsigned long long)));
+	TraceParams p;
+	p.nodes = s->d_nodes; p.woop = s->d_woop; p.tri_indices = s->d_tri_indices; p.rays = d_rays;
+	p.n = n; p.n_ptr = nullptr;
+	p.out_tri = s->stage_out.as<int32_t>(); p.out_t = nullptr; p.out_uv = nullptr; p.out_occ = nullptr;
+	p.counter = s->d_counters + (s->counter_cursor++ % kCounterRing);
+	p.stats = d_stats;
+	p.refill_threshold = s->refill_threshold > 0 ? s->refill_threshold : 28;
+	ADYPT_CUDA(cudaMemset(p.counter, 0, sizeof(unsigned long long)));
+	trace_kernel<false, true><<<(unsigned)s->sm_count * 4u, kTraceBlock>>>(p);
+	count_launch();
+	ADYPT_CUDA(cudaDeviceSynchronize());
+	unsigned long long h[4];
+	ADYPT_CUDA(cudaMemcpy(h, d_stats, sizeof(h), cudaMemcpyDeviceToHost));
+	for (int i = 0; i < 4; ++i) out[i] = h[i];
+	return ADYPT_OK;
 }
 
 int adypt_trace_any(adypt_scene *s, const float *rays, uint64_t n, uint8_t *occluded, int memspace, void *stream)

@@ -33,6 +33,7 @@ struct TraceParams {
 	float2 *__restrict__ out_uv;            // closest, nullable
 	uint8_t *__restrict__ out_occ;          // any
 	unsigned long long *counter;            // zeroed before launch
+	unsigned long long *stats;              // STATS kernels only: [0] nodes visited [1] triangles tested [2] hits [3] max stack depth
 	int refill_threshold;                   // leave the traversal loop when fewer lanes than this are busy
 };
 
@@ -84,7 +85,7 @@ __device__ __forceinline__ uint32_t test_children4(uint32_t meta4, uint32_t octi
 	return hitmask;
 }
 
-template <bool ANY>
+template <bool ANY, bool STATS = false>
 __global__ void __launch_bounds__(kTraceBlock, 6) trace_kernel(const TraceParams p)
 {
 	__shared__ uint2 s_stack[kSmemStack][kTraceBlock];
@@ -108,6 +109,7 @@ __global__ void __launch_bounds__(kTraceBlock, 6) trace_kernel(const TraceParams
 	int32_t hit_idx = -1;
 	uint2 ng = make_uint2(0, 0), tg = make_uint2(0, 0);
 	int sp = 0;
+	unsigned long long st_nodes = 0, st_tris = 0, st_hits = 0, st_depth = 0; // dead code unless STATS
 
 	for (;;) {
 		// ---------------------------------------------------------------- refill idle lanes
@@ -163,7 +165,9 @@ __global__ void __launch_bounds__(kTraceBlock, 6) trace_kernel(const TraceParams
 						if (sp < kSmemStack) s_stack[sp][tid] = ng;
 						else if (sp < kSmemStack + kLocalStack) l_stack[sp - kSmemStack] = ng;
 						++sp;
+						if (STATS && (unsigned long long)sp > st_depth) st_depth = sp;
 					}
+					if (STATS) ++st_nodes;
 					const uint32_t slot = (bit - 24u) ^ octinv;
 					const uint32_t rel = (uint32_t)__popc(imask & ~(0xffffffffu << slot));
 					const uint4 *np = p.nodes + (size_t)(base + rel) * 5u;
@@ -203,6 +207,7 @@ __global__ void __launch_bounds__(kTraceBlock, 6) trace_kernel(const TraceParams
 					tg.y &= tg.y - 1u;
 					const float4 *wp = p.woop + (size_t)tr * 3u;
 					const float4 m0 = __ldg(wp), m1 = __ldg(wp + 1), m2 = __ldg(wp + 2);
+					if (STATS) ++st_tris;
 					const float toz = __fsub_rn(m0.w, dot3_fma(ox, oy, oz, m0));
 					const float tidz = __frcp_rn(dot3_fma(dx, dy, dz, m0));
 					const float tt = __fmul_rn(toz, tidz);
@@ -229,6 +234,7 @@ __global__ void __launch_bounds__(kTraceBlock, 6) trace_kernel(const TraceParams
 
 				if (finished) {
 					active = false;
+					if (STATS && hit_t < 1e9f) ++st_hits;
 					if (ANY) {
 						p.out_occ[ray_idx] = (hit_t < 1e9f) ? 1 : 0;
 					} else {
@@ -240,6 +246,12 @@ __global__ void __launch_bounds__(kTraceBlock, 6) trace_kernel(const TraceParams
 			}
 			busy = __ballot_sync(kFullMask, active);
 		} while (busy != 0u && (exhausted || __popc(busy) >= p.refill_threshold));
+	}
+	if (STATS) {
+		atomicAdd(p.stats + 0, st_nodes);
+		atomicAdd(p.stats + 1, st_tris);
+		atomicAdd(p.stats + 2, st_hits);
+		atomicMax(p.stats + 3, st_depth);
 	}
 }
 

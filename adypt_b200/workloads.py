@@ -249,9 +249,11 @@ def city(cells: int = 183, seed: int = 1, mixed_materials: bool = False, name: s
 def tiny_scene(kind: str) -> SceneMesh:
     """Hand-checkable scenes for known-answer tests."""
     m = [Material("m0", kd=(0.8, 0.8, 0.8))]
-    if kind == "one_triangle":
-        v = np.array([(0, 0, 0), (1, 0, 0), (0, 1, 0)], dtype=np.float32)
-        f = np.array([(0, 1, 2)], dtype=np.int32)
+    if kind == "two_triangles":
+        # the smallest scene the reference can build: with ONE triangle the SBVH root is a leaf and
+        # WideBVHBuilder::fetch_children dereferences its left child -1 (WideBVHBuilder.cpp:93-108)
+        v = np.array([(0, 0, 0), (1, 0, 0), (0, 1, 0), (3, 0, 1), (4, 0, 1), (3, 1, 1)], dtype=np.float32)
+        f = np.array([(0, 1, 2), (3, 4, 5)], dtype=np.int32)
     elif kind == "shared_edge":
         # two coplanar triangles sharing the diagonal of the unit square in z=0
         v = np.array([(0, 0, 0), (1, 0, 0), (1, 1, 0), (0, 1, 0)], dtype=np.float32)

@@ -96,6 +96,10 @@ int adypt_scene_device_bytes(adypt_scene *scene, uint64_t *bytes);
 int adypt_trace_closest(adypt_scene *scene, const float *rays, uint64_t n, int32_t *tri, float *t, float *uv,
                         int memspace, void *stream);
 int adypt_trace_any(adypt_scene *scene, const float *rays, uint64_t n, uint8_t *occluded, int memspace, void *stream);
+/* Instrumented closest-hit pass over the same rays (results discarded): out[0] = nodes visited, out[1] =
+ * triangles tested, out[2] = rays that hit, out[3] = deepest traversal stack. These are the per-ray work
+ * counts behind the roofline's algorithmic bytes; the oracle counts the same events. Blocking. */
+int adypt_trace_stats(adypt_scene *scene, const float *rays, uint64_t n, int memspace, uint64_t out[4]);
 /* number of kernel launches adypt_* calls have issued so far on this scene's device (bench accounting) */
 int adypt_launch_count(uint64_t *launches);
 /* tuning knobs of the persistent traversal kernel (0 = default): CTAs per SM and the refill threshold */

@@ -1,0 +1,115 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+CACHE = os.path.join(ROOT, ".cache", "scenes")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu on the GPU box")
+
+
+def fnv1a(arr) -> int:
+    """64-bit FNV-1a over the raw bytes of an array (golden hashes)."""
+    data = np.ascontiguousarray(arr).view(np.uint8).ravel()
+    # vectorised FNV is awkward; hash 8-byte words with a multiplicative mix instead, then FNV the digest
+    pad = (-data.size) % 8
+    if pad:
+        data = np.concatenate([data, np.zeros(pad, dtype=np.uint8)])
+    w = data.view(np.uint64)
+    idx = np.arange(w.size, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        m = (w + np.uint64(0x9E3779B97F4A7C15) * (idx + np.uint64(1)))
+        m = (m ^ (m >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        m = (m ^ (m >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        m = m ^ (m >> np.uint64(31))
+        acc = np.bitwise_xor.reduce(m) ^ np.uint64(data.size)
+    h = 0xCBF29CE484222325
+    for b in int(acc).to_bytes(8, "little"):
+        h = ((h ^ b) * 0x100000001B3) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
+class GoldenScene:
+    """Arrays of a committed fixture (tests/golden/<name>.npz): no reference needed to load it."""
+
+    def __init__(self, path):
+        z = np.load(path)
+        self.nodes, self.tri_indices, self.woop = z["nodes"], z["tri_indices"], z["woop"]
+        self.tris, self.mats = z["tris"], z["mats"]
+        self.extra = {k: z[k] for k in z.files if k not in ("nodes", "tri_indices", "woop", "tris", "mats")}
+
+
+@pytest.fixture(scope="session")
+def golden_dir():
+    return GOLDEN
+
+
+def load_golden(name):
+    return GoldenScene(os.path.join(GOLDEN, name + ".npz"))
+
+
+@pytest.fixture(scope="session")
+def refmod():
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref/libadypt_ref.so not built (needs /root/reference at build time)")
+    return ref
+
+
+@pytest.fixture(scope="session")
+def cpu():
+    from oracle import cpu as c
+    c.lib()
+    return c
+
+
+@pytest.fixture(scope="session")
+def c1(refmod):
+    """C1: 65 536-triangle sphere lattice through the reference OBJ -> SBVH -> CWBVH pipeline."""
+    from adypt_b200 import workloads as W
+    mesh = W.sphere_lattice(5)
+    bvh = refmod.build(mesh.write_obj(CACHE))
+    return mesh, bvh
+
+
+@pytest.fixture(scope="session")
+def city_small(refmod):
+    """A 24x24-cell city (~17k triangles) with every material type: quick C2/C3 stand-in."""
+    from adypt_b200 import workloads as W
+    mesh = W.city(24, 1, mixed_materials=True)
+    bvh = refmod.build(mesh.write_obj(CACHE))
+    return mesh, bvh
+
+
+@pytest.fixture(scope="session")
+def c2(refmod):
+    """C2: ~1.0M-triangle box city (reference build takes ~20 s the first time, cached afterwards)."""
+    from adypt_b200 import workloads as W
+    mesh = W.city(183, 1)
+    bvh = refmod.build(mesh.write_obj(CACHE))
+    return mesh, bvh
+
+
+def gpu_available():
+    try:
+        import adypt_b200 as A
+        return A.device_count() > 0
+    except Exception:
+        return False
+
+
+@pytest.fixture(scope="session")
+def A():
+    """The product package, with the CUDA library loaded; GPU tests fail loudly if it is missing."""
+    import adypt_b200 as A
+    A.load_library()
+    assert A.device_count() > 0, "no CUDA device: the product path has no CPU fallback"
+    return A

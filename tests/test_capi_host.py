@@ -1,0 +1,112 @@
+"""C-ABI library checks that need no GPU: it loads, exports every symbol the header declares, fails loudly
+(no CPU fallback) without a device, and its host-side arithmetic / EXR writer are right."""
+import ctypes as C
+import glob
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, gpu_available, load_golden
+
+import adypt_b200 as A
+from exr_reader import read_exr
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def test_library_is_built_in_tree():
+    assert os.path.exists(A.LIB_PATH), "run python -c 'import __graft_entry__ as g; g.build()'"
+    assert A.LIB_PATH.startswith(ROOT)
+
+
+def test_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "adypt_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(adypt_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 30
+    lib = A.load_library()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/adypt_b200.h but not exported"
+    assert sorted(A.EXPORTS) == declared
+    assert lib.adypt_version() == 100
+
+
+def test_header_compiles_as_c(tmp_path):
+    src = tmp_path / "t.c"
+    src.write_text('#include "adypt_b200.h"\nint main(void){ adypt_pt_config c; return sizeof(c) == 40 ? 0 : 1; }\n')
+    exe = tmp_path / "t"
+    import subprocess
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    assert subprocess.call([str(exe)]) == 0
+
+
+@pytest.mark.skipif(gpu_available(), reason="checks behaviour on a machine WITHOUT a GPU")
+def test_no_device_fails_loudly():
+    g = load_golden("tiny_strip")
+    with pytest.raises(A.AdyptError) as e:
+        A.Scene(g.nodes, g.tri_indices, g.woop, g.tris, g.mats)
+    assert e.value.code == -2  # ADYPT_ENODEV
+    assert "no CPU fallback" in str(e.value) or "cudaGetDeviceCount" in str(e.value)
+
+
+def test_argument_validation():
+    lib = A.load_library()
+    assert lib.adypt_scene_create(None, None) == -1
+    assert b"NULL" in lib.adypt_last_error()
+    assert lib.adypt_trace_closest(None, None, 0, None, None, None, 0, None) == -1
+    assert lib.adypt_tracer_sample(None, 1) == -1
+    assert lib.adypt_scene_destroy(None) == 0 and lib.adypt_tracer_destroy(None) == 0
+
+
+def test_product_never_imports_oracle():
+    """The product path must not route through the oracle (or any CPU fallback)."""
+    for path in glob.glob(os.path.join(ROOT, "adypt_b200", "**", "*"), recursive=True):
+        if os.path.isfile(path) and path.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".inc")):
+            txt = open(path, errors="replace").read()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), path
+            assert "liboracle" not in txt and "libadypt_ref" not in txt, path
+            assert not re.search(r'#include\s+"[^"]*oracle', txt), path
+
+
+def test_camera_matrices_match_reference_golden():
+    """adypt_camera_matrices == Camera::GetProjection/GetView of the reference (golden from oracle/_ref)."""
+    z = np.load(os.path.join(GOLDEN, "ref_camera.npz"))
+    for i, (fov, yaw, pitch, w, h) in enumerate(z["params"]):
+        p, v = A.camera_matrices(float(fov), float(yaw), float(pitch), int(w), int(h))
+        assert np.array_equal(bits(p), bits(z["proj"][i])), i
+        assert np.array_equal(bits(v), bits(z["view"][i])), i
+
+
+@pytest.mark.parametrize("fp16", [False, True])
+def test_exr_round_trip(tmp_path, fp16):
+    rng = np.random.default_rng(3)
+    h, w = 37, 53  # not a multiple of the 16-line ZIP chunk
+    img = rng.random((h, w, 3), dtype=np.float32) * 4.0
+    img[0, 0] = [0.0, 1.0, 65504.0]
+    img[1, 1] = [1e-8, 6e-5, 70000.0]  # half: flush / subnormal / overflow to inf
+    path = str(tmp_path / "o.exr")
+    A.write_exr(path, img, fp16=fp16)
+    r = read_exr(path)
+    assert (r["width"], r["height"]) == (w, h)
+    assert [c for c, _ in r["channels"]] == ["B", "G", "R"]
+    assert r["compression"] == 3  # ZIP, like tinyexr's SaveEXR default
+    got = np.stack([r["data"]["R"], r["data"]["G"], r["data"]["B"]], axis=2)
+    if fp16:
+        assert np.array_equal(got, img.astype(np.float16).astype(np.float32))  # round-to-nearest-even
+    else:
+        assert np.array_equal(bits(got), bits(img))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/results"), reason="reference tree not present")
+def test_reader_parses_reference_showcase_exr():
+    """Pins the test reader (and with it the writer's layout) on a file written by the reference's tinyexr."""
+    f = sorted(glob.glob("/root/reference/results/*.exr"))[0]
+    r = read_exr(f)
+    assert (r["width"], r["height"]) == (1280, 720)
+    assert [c for c, _ in r["channels"]] == ["B", "G", "R"] and all(t == 1 for _, t in r["channels"])
+    assert r["compression"] == 3
+    assert np.isfinite(r["data"]["R"]).all() and r["data"]["R"].mean() > 0
