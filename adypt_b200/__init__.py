@@ -32,6 +32,8 @@ EXPORTS = [
     "adypt_tracer_clear_sum", "adypt_tracer_resolve_sum", "adypt_tracer_spp", "adypt_tracer_read",
     "adypt_tracer_result_buffer", "adypt_tracer_save_exr", "adypt_tracer_sync", "adypt_tracer_primary_rays",
     "adypt_tracer_stats", "adypt_write_exr",
+    "adypt_host_scene_load_obj", "adypt_host_scene_from_triangles", "adypt_host_scene_destroy", "adypt_host_scene_build_bvh",
+    "adypt_host_scene_load_bvh", "adypt_host_scene_save_bvh", "adypt_host_scene_get", "adypt_host_scene_upload",
 ]
 
 

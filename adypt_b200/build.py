@@ -16,7 +16,7 @@ LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libadypt_b200.so")
 
 CU_SOURCES = ["scene.cu", "tracer.cu"]
-CPP_SOURCES = ["hostmath.cpp", "exr.cpp"]
+CPP_SOURCES = ["hostmath.cpp", "exr.cpp", "host/bvh_build.cpp", "host/obj_loader.cpp", "host/host_api.cpp"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -39,7 +39,7 @@ def _stale() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "adypt_b200.h"), __file__]
+    deps = [os.path.join(d, f) for d, _, fs in os.walk(CSRC) for f in fs] + [os.path.join(HERE, "..", "include", "adypt_b200.h"), __file__]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -53,7 +53,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     objs = []
     procs = []
     for src in _sources():
-        obj = os.path.join(objdir, os.path.basename(src) + ".o")
+        obj = os.path.join(objdir, os.path.relpath(src, CSRC).replace(os.sep, "_") + ".o")
         cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-x", "cu", "-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)

@@ -36,16 +36,21 @@ def log(*a):
 
 
 def build_inputs():
-    """C2 scene arrays. The CWBVH comes from the product's own from-scratch builder when it is available
-    (adypt_b200.host), byte-identical to the reference's; until then from the reference pipeline compiled in
-    place (oracle/_ref) -- input preparation only, nothing on the timed path."""
+    """C2 scene arrays from the product's own host stages (adypt_b200.host): Triangle[] assembly and the
+    from-scratch SBVH -> CWBVH builder, byte-identical to the reference's src/BVH pipeline (tests/
+    test_host_builder.py). The node/index arrays are cached in the reference's own .bvh format
+    (WideBVH.cpp:9-66), as Instance::Initialize does (Instance.cpp:19-31). Nothing here touches oracle/."""
+    from adypt_b200 import host
     mesh = W.city(CELLS, SCENE_SEED)
-    try:
-        from adypt_b200 import host  # product-side builder (SURVEY §8f-1)
-        return mesh, host.build_scene(mesh)
-    except ImportError:
-        from oracle import ref
-        return mesh, ref.build(mesh.write_obj(CACHE))
+    hs = host.HostScene.from_triangles(mesh.positions(), mesh.face_mat, host.materials_array(mesh.materials))
+    os.makedirs(CACHE, exist_ok=True)
+    bvh_path = os.path.join(CACHE, mesh.name + ".bvh")
+    if not hs.load_bvh(bvh_path):
+        t0 = time.perf_counter()
+        hs.build_bvh()
+        log(f"built CWBVH in {time.perf_counter() - t0:.1f} s")
+        hs.save_bvh(bvh_path)
+    return mesh, hs
 
 
 def workload_config(n_rays, extra=None):
@@ -90,6 +95,7 @@ def cpu_leg(bvh, rays, budget_s=12.0):
     from oracle import cpu
     cores = cpu.hardware_threads()
     probe = min(rays.shape[0], 262144)
+    bvh.woop = cpu.build_woop(bvh.tris, bvh.tri_indices)
     t0 = time.perf_counter()
     cpu.trace_closest(bvh.nodes, bvh.tri_indices, bvh.woop, rays[:probe], want_t=False)
     rate = probe / (time.perf_counter() - t0)
@@ -113,6 +119,7 @@ def run_reference(args, rank, world):
         return
     from oracle import cpu
     mesh, bvh = build_inputs()
+    bvh.woop = cpu.build_woop(bvh.tris, bvh.tri_indices)
     cam = W.city_camera(CELLS)
     m = cpu.camera_matrices(cam["fov"], cam["yaw"], cam["pitch"], PRIMARY, PRIMARY)
     prim = cpu.primary_rays(cam["position"], 1e-4, m["inv_proj"], m["inv_view"], PRIMARY, PRIMARY)
@@ -158,7 +165,7 @@ def run_native(args, rank, world, local_rank):
     A.load_library()
 
     mesh, bvh = build_inputs()
-    scene = A.Scene(bvh.nodes, bvh.tri_indices, None, bvh.tris, bvh.mats, device=local_rank)  # Woop built on the GPU
+    scene = bvh.upload(local_rank)  # OglScene::Initialize: Woop rows are built on the GPU
     tracer = A.Tracer(scene, A.PTConfig.make(), PRIMARY, PRIMARY, bias_seed=7)
     cam = W.city_camera(CELLS)
     tracer.look(cam["position"], cam["yaw"], cam["pitch"], cam["fov"])

@@ -176,6 +176,47 @@ int adypt_tracer_stats(adypt_tracer *tracer, uint64_t *segments, uint64_t *launc
 /* standalone EXR writer used by adypt_tracer_save_exr (rgb: width*height*3 floats) */
 int adypt_write_exr(const char *filename, const float *rgb, int32_t width, int32_t height, int32_t save_as_fp16);
 
+/* ------------------------------------------------------------------------------------------------
+ * Host side (no GPU needed): the CPU stages that FEED the tracer in the reference -- Scene (src/Util/Scene.*),
+ * SBVHBuilder + WideBVHBuilder (src/BVH/*) and the .bvh cache (src/BVH/WideBVH.cpp) -- rebuilt from scratch
+ * with byte-identical output. A host scene owns Triangle[], GPUMaterial[], the 80-byte
+ * node array and the leaf-order index array. */
+typedef struct adypt_host_scene adypt_host_scene;
+
+typedef struct { /* InstanceConfig::BVH (src/InstanceConfig.hpp:15-20) */
+	int32_t max_spatial_depth;
+	float triangle_sah;
+	float node_sah;
+} adypt_bvh_config;
+
+typedef struct {
+	uint32_t n_tris, n_mats, n_nodes, n_refs, n_binary_nodes;
+	const void *triangles;      /* n_tris * 100 B */
+	const void *materials;      /* n_mats * 64 B */
+	const void *nodes;          /* n_nodes * 80 B (NULL before a BVH is built or loaded) */
+	const int32_t *tri_indices; /* n_refs */
+	const void *binary_nodes;   /* n_binary_nodes * 32 B, the intermediate SBVH (NULL when loaded from a .bvh file) */
+	float aabb[6];              /* Scene::GetAABB: min xyz, max xyz */
+} adypt_host_scene_info;
+
+/* Scene::LoadFromFile (src/Util/Scene.cpp:9-136): Wavefront OBJ + MTL -> Triangle[] (flat normals generated when
+ * the file has none, v texture coordinate flipped) and materials as OglScene::init_materials lays them out. */
+int adypt_host_scene_load_obj(const char *obj_path, adypt_host_scene **out);
+/* the same Triangle records from raw corner positions (n_tris * 9 floats) + material ids, with the flat normals
+ * Scene.cpp:117-123 generates: for callers that already hold the mesh in memory */
+int adypt_host_scene_from_triangles(const float *positions, const int32_t *material_ids, uint32_t n_tris,
+                                    const void *materials64, uint32_t n_mats, adypt_host_scene **out);
+int adypt_host_scene_destroy(adypt_host_scene *scene);
+/* SBVHBuilder::Run + WideBVHBuilder::Run (Instance.cpp:22-24) */
+int adypt_host_scene_build_bvh(adypt_host_scene *scene, const adypt_bvh_config *config);
+/* WideBVH::LoadFromFile / SaveToFile (src/BVH/WideBVH.cpp:9-66). load returns ADYPT_EIO when the file is missing,
+ * has another magic or was built with other parameters -- the caller then rebuilds, as Instance.cpp:20-31 does */
+int adypt_host_scene_load_bvh(adypt_host_scene *scene, const char *bvh_path, const adypt_bvh_config *expected);
+int adypt_host_scene_save_bvh(adypt_host_scene *scene, const char *bvh_path, const adypt_bvh_config *config);
+int adypt_host_scene_get(adypt_host_scene *scene, adypt_host_scene_info *info);
+/* OglScene::Initialize(scene, wbvh) (Instance.cpp:33): uploads to `device`, Woop rows built on the GPU */
+int adypt_host_scene_upload(adypt_host_scene *scene, int32_t device, adypt_scene **out);
+
 #ifdef __cplusplus
 }
 #endif
