@@ -178,7 +178,7 @@ int adypt_write_exr(const char *filename, const float *rgb, int32_t width, int32
 
 /* ------------------------------------------------------------------------------------------------
  * Host side (no GPU needed): the CPU stages that FEED the tracer in the reference -- Scene (src/Util/Scene.*),
- * SBVHBuilder + WideBVHBuilder (src/BVH/*) and the .bvh cache (src/BVH/WideBVH.cpp) -- rebuilt from scratch
+ * SBVHBuilder + WideBVHBuilder (src/BVH) and the .bvh cache (src/BVH/WideBVH.cpp) -- rebuilt from scratch
  * with byte-identical output. A host scene owns Triangle[], GPUMaterial[], the 80-byte
  * node array and the leaf-order index array. */
 typedef struct adypt_host_scene adypt_host_scene;
