@@ -31,7 +31,7 @@ EXPORTS = [
     "adypt_tracer_primary", "adypt_tracer_sample", "adypt_tracer_accumulate", "adypt_tracer_sum_buffer",
     "adypt_tracer_clear_sum", "adypt_tracer_resolve_sum", "adypt_tracer_spp", "adypt_tracer_read",
     "adypt_tracer_result_buffer", "adypt_tracer_save_exr", "adypt_tracer_sync", "adypt_tracer_primary_rays",
-    "adypt_tracer_stats", "adypt_write_exr",
+    "adypt_tracer_stats", "adypt_write_exr", "adypt_debug_math",
     "adypt_host_scene_load_obj", "adypt_host_scene_from_triangles", "adypt_host_scene_destroy", "adypt_host_scene_build_bvh",
     "adypt_host_scene_load_bvh", "adypt_host_scene_save_bvh", "adypt_host_scene_get", "adypt_host_scene_upload",
 ]
@@ -84,7 +84,7 @@ def load_library():
         "adypt_trace_any": [vp, vp, u64, vp, C.c_int, vp],
         "adypt_launch_count": [vp],
         "adypt_trace_stats": [vp, vp, u64, C.c_int, vp],
-        "adypt_trace_configure": [vp, C.c_int, C.c_int],
+        "adypt_trace_configure": [vp, C.c_int, C.c_int, C.c_int],
         "adypt_tracer_create": [vp, C.POINTER(PTConfig), i32, i32, u64, vp],
         "adypt_tracer_destroy": [vp],
         "adypt_tracer_set_config": [vp, C.POINTER(PTConfig)],
@@ -106,6 +106,7 @@ def load_library():
         "adypt_tracer_primary_rays": [vp, vp, C.c_int],
         "adypt_tracer_stats": [vp, vp, vp],
         "adypt_write_exr": [C.c_char_p, vp, i32, i32, i32],
+        "adypt_debug_math": [i32, i32, vp, vp, u64, vp, vp],
     }
     for name, args in sig.items():
         f = getattr(l, name)
@@ -162,6 +163,21 @@ def write_exr(path, rgb, fp16=False):
     _check(load_library().adypt_write_exr(path.encode(), rgb.ctypes.data, w, h, int(fp16)))
 
 
+def debug_sincos(x, device=0):
+    """GPU evaluation of the shading stage's deterministic sin/cos (adypt_debug_math op 0)."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    s, c = np.empty_like(x), np.empty_like(x)
+    _check(load_library().adypt_debug_math(device, 0, x.ctypes.data, None, x.size, s.ctypes.data, c.ctypes.data))
+    return s, c
+
+
+def debug_pow(x, y, device=0):
+    x, y = np.ascontiguousarray(x, dtype=np.float32), np.ascontiguousarray(y, dtype=np.float32)
+    o = np.empty_like(x)
+    _check(load_library().adypt_debug_math(device, 1, x.ctypes.data, y.ctypes.data, x.size, o.ctypes.data, None))
+    return o
+
+
 class Scene:
     """Device-resident CWBVH scene: OglScene::Initialize(scene, wbvh) (OglScene.cpp:46-49, 118-141)."""
 
@@ -209,8 +225,8 @@ class Scene:
         _check(load_library().adypt_scene_device_bytes(self._h, C.byref(b)))
         return b.value
 
-    def configure(self, ctas_per_sm=0, refill_threshold=0):
-        _check(load_library().adypt_trace_configure(self._h, ctas_per_sm, refill_threshold))
+    def configure(self, ctas_per_sm=0, refill_threshold=0, variant=0):
+        _check(load_library().adypt_trace_configure(self._h, ctas_per_sm, refill_threshold, variant))
 
     def trace_closest(self, rays, tri=None, t=None, uv=None, stream=None, want_t=True, want_uv=True):
         """Batch closest hit. `rays`: (n,8) float32 numpy array (host) or CUDA torch tensor (device).

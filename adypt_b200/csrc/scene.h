@@ -16,6 +16,7 @@ struct adypt_scene {
 	unsigned counter_cursor = 0;
 	int ctas_per_sm = 0;       // 0 = occupancy query
 	int refill_threshold = 0;  // 0 = default
+	int variant = 0;           // code-generation variant of the closest-hit kernel (tuning only)
 	int occ_closest = 0, occ_any = 0;
 	adypt::DeviceBuffer stage_in, stage_out; // staging for host-pointer batch calls
 	uint64_t device_bytes = 0;

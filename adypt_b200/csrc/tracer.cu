@@ -15,11 +15,12 @@
 // dispatching the reference's megakernel once per sample.
 //
 // FP policy: every GLSL expression is evaluated un-fused, left to right in IEEE fp32
-// (the library is built with -fmad=false); sin/cos/pow come from CUDA's libdevice, which is why image
-// parity against the CPU oracle is an RMSE bound rather than bit equality.
+// (the library is built with -fmad=false), sqrt and division are IEEE, and sin/cos/pow are the deterministic
+// double-precision recipes of detmath.cuh -- so images match the CPU oracle bit for bit.
 #include <algorithm>
 #include <cstring>
 #include <vector>
+#include "detmath.cuh"
 #include "hostmath.h"
 #include "scene.h"
 #include "traverse.cuh"
@@ -141,8 +142,9 @@ __device__ __forceinline__ V3 bary(const float *a, const float *b, const float *
 __device__ __forceinline__ V3 sample_hemisphere(float rx, float ry, float e) // :52-64
 {
 	rx *= 6.28318530718f;
-	const float cos_phi = cosf(rx), sin_phi = sinf(rx);
-	const float cos_theta = powf(1.0f - ry, 1.0f / (e + 1.0f));
+	float cos_phi, sin_phi;
+	detmath::sincos(rx, &sin_phi, &cos_phi);
+	const float cos_theta = detmath::pow(1.0f - ry, 1.0f / (e + 1.0f));
 	const float sin_theta = __fsqrt_rn(1.0f - cos_theta * cos_theta);
 	return normalize(v3(sin_theta * cos_phi, sin_theta * sin_phi, cos_theta));
 }
@@ -182,7 +184,7 @@ __device__ __forceinline__ bool shade_segment(const ShadeBuffers &B, const PTArg
 			const V3 r = reflect(dir, normal), s = sample_hemisphere(rx, ry, e);
 			dir = align_direction(s, r);
 			if (dot(dir, normal) < 0.0f) return false;
-			color = color * (diffuse + specular * powf(dot(dir, r), e));
+			color = color * (diffuse + specular * detmath::pow(dot(dir, r), e));
 		} else
 			do_diffuse = true;
 		break;
@@ -368,6 +370,19 @@ __global__ void k_view(const uint8_t *__restrict__ tris, const Material *__restr
 			else if (type == 5) c = bary(t, t + 3, t + 6, uv.x, uv.y);
 		}
 		out[i] = make_float4(c.x, c.y, c.z, 1.0f);
+	}
+}
+
+__global__ void k_debug_math(int op, const float *__restrict__ x, const float *__restrict__ y, unsigned long long n, float *__restrict__ o, float *__restrict__ o2)
+{
+	for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+		if (op == 0) {
+			float s, c;
+			detmath::sincos(x[i], &s, &c);
+			o[i] = s;
+			o2[i] = c;
+		} else
+			o[i] = detmath::pow(x[i], y[i]);
 	}
 }
 
@@ -781,6 +796,30 @@ int adypt_tracer_primary_rays(adypt_tracer *t, float *rays, int memspace)
 	ADYPT_CUDA(cudaGetLastError());
 	if (memspace == ADYPT_MEM_HOST) ADYPT_CUDA(cudaMemcpyAsync(rays, dst, (size_t)t->npix * 32u, cudaMemcpyDeviceToHost, t->stream));
 	ADYPT_CUDA(cudaStreamSynchronize(t->stream));
+	return ADYPT_OK;
+}
+
+int adypt_debug_math(int32_t device, int32_t op, const float *x, const float *y, uint64_t n, float *out, float *out2)
+{
+	if (!x || !out || (op == 0 && !out2) || (op == 1 && !y) || (op != 0 && op != 1)) return fail(ADYPT_EINVAL, "bad argument");
+	if (n == 0) return ADYPT_OK;
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return fail(ADYPT_ENODEV, "no such CUDA device (no CPU fallback)");
+	DeviceGuard g(device);
+	float *d = nullptr;
+	ADYPT_CUDA(cudaMalloc((void **)&d, (size_t)n * 16u));
+	float *dx = d, *dy = d + n, *d0 = d + 2 * n, *d1 = d + 3 * n;
+	cudaError_t e = cudaMemcpy(dx, x, (size_t)n * 4u, cudaMemcpyHostToDevice);
+	if (e == cudaSuccess && y) e = cudaMemcpy(dy, y, (size_t)n * 4u, cudaMemcpyHostToDevice);
+	if (e == cudaSuccess) {
+		k_debug_math<<<256, 256>>>(op, dx, dy, n, d0, d1);
+		count_launch();
+		e = cudaDeviceSynchronize();
+	}
+	if (e == cudaSuccess) e = cudaMemcpy(out, d0, (size_t)n * 4u, cudaMemcpyDeviceToHost);
+	if (e == cudaSuccess && op == 0) e = cudaMemcpy(out2, d1, (size_t)n * 4u, cudaMemcpyDeviceToHost);
+	cudaFree(d);
+	if (e != cudaSuccess) return fail(ADYPT_ECUDA, std::string("adypt_debug_math: ") + cudaGetErrorString(e));
 	return ADYPT_OK;
 }
 

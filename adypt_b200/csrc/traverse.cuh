@@ -35,6 +35,7 @@ struct TraceParams {
 	unsigned long long *counter;            // zeroed before launch
 	unsigned long long *stats;              // STATS kernels only: [0] nodes visited [1] triangles tested [2] hits [3] max stack depth
 	int refill_threshold;                   // leave the traversal loop when fewer lanes than this are busy
+	uint32_t magic;                         // 0x4B000000, passed as data so ptxas keeps it in a register (see byte_to_float)
 };
 
 constexpr int kTraceBlock = 128;      // threads per CTA
@@ -48,46 +49,71 @@ __device__ __forceinline__ float dot3_fma(float ax, float ay, float az, const fl
 	return __fmaf_rn(az, m.z, __fmaf_rn(ay, m.y, __fmul_rn(ax, m.x)));
 }
 
-// exact uint8 -> float: splice the byte into the mantissa of 2^23 and subtract 2^23 (one PRMT + one FADD,
-// no conversion-pipe instruction); identical to (float)byte
-__device__ __forceinline__ float byte_to_float(uint32_t word, uint32_t selector)
+// exact uint8 -> float, two interchangeable forms (both equal (float)byte bit for bit):
+//  * MAGIC: splice the byte into the mantissa of 2^23 (PRMT with an IMMEDIATE selector against a register that
+//    holds 0x4B000000) and subtract 2^23 (FADD): alu pipe + fma pipe, no conversion-pipe instruction. `magic`
+//    arrives as a kernel parameter so ptxas cannot fold it: folded, it becomes PRMT's immediate and the four
+//    selectors get re-materialised in registers for every use (45 IMAD.U32 per node step in profile r1a).
+//  * CVT: I2F.U8 with a byte selector: one instruction, but on the quarter-rate conversion pipe.
+// kCvtPlanes (0..6) of the six quantised planes use CVT, the rest MAGIC, to balance the pipes.
+template <int K>
+__device__ __forceinline__ float byte_to_float_magic(uint32_t word, uint32_t magic)
 {
-	return __fsub_rn(__uint_as_float(__byte_perm(word, 0x4B000000u, selector)), 8388608.0f);
+	uint32_t r;
+	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(word), "r"(magic), "n"(0x7540 | K));
+	return __fsub_rn(__uint_as_float(r), 8388608.0f);
+}
+template <int K>
+__device__ __forceinline__ float byte_to_float_cvt(uint32_t word)
+{
+	return (float)((word >> (8 * K)) & 0xffu);
+}
+template <int K, bool CVT>
+__device__ __forceinline__ float byte_to_float(uint32_t word, uint32_t magic)
+{
+	return CVT ? byte_to_float_cvt<K>(word) : byte_to_float_magic<K>(word, magic);
 }
 
 // one group of four children (one 32-bit lane of each quantised plane), traversal.glsl:86-143 / :145-202
+template <int K, int CVT_PLANES>
+__device__ __forceinline__ uint32_t test_child(uint32_t child_bits4, uint32_t bit_index4, uint32_t s_lox, uint32_t s_loy, uint32_t s_loz,
+                                               uint32_t s_hix, uint32_t s_hiy, uint32_t s_hiz, float aix, float aiy, float aiz,
+                                               float aox, float aoy, float aoz, float tmin, float hit_t, uint32_t magic)
+{
+	const float txmin = __fmaf_rn(byte_to_float<K, (CVT_PLANES > 0)>(s_lox, magic), aix, aox);
+	const float tymin = __fmaf_rn(byte_to_float<K, (CVT_PLANES > 2)>(s_loy, magic), aiy, aoy);
+	const float tzmin = __fmaf_rn(byte_to_float<K, (CVT_PLANES > 4)>(s_loz, magic), aiz, aoz);
+	const float txmax = __fmaf_rn(byte_to_float<K, (CVT_PLANES > 1)>(s_hix, magic), aix, aox);
+	const float tymax = __fmaf_rn(byte_to_float<K, (CVT_PLANES > 3)>(s_hiy, magic), aiy, aoy);
+	const float tzmax = __fmaf_rn(byte_to_float<K, (CVT_PLANES > 5)>(s_hiz, magic), aiz, aoz);
+	const float ctmin = fmaxf(fmaxf(txmin, tymin), fmaxf(tzmin, tmin));
+	const float ctmax = fminf(fminf(txmax, tymax), fminf(tzmax, hit_t));
+	if (ctmin <= ctmax) {
+		const uint32_t bits = (child_bits4 >> (8 * K)) & 0xffu;
+		const uint32_t idx = (bit_index4 >> (8 * K)) & 0xffu;
+		return bits << idx;
+	}
+	return 0u;
+}
+
+template <int CVT_PLANES>
 __device__ __forceinline__ uint32_t test_children4(uint32_t meta4, uint32_t octinv4, uint32_t s_lox, uint32_t s_loy,
                                                    uint32_t s_loz, uint32_t s_hix, uint32_t s_hiy, uint32_t s_hiz,
                                                    float aix, float aiy, float aiz, float aox, float aoy, float aoz,
-                                                   float tmin, float hit_t)
+                                                   float tmin, float hit_t, uint32_t magic)
 {
 	const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
 	const uint32_t bit_index4 = (meta4 ^ (octinv4 & ((is_inner4 >> 4) * 0xffu))) & 0x1f1f1f1fu;
 	const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
-	uint32_t hitmask = 0;
-#pragma unroll
-	for (int k = 0; k < 4; ++k) {
-		const uint32_t sel = 0x7540u | (uint32_t)k;
-		const float txmin = __fmaf_rn(byte_to_float(s_lox, sel), aix, aox);
-		const float tymin = __fmaf_rn(byte_to_float(s_loy, sel), aiy, aoy);
-		const float tzmin = __fmaf_rn(byte_to_float(s_loz, sel), aiz, aoz);
-		const float txmax = __fmaf_rn(byte_to_float(s_hix, sel), aix, aox);
-		const float tymax = __fmaf_rn(byte_to_float(s_hiy, sel), aiy, aoy);
-		const float tzmax = __fmaf_rn(byte_to_float(s_hiz, sel), aiz, aoz);
-		const float ctmin = fmaxf(fmaxf(txmin, tymin), fmaxf(tzmin, tmin));
-		const float ctmax = fminf(fminf(txmax, tymax), fminf(tzmax, hit_t));
-		if (ctmin <= ctmax) {
-			const uint32_t bits = (child_bits4 >> (8 * k)) & 0xffu;
-			const uint32_t idx = (bit_index4 >> (8 * k)) & 0xffu;
-			hitmask |= bits << idx;
-		}
-	}
-	return hitmask;
+#define ADYPT_CHILD(K) test_child<K, CVT_PLANES>(child_bits4, bit_index4, s_lox, s_loy, s_loz, s_hix, s_hiy, s_hiz, aix, aiy, aiz, aox, aoy, aoz, tmin, hit_t, magic)
+	return ADYPT_CHILD(0) | ADYPT_CHILD(1) | ADYPT_CHILD(2) | ADYPT_CHILD(3);
+#undef ADYPT_CHILD
 }
 
-template <bool ANY, bool STATS = false>
-__global__ void __launch_bounds__(kTraceBlock, 6) trace_kernel(const TraceParams p)
+template <bool ANY, bool STATS = false, int CVT_PLANES = 0, int MIN_CTAS = 6>
+__global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const TraceParams p)
 {
+	const uint32_t magic = p.magic;
 	__shared__ uint2 s_stack[kSmemStack][kTraceBlock];
 	uint2 l_stack[kLocalStack];
 
@@ -186,14 +212,14 @@ __global__ void __launch_bounds__(kTraceBlock, 6) trace_kernel(const TraceParams
 					const bool nx = idx < 0.0f, ny = idy < 0.0f, nz = idz < 0.0f;
 					// planes: n2 = (lox.lo, lox.hi, loy.lo, loy.hi) n3 = (loz.lo, loz.hi, hix.lo, hix.hi)
 					//         n4 = (hiy.lo, hiy.hi, hiz.lo, hiz.hi)
-					uint32_t hitmask = test_children4(n1.z, octinv4,
+					uint32_t hitmask = test_children4<CVT_PLANES>(n1.z, octinv4,
 						nx ? n3.z : n2.x, ny ? n4.x : n2.z, nz ? n4.z : n3.x,
 						nx ? n2.x : n3.z, ny ? n2.z : n4.x, nz ? n3.x : n4.z,
-						aix, aiy, aiz, aox, aoy, aoz, tmin, hit_t);
-					hitmask |= test_children4(n1.w, octinv4,
+						aix, aiy, aiz, aox, aoy, aoz, tmin, hit_t, magic);
+					hitmask |= test_children4<CVT_PLANES>(n1.w, octinv4,
 						nx ? n3.w : n2.y, ny ? n4.y : n2.w, nz ? n4.w : n3.y,
 						nx ? n2.y : n3.w, ny ? n2.w : n4.y, nz ? n3.y : n4.w,
-						aix, aiy, aiz, aox, aoy, aoz, tmin, hit_t);
+						aix, aiy, aiz, aox, aoy, aoz, tmin, hit_t, magic);
 					ng.y = (hitmask & 0xff000000u) | (n0.w >> 24);
 					tg.y = hitmask & 0x00ffffffu;
 				} else { // :207-211

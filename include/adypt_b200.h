@@ -102,8 +102,9 @@ int adypt_trace_any(adypt_scene *scene, const float *rays, uint64_t n, uint8_t *
 int adypt_trace_stats(adypt_scene *scene, const float *rays, uint64_t n, int memspace, uint64_t out[4]);
 /* number of kernel launches adypt_* calls have issued so far on this scene's device (bench accounting) */
 int adypt_launch_count(uint64_t *launches);
-/* tuning knobs of the persistent traversal kernel (0 = default): CTAs per SM and the refill threshold */
-int adypt_trace_configure(adypt_scene *scene, int ctas_per_sm, int refill_threshold);
+/* tuning knobs of the persistent traversal kernel (0 = default): CTAs per SM, the refill threshold, and a
+ * code-generation variant of the closest-hit kernel (0..5; same algorithm, identical results) */
+int adypt_trace_configure(adypt_scene *scene, int ctas_per_sm, int refill_threshold, int variant);
 
 /* ------------------------------------------------------------------------------------------------
  * Tracer: replaces OglPathTracer (src/Tracer/OglPathTracer.hpp:66-82).
@@ -172,6 +173,11 @@ int adypt_tracer_sync(adypt_tracer *tracer);
 int adypt_tracer_primary_rays(adypt_tracer *tracer, float *rays, int memspace);
 /* per-tracer statistics since creation: traced path segments and kernel launches */
 int adypt_tracer_stats(adypt_tracer *tracer, uint64_t *segments, uint64_t *launches);
+
+/* Evaluates the shading stage's deterministic sin/cos (op 0: out = sin(x), out2 = cos(x)) or pow (op 1: out =
+ * pow(x, y)) ON THE GPU for n host values: lets tests check the CUDA copy of the recipe against the CPU oracle's
+ * bit for bit. Host pointers; y / out2 may be NULL when unused. */
+int adypt_debug_math(int32_t device, int32_t op, const float *x, const float *y, uint64_t n, float *out, float *out2);
 
 /* standalone EXR writer used by adypt_tracer_save_exr (rgb: width*height*3 floats) */
 int adypt_write_exr(const char *filename, const float *rgb, int32_t width, int32_t height, int32_t save_as_fp16);

@@ -43,6 +43,8 @@ def lib():
         l.oracle_sobol_at.argtypes = [C.c_uint32, C.c_uint32, vp]
         l.oracle_pt_render.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, C.POINTER(PTConfig), vp, i32, i32, vp, vp, vp, i32, i32]
         l.oracle_primary_view.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, i32]
+        l.oracle_det_sincos.argtypes = [vp, u64, vp, vp]
+        l.oracle_det_pow.argtypes = [vp, vp, u64, vp]
         _lib = l
     return _lib
 
@@ -169,4 +171,18 @@ def primary_view(bvh, origin, tmin, inv_proj, inv_view, width, height, vtype, nt
     nodes, ti, woop = _c(bvh.nodes, np.uint8), _c(bvh.tri_indices, np.int32), _c(bvh.woop, np.float32)
     tris, mats = _c(bvh.tris, np.uint8), _c(bvh.mats, np.uint8)
     lib().oracle_primary_view(_p(nodes), _p(ti), _p(woop), _p(tris), _p(mats), _p(ot), _p(ip), _p(iv), width, height, vtype, _p(out), nthreads)
+    return out
+
+
+def det_sincos(x):
+    x = _c(x, np.float32)
+    s, c = np.empty_like(x), np.empty_like(x)
+    lib().oracle_det_sincos(_p(x), x.size, _p(s), _p(c))
+    return s, c
+
+
+def det_pow(x, y):
+    x, y = _c(x, np.float32), _c(y, np.float32)
+    out = np.empty_like(x)
+    lib().oracle_det_pow(_p(x), _p(y), x.size, _p(out))
     return out

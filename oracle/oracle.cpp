@@ -29,6 +29,8 @@
 #include <thread>
 #include <vector>
 
+#include "detmath.h"
+
 namespace {
 
 // ---------------------------------------------------------------------------------------------
