@@ -34,6 +34,7 @@ EXPORTS = [
     "adypt_tracer_stats", "adypt_write_exr", "adypt_debug_math",
     "adypt_host_scene_load_obj", "adypt_host_scene_from_triangles", "adypt_host_scene_destroy", "adypt_host_scene_build_bvh",
     "adypt_host_scene_load_bvh", "adypt_host_scene_save_bvh", "adypt_host_scene_get", "adypt_host_scene_upload",
+    "adypt_config_set_default", "adypt_config_load", "adypt_config_to_json", "adypt_config_save",
 ]
 
 

@@ -55,7 +55,8 @@ __device__ __forceinline__ float dot3_fma(float ax, float ay, float az, const fl
 //    arrives as a kernel parameter so ptxas cannot fold it: folded, it becomes PRMT's immediate and the four
 //    selectors get re-materialised in registers for every use (45 IMAD.U32 per node step in profile r1a).
 //  * CVT: I2F.U8 with a byte selector: one instruction, but on the quarter-rate conversion pipe.
-// kCvtPlanes (0..6) of the six quantised planes use CVT, the rest MAGIC, to balance the pipes.
+// CVT_PLANES (0..6) of the six quantised planes use CVT, the rest MAGIC, to balance the pipes. Measured on B200
+// (profiles/r1_tuning.md): 2 CVT planes at 8 CTAs/SM (64 registers) is fastest; all-MAGIC and all-CVT both lose.
 template <int K>
 __device__ __forceinline__ float byte_to_float_magic(uint32_t word, uint32_t magic)
 {
@@ -110,7 +111,7 @@ __device__ __forceinline__ uint32_t test_children4(uint32_t meta4, uint32_t octi
 #undef ADYPT_CHILD
 }
 
-template <bool ANY, bool STATS = false, int CVT_PLANES = 0, int MIN_CTAS = 6>
+template <bool ANY, bool STATS = false, int CVT_PLANES = 2, int MIN_CTAS = 8>
 __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const TraceParams p)
 {
 	const uint32_t magic = p.magic;

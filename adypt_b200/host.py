@@ -19,6 +19,42 @@ class BvhConfig(C.Structure):
         return cls(max_spatial_depth, triangle_sah, node_sah)
 
 
+class CamConfig(C.Structure):
+    """InstanceConfig::Cam (src/InstanceConfig.hpp:30-35)."""
+    _fields_ = [("speed", C.c_float), ("mouse_sensitive", C.c_float), ("fov", C.c_float), ("yaw", C.c_float),
+                ("pitch", C.c_float), ("position", C.c_float * 3)]
+
+
+class InstanceConfig(C.Structure):
+    """InstanceConfig (src/InstanceConfig.hpp:12-48): the .config file."""
+    from . import PTConfig as _PT
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("bvh", BvhConfig), ("pt", _PT), ("cam", CamConfig),
+                ("obj_filename", C.c_char * 1024), ("bvh_filename", C.c_char * 1024)]
+
+    @classmethod
+    def default(cls):
+        c = cls()
+        _check(_lib().adypt_config_set_default(C.byref(c)))
+        return c
+
+    @classmethod
+    def load(cls, path: str):
+        """InstanceConfig::LoadFromFile; raises AdyptError carrying the reference's [PARSER]ERR text."""
+        c = cls()
+        _check(_lib().adypt_config_load(path.encode(), C.byref(c)))
+        return c
+
+    def to_json(self) -> str:
+        need = C.c_uint64(0)
+        _check(_lib().adypt_config_to_json(C.byref(self), None, 0, C.byref(need)))
+        buf = C.create_string_buffer(need.value)
+        _check(_lib().adypt_config_to_json(C.byref(self), buf, need.value, None))
+        return buf.value.decode()
+
+    def save(self, path: str):
+        _check(_lib().adypt_config_save(C.byref(self), path.encode()))
+
+
 class _Info(C.Structure):
     _fields_ = [("n_tris", C.c_uint32), ("n_mats", C.c_uint32), ("n_nodes", C.c_uint32), ("n_refs", C.c_uint32),
                 ("n_binary_nodes", C.c_uint32), ("triangles", C.c_void_p), ("materials", C.c_void_p), ("nodes", C.c_void_p),
@@ -43,6 +79,10 @@ def _lib():
         l.adypt_host_scene_upload.argtypes = [vp, C.c_int32, vp]
         for n in ("load_obj", "from_triangles", "destroy", "build_bvh", "load_bvh", "save_bvh", "get", "upload"):
             getattr(l, "adypt_host_scene_" + n).restype = C.c_int
+        l.adypt_config_set_default.argtypes = [vp]
+        l.adypt_config_load.argtypes = [C.c_char_p, vp]
+        l.adypt_config_to_json.argtypes = [vp, vp, C.c_uint64, vp]
+        l.adypt_config_save.argtypes = [vp, C.c_char_p]
         _bound = True
     return l
 

@@ -103,7 +103,7 @@ int adypt_trace_stats(adypt_scene *scene, const float *rays, uint64_t n, int mem
 /* number of kernel launches adypt_* calls have issued so far on this scene's device (bench accounting) */
 int adypt_launch_count(uint64_t *launches);
 /* tuning knobs of the persistent traversal kernel (0 = default): CTAs per SM, the refill threshold, and a
- * code-generation variant of the closest-hit kernel (0..5; same algorithm, identical results) */
+ * code-generation variant of the closest-hit kernel (0..7; same algorithm, identical results) */
 int adypt_trace_configure(adypt_scene *scene, int ctas_per_sm, int refill_threshold, int variant);
 
 /* ------------------------------------------------------------------------------------------------
@@ -222,6 +222,28 @@ int adypt_host_scene_save_bvh(adypt_host_scene *scene, const char *bvh_path, con
 int adypt_host_scene_get(adypt_host_scene *scene, adypt_host_scene_info *info);
 /* OglScene::Initialize(scene, wbvh) (Instance.cpp:33): uploads to `device`, Woop rows built on the GPU */
 int adypt_host_scene_upload(adypt_host_scene *scene, int32_t device, adypt_scene **out);
+
+/* ------------------------------------------------------------------------------------------------
+ * The .config instance file: InstanceConfig (src/InstanceConfig.hpp:12-48). Same JSON schema, the same
+ * acceptance rules (every key mandatory; "Float" values must be written as doubles -- 45.0, not 45 -- exactly
+ * as rapidjson's IsFloat demands, InstanceConfig.cpp:17-18) and the same PrettyWriter text on output. */
+typedef struct {
+	int32_t width, height;
+	adypt_bvh_config bvh;
+	adypt_pt_config pt;
+	struct {
+		float speed, mouse_sensitive, fov, yaw, pitch;
+		float position[3];
+	} cam;                    /* InstanceConfig::Cam (InstanceConfig.hpp:30-35) */
+	char obj_filename[1024];  /* scene.filename */
+	char bvh_filename[1024];  /* bvh.filename */
+} adypt_instance_config;
+
+int adypt_config_set_default(adypt_instance_config *config);                 /* InstanceConfig::SetDefault */
+int adypt_config_load(const char *path, adypt_instance_config *config);      /* InstanceConfig::LoadFromFile; the
+                                                 "[PARSER]ERR: ..." line the reference prints is in adypt_last_error() */
+int adypt_config_to_json(const adypt_instance_config *config, char *buf, uint64_t cap, uint64_t *needed); /* GetJson */
+int adypt_config_save(const adypt_instance_config *config, const char *path); /* InstanceConfig::SaveToFile */
 
 #ifdef __cplusplus
 }

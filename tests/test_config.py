@@ -1,0 +1,125 @@
+"""The .config instance file: our reader/writer against the reference's InstanceConfig compiled
+in place (oracle/_ref) -- same values, same accept/reject decisions (rapidjson's IsFloat quirk), same text."""
+import json
+
+import pytest
+
+from adypt_b200 import AdyptError, host
+
+GOOD = {
+    "width": 1920, "height": 1080,
+    "scene": {"filename": "models/city.obj"},
+    "pathTracer": {"invocationSize": 8, "stackSize": 12, "maxBounce": 5, "subpixel": 8, "tmpLifetime": 16,
+                   "rayTMin": 0.0001, "clamp": 4.0, "sun": [1.0, 0.9, 0.8]},
+    "bvh": {"filename": "models/city.bvh", "maxSpatialDepth": 48, "triangleSAH": 0.3, "nodeSAH": 1.0},
+    "camera": {"speed": 1.0, "mouseSensitive": 0.3, "fov": 45.0, "yaw": 7.0, "pitch": -31.0,
+               "position": [91.87, 24.98, 189.76]},
+}
+
+
+def write(tmp_path, obj, name="a.config"):
+    p = tmp_path / name
+    p.write_text(obj if isinstance(obj, str) else json.dumps(obj))
+    return str(p)
+
+
+def fields(c):
+    return (c.width, c.height, c.pt.invocation_size, c.pt.stack_size, c.pt.max_bounce, c.pt.subpixel, c.pt.tmp_lifetime,
+            c.pt.ray_tmin, c.pt.clamp, tuple(c.pt.sun), c.bvh.max_spatial_depth, c.bvh.triangle_sah, c.bvh.node_sah,
+            c.cam.speed, c.cam.mouse_sensitive, c.cam.fov, c.cam.yaw, c.cam.pitch, tuple(c.cam.position),
+            c.obj_filename, c.bvh_filename)
+
+
+def ref_fields(r):
+    return (r.width, r.height, r.invocation_size, r.stack_size, r.max_bounce, r.subpixel, r.tmp_lifetime, r.ray_tmin, r.clamp,
+            tuple(r.sun), r.max_spatial_depth, r.triangle_sah, r.node_sah, r.speed, r.mouse_sensitive, r.fov, r.yaw, r.pitch,
+            tuple(r.position), r.obj_filename, r.bvh_filename)
+
+
+def test_load_matches_reference(refmod, tmp_path):
+    p = write(tmp_path, GOOD)
+    assert fields(host.InstanceConfig.load(p)) == ref_fields(refmod.config_load(p))
+
+
+def test_written_text_is_identical_to_the_reference(refmod, tmp_path):
+    odd = json.loads(json.dumps(GOOD))
+    odd["pathTracer"]["rayTMin"] = 1e-7
+    odd["pathTracer"]["sun"] = [0.0, 123456789.0, 3.5e30]
+    odd["camera"]["position"] = [-0.5, 1e21, 2.5e-5]
+    odd["camera"]["yaw"] = 359.99
+    odd["scene"]["filename"] = 'dir with "quotes"\\and\ttab/x.obj'
+    for obj in (GOOD, odd):
+        p = write(tmp_path, obj)
+        ours = host.InstanceConfig.load(p).to_json()
+        theirs = refmod.config_roundtrip_json(p)  # InstanceConfig::GetJson of the same file
+        # Same layout, key order, escapes and number STYLE (fixed vs exponent, trailing .0). The digits are the
+        # shortest round-trip decimal here and rapidjson's Grisu2 there, which now and then ends in a different
+        # last digit (0.30000001192092896 vs ...898): both parse to the same double, so compare values exactly
+        # and texts with every number's digits masked.
+        assert json.loads(ours) == json.loads(theirs)
+        import re
+        mask = lambda t: re.sub(r"\d", "#", re.sub(r"(?<=\d)\d(?=[,\n e])", "#", t))
+        assert len(ours.splitlines()) == len(theirs.splitlines())
+        for a, b in zip(ours.splitlines(), theirs.splitlines()):
+            assert mask(a) == mask(b) and abs(len(a) - len(b)) <= 1, (a, b)
+            if not re.search(r"\d\.\d{8,}", a):
+                assert a == b
+        # and what we write loads back, in both programs, to the same values
+        q = str(tmp_path / "b.config")
+        host.InstanceConfig.load(p).save(q)
+        assert fields(host.InstanceConfig.load(q)) == ref_fields(refmod.config_load(q)) == fields(host.InstanceConfig.load(p))
+
+
+@pytest.mark.parametrize("mutate", [
+    lambda c: c["camera"].__setitem__("fov", 45),            # IsFloat quirk: an integer literal is NOT a Float
+    lambda c: c.__setitem__("width", 1280.0),                 # ... and a double is not a Uint
+    lambda c: c.__setitem__("width", -1),
+    lambda c: c["pathTracer"].__setitem__("sun", [1.0, 1.0]),
+    lambda c: c["pathTracer"].__setitem__("sun", [1, 1, 1]),
+    lambda c: c["scene"].__setitem__("filename", 5),
+    lambda c: c["pathTracer"].__setitem__("maxBounce", 4294967296),
+])
+def test_rejects_exactly_what_the_reference_rejects(refmod, tmp_path, mutate):
+    bad = json.loads(json.dumps(GOOD))
+    mutate(bad)
+    p = write(tmp_path, bad)
+    assert refmod.config_load(p) is None
+    with pytest.raises(AdyptError) as e:
+        host.InstanceConfig.load(p)
+    assert "[PARSER]ERR" in str(e.value)
+
+
+@pytest.mark.parametrize("mutate", [lambda c: c["bvh"].pop("nodeSAH"), lambda c: c.pop("camera")])
+def test_missing_keys_are_rejected_where_the_reference_aborts(tmp_path, mutate):
+    """Every key is mandatory. The reference indexes the missing member and dies in rapidjson's assertion
+    (document.h operator[]); we return the error the CHECK macro would have printed."""
+    bad = json.loads(json.dumps(GOOD))
+    mutate(bad)
+    with pytest.raises(AdyptError) as e:
+        host.InstanceConfig.load(write(tmp_path, bad))
+    assert "[PARSER]ERR: undefined" in str(e.value)
+
+
+@pytest.mark.parametrize("text", ["", "[1,2]", '{"width": }', "{", "nonsense"])
+def test_malformed_json_is_rejected(refmod, tmp_path, text):
+    p = write(tmp_path, text)
+    assert refmod.config_load(p) is None
+    with pytest.raises(AdyptError):
+        host.InstanceConfig.load(p)
+
+
+def test_accepts_float_spellings_like_the_reference(refmod, tmp_path):
+    txt = json.dumps(GOOD).replace('"fov": 45.0', '"fov": 4.5e1').replace('"clamp": 4.0', '"clamp": 4E0').replace('"yaw": 7.0', '"yaw": 700.0e-2')
+    p = write(tmp_path, txt)
+    assert fields(host.InstanceConfig.load(p)) == ref_fields(refmod.config_load(p))
+
+
+def test_defaults_match_instanceconfig_hpp():
+    c = host.InstanceConfig.default()
+    assert (c.width, c.height) == (1280, 720)
+    assert (c.pt.invocation_size, c.pt.stack_size, c.pt.max_bounce, c.pt.subpixel, c.pt.tmp_lifetime) == (8, 12, 5, 8, 16)
+    assert abs(c.pt.ray_tmin - 1e-4) < 1e-10 and c.pt.clamp == 4.0
+    assert (c.bvh.max_spatial_depth, c.bvh.node_sah) == (48, 1.0) and abs(c.bvh.triangle_sah - 0.3) < 1e-7
+    assert c.cam.fov == 45.0 and c.cam.speed == 1.0
+    with pytest.raises(AdyptError):
+        host.InstanceConfig.load("/nonexistent/x.config")
