@@ -14,6 +14,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libadypt_b200.so")
+BINDIR = os.path.join(HERE, "bin")
+CLI = os.path.join(BINDIR, "adypt_headless")
 
 CU_SOURCES = ["scene.cu", "tracer.cu"]
 CPP_SOURCES = ["hostmath.cpp", "exr.cpp", "host/bvh_build.cpp", "host/obj_loader.cpp", "host/host_api.cpp", "host/config.cpp"]
@@ -67,6 +69,13 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")
+    # headless CLI (replaces the GLFW/ImGui viewer): plain C++ over the C-ABI, finds the library next to itself
+    os.makedirs(BINDIR, exist_ok=True)
+    cli = ["g++", "-std=c++11", "-O2", "-Wall", "-I", os.path.join(HERE, "..", "include"), os.path.join(CSRC, "cli", "adypt_headless.cpp"),
+           "-o", CLI, "-L", LIBDIR, "-ladypt_b200", "-Wl,-rpath,$ORIGIN/../lib"]
+    r = subprocess.run(cli, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"CLI build failed:\n{r.stdout}")
     return LIB
 
 

@@ -1,0 +1,83 @@
+// Headless replacement for the reference's GLFW/ImGui viewer (src/main.cpp, src/Application.*): loads an Adypt
+// .config instance, renders N samples per pixel (or one AOV frame) on the GPU and writes an OpenEXR file.
+//
+//   adypt_headless scene.config [--spp N] [--out result.exr] [--fp16] [--seed S] [--device D]
+//                  [--viewer diffuse|specular|emissive|normal|position] [--per-frame] [--no-bvh-cache] [--keep-config]
+//
+// Same file formats as the reference (.config JSON, OBJ/MTL, .bvh cache); --spp/--seed/--out are new (the
+// reference renders until the user stops it and seeds from std::random_device).
+#include <chrono>
+#include <cstdlib>
+#include <cstring>
+#include "adypt_b200.hpp"
+
+using namespace adypt_b200;
+
+static int usage()
+{
+	fprintf(stderr, "usage: adypt_headless <instance.config> [--spp N] [--out file.exr] [--fp16] [--seed S] [--device D]\n"
+	                "                      [--viewer diffuse|specular|emissive|normal|position] [--per-frame] [--no-bvh-cache] [--keep-config]\n");
+	return 2;
+}
+
+int main(int argc, char **argv)
+{
+	if (argc < 2) return usage();
+	const char *config = nullptr, *out = "result.exr", *viewer = nullptr;
+	int spp = 64, device = 0;
+	bool fp16 = false, per_frame = false, cache = true, keep = false;
+	unsigned long long seed = 0;
+	for (int i = 1; i < argc; ++i) {
+		const char *a = argv[i];
+		auto next = [&]() -> const char * { return i + 1 < argc ? argv[++i] : ""; };
+		if (!strcmp(a, "--spp")) spp = atoi(next());
+		else if (!strcmp(a, "--out")) out = next();
+		else if (!strcmp(a, "--fp16")) fp16 = true;
+		else if (!strcmp(a, "--seed")) seed = strtoull(next(), nullptr, 10);
+		else if (!strcmp(a, "--device")) device = atoi(next());
+		else if (!strcmp(a, "--viewer")) viewer = next();
+		else if (!strcmp(a, "--per-frame")) per_frame = true; // one Trace(true) per sample, like the viewer's main loop
+		else if (!strcmp(a, "--no-bvh-cache")) cache = false;
+		else if (!strcmp(a, "--keep-config")) keep = true;    // do not rewrite the .config on exit
+		else if (a[0] == '-') return usage();
+		else config = a;
+	}
+	if (!config || spp < 0) return usage();
+
+	Instance instance;
+	instance.m_device = device;
+	instance.m_use_bvh_cache = cache;
+	instance.m_autosave = !keep;
+	instance.m_path_tracer.m_bias_seed = seed;
+	if (!instance.InitializeFromFile(config)) return 1;
+
+	instance.m_enable_pt_flag = false;
+	if (viewer) {
+		static const char *names[] = {"diffuse", "specular", "emissive", "radiance", "normal", "position"};
+		int t = -1;
+		for (int k = 0; k < 6; ++k)
+			if (!strcmp(viewer, names[k])) t = k;
+		if (t < 0 || t == 3) return usage();
+		instance.m_path_tracer.m_viewer_type = (CudaPathTracer::ViewerTypes)t;
+	}
+	instance.Update(); // sets the camera and renders the AOV frame, exactly like the viewer before "Start"
+	double seconds = 0.0;
+	if (!viewer) {
+		instance.m_enable_pt_flag = true;
+		const auto t0 = std::chrono::steady_clock::now();
+		if (per_frame)
+			for (int s = 0; s < spp; ++s) instance.Update(1);
+		else
+			instance.Update(spp);
+		instance.m_path_tracer.Sync();
+		seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+	}
+	instance.m_path_tracer.SaveResult(out, fp16);
+	uint64_t segments = 0, launches = 0;
+	adypt_tracer_stats(instance.m_path_tracer.Handle(), &segments, &launches);
+	const double samples = (double)instance.m_config.m_width * instance.m_config.m_height * instance.m_path_tracer.GetSPP();
+	printf("{\"spp\": %d, \"width\": %d, \"height\": %d, \"seconds\": %.6f, \"samples_per_s\": %.1f, \"segments\": %llu, \"launches\": %llu, \"out\": \"%s\"}\n",
+	       instance.m_path_tracer.GetSPP(), instance.m_config.m_width, instance.m_config.m_height, seconds,
+	       seconds > 0 ? samples / seconds : 0.0, (unsigned long long)segments, (unsigned long long)launches, out);
+	return 0;
+}

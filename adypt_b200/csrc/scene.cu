@@ -153,6 +153,8 @@ static void free_scene(adypt_scene *s)
 	cudaFree(s->d_counters);
 	s->stage_in.release();
 	s->stage_out.release();
+	for (int i = 0; i < 3; ++i)
+		if (s->pipe[i]) cudaStreamDestroy(s->pipe[i]);
 	delete s;
 }
 
@@ -293,27 +295,42 @@ int adypt_trace_configure(adypt_scene *s, int ctas_per_sm, int refill_threshold,
 	return ADYPT_OK;
 }
 
-static int trace_host(adypt_scene *s, const float *rays, uint64_t n, int32_t *tri, float *t, float *uv, uint8_t *occ, cudaStream_t stream)
+static int trace_host(adypt_scene *s, const float *rays, uint64_t n, int32_t *tri, float *t, float *uv, uint8_t *occ, cudaStream_t user_stream)
 {
-	// host arrays: stage through device buffers owned by the scene; returns with results in place
+	// Host arrays: the batch is cut into chunks that flow through three internal streams, so the H2D copy of
+	// chunk i+1, the traversal of chunk i and the D2H copy of chunk i-1 overlap (PCIe is full duplex). With
+	// pinned host memory the whole call is bound by the 32 B/ray upload; pageable memory still works, just
+	// without the overlap. Returns when every result is in the caller's arrays.
 	const size_t in_bytes = (size_t)n * 32u;
 	const size_t o_tri = 0, o_t = o_tri + (size_t)n * 4u, o_uv = o_t + (size_t)n * 4u, o_occ = o_uv + (size_t)n * 8u;
 	const size_t out_bytes = o_occ + (size_t)n;
 	ADYPT_TRY(s->stage_in.reserve(in_bytes));
 	ADYPT_TRY(s->stage_out.reserve(out_bytes));
+	if (!s->pipe[0])
+		for (int i = 0; i < 3; ++i) ADYPT_CUDA(cudaStreamCreateWithFlags(&s->pipe[i], cudaStreamNonBlocking));
+	ADYPT_CUDA(cudaStreamSynchronize(user_stream)); // earlier work queued by the caller on its stream comes first
 	uint8_t *o = s->stage_out.as<uint8_t>();
-	ADYPT_CUDA(cudaMemcpyAsync(s->stage_in.ptr, rays, in_bytes, cudaMemcpyHostToDevice, stream));
-	if (occ) {
-		ADYPT_TRY(launch_trace(s, s->stage_in.as<float4>(), n, nullptr, nullptr, nullptr, o + o_occ, stream));
-		ADYPT_CUDA(cudaMemcpyAsync(occ, o + o_occ, (size_t)n, cudaMemcpyDeviceToHost, stream));
-	} else {
-		ADYPT_TRY(launch_trace(s, s->stage_in.as<float4>(), n, (int32_t *)(o + o_tri), t ? (float *)(o + o_t) : nullptr,
-		                       uv ? (float2 *)(o + o_uv) : nullptr, nullptr, stream));
-		ADYPT_CUDA(cudaMemcpyAsync(tri, o + o_tri, (size_t)n * 4u, cudaMemcpyDeviceToHost, stream));
-		if (t) ADYPT_CUDA(cudaMemcpyAsync(t, o + o_t, (size_t)n * 4u, cudaMemcpyDeviceToHost, stream));
-		if (uv) ADYPT_CUDA(cudaMemcpyAsync(uv, o + o_uv, (size_t)n * 8u, cudaMemcpyDeviceToHost, stream));
+	const uint64_t chunk = 1u << 20;
+	int k = 0;
+	for (uint64_t b = 0; b < n; b += chunk, ++k) {
+		const uint64_t m = (n - b < chunk) ? n - b : chunk;
+		cudaStream_t st = s->pipe[k % 3];
+		float4 *d_in = s->stage_in.as<float4>() + 2 * b;
+		ADYPT_CUDA(cudaMemcpyAsync(d_in, rays + 8 * b, (size_t)m * 32u, cudaMemcpyHostToDevice, st));
+		if (occ) {
+			ADYPT_TRY(launch_trace(s, d_in, m, nullptr, nullptr, nullptr, o + o_occ + b, st));
+			ADYPT_CUDA(cudaMemcpyAsync(occ + b, o + o_occ + b, (size_t)m, cudaMemcpyDeviceToHost, st));
+		} else {
+			int32_t *d_tri = (int32_t *)(o + o_tri) + b;
+			float *d_t = t ? (float *)(o + o_t) + b : nullptr;
+			float2 *d_uv = uv ? (float2 *)(o + o_uv) + b : nullptr;
+			ADYPT_TRY(launch_trace(s, d_in, m, d_tri, d_t, d_uv, nullptr, st));
+			ADYPT_CUDA(cudaMemcpyAsync(tri + b, d_tri, (size_t)m * 4u, cudaMemcpyDeviceToHost, st));
+			if (t) ADYPT_CUDA(cudaMemcpyAsync(t + b, d_t, (size_t)m * 4u, cudaMemcpyDeviceToHost, st));
+			if (uv) ADYPT_CUDA(cudaMemcpyAsync(uv + 2 * b, d_uv, (size_t)m * 8u, cudaMemcpyDeviceToHost, st));
+		}
 	}
-	ADYPT_CUDA(cudaStreamSynchronize(stream));
+	for (int i = 0; i < 3; ++i) ADYPT_CUDA(cudaStreamSynchronize(s->pipe[i]));
 	return ADYPT_OK;
 }
 

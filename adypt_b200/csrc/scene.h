@@ -19,6 +19,7 @@ struct adypt_scene {
 	int variant = 0;           // code-generation variant of the closest-hit kernel (tuning only)
 	int occ_closest = 0, occ_any = 0;
 	adypt::DeviceBuffer stage_in, stage_out; // staging for host-pointer batch calls
+	cudaStream_t pipe[3] = {nullptr, nullptr, nullptr}; // copy/compute pipeline of host-pointer batch calls
 	uint64_t device_bytes = 0;
 };
 

@@ -35,13 +35,13 @@ def log(*a):
     print("[bench]", *a, file=sys.stderr, flush=True)
 
 
-def build_inputs():
+def build_inputs(mixed=False):
     """C2 scene arrays from the product's own host stages (adypt_b200.host): Triangle[] assembly and the
     from-scratch SBVH -> CWBVH builder, byte-identical to the reference's src/BVH pipeline (tests/
     test_host_builder.py). The node/index arrays are cached in the reference's own .bvh format
     (WideBVH.cpp:9-66), as Instance::Initialize does (Instance.cpp:19-31). Nothing here touches oracle/."""
     from adypt_b200 import host
-    mesh = W.city(CELLS, SCENE_SEED)
+    mesh = W.city(CELLS, SCENE_SEED, mixed_materials=mixed)
     hs = host.HostScene.from_triangles(mesh.positions(), mesh.face_mat, host.materials_array(mesh.materials))
     os.makedirs(CACHE, exist_ok=True)
     bvh_path = os.path.join(CACHE, mesh.name + ".bvh")
@@ -234,7 +234,7 @@ def run_native(args, rank, world, local_rank):
     clocks = sampler.stop()
     assert torch.equal(h_tri.to(dev), d_tri), "host-path results differ from device-path results"
     e2e = {"value": world * n / float(e2e_s.item()) / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(n * 32), "d2h_bytes_per_step": int(n * 16),
-           "how": "adypt_trace_closest(ADYPT_MEM_HOST) on pinned host arrays, wall clock around K blocking calls"}
+           "how": "adypt_trace_closest(ADYPT_MEM_HOST) on pinned host arrays (1M-ray chunks pipelined over 3 streams), wall clock around K blocking calls"}
 
     # ---- roofline of the dominant (only) kernel in the step
     st = scene.trace_stats(d_rays)
@@ -260,6 +260,8 @@ def run_native(args, rank, world, local_rank):
            "data": "synthetic", "config": workload_config(n, {"triangles": int(mesh.n_tris), "parallelism": f"{world} independent ray batches (one per GPU), no collective"}),
            "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks,
            "target": {"Mrays/s": 1500.0, "met": value / world >= 1500.0}}
+    if not args.no_aux:
+        out["aux"] = path_tracer_aux(A, torch, dist, local_rank, world)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cb, counters, ns = cpu_leg(bvh, rays)
         out["cpu_baseline"] = cb
@@ -272,6 +274,36 @@ def run_native(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def path_tracer_aux(A, torch, dist, local_rank, world):
+    """Second half of BASELINE.json's metric: 1080p path samples/s (configs[2], "C3"): the same city with
+    glossy / mirror / glass / emissive boxes, 1920x1080, maxBounce 5 (4 bounces), 64 spp, no Russian roulette
+    (the reference has none). Each rank renders the full image (weak scaling); wall clock around sample()+sync."""
+    mesh, hs = build_inputs(mixed=True)
+    scene = hs.upload(local_rank)
+    w, h, spp = 1920, 1080, 64
+    tr = A.Tracer(scene, A.PTConfig.make(sun=(1.0, 1.0, 1.0)), w, h, bias_seed=7)
+    cam = W.city_camera(CELLS)
+    tr.look(cam["position"], cam["yaw"], cam["pitch"], cam["fov"])
+    tr.sample(16)
+    tr.sync()
+    tr.primary(0)
+    s0 = tr.stats()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    tr.sample(spp)
+    tr.sync()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=torch.device("cuda", local_rank))
+    if dist is not None:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    dt = float(dt.item())
+    s1 = tr.stats()
+    seg = s1["segments"] - s0["segments"]
+    return {"workload": "C3: 1920x1080, 64 spp, maxBounce 5, mixed-material 1M-tri city, wavefront path tracer",
+            "path_samples_per_s": world * w * h * spp / dt, "path_segments_per_s": world * seg / dt, "segments_per_sample": seg / (w * h * spp),
+            "seconds": dt, "gpu_launches": s1["launches"] - s0["launches"], "scaling": "weak"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -279,6 +311,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-aux", action="store_true", help="skip the 1080p path-tracing measurement")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
