@@ -43,7 +43,8 @@ def test_cli_render_matches_api_and_oracle(A, cpu, tmp_path):
     r = subprocess.run([CLI, path, "--spp", "24", "--seed", "7", "--out", out], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "[INSTANCE]Info: Initialized from" in r.stdout and "[PT]INFO: Saved image to" in r.stdout
-    info = json.loads(r.stdout.strip().splitlines()[-1])
+    info = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    assert "[INSTANCE]Info: " + path + " saved" in r.stdout  # the destructor rewrites the .config (Instance.cpp:83-86)
     assert info["spp"] == 24 and info["samples_per_s"] > 0
     assert os.path.exists(str(tmp_path / "clicity.bvh"))  # cache written like Instance.cpp:25
     img = read_exr(out)
