@@ -109,7 +109,7 @@ int launch_trace(adypt_scene *s, const float4 *d_rays, uint64_t n, int32_t *d_tr
 	p.magic = 0x4B000000u;
 	p.counter = s->d_counters + (s->counter_cursor++ % kCounterRing);
 	p.refill_threshold = s->refill_threshold > 0 ? s->refill_threshold : 28;
-	int per_sm = s->ctas_per_sm > 0 ? s->ctas_per_sm : (any ? s->occ_any : ((s->variant == 1 || s->variant == 7) ? 6 : s->occ_closest));
+	int per_sm = s->ctas_per_sm > 0 ? s->ctas_per_sm : (any ? s->occ_any : ((s->variant == 1 || s->variant == 7 || s->variant == 9) ? 6 : s->occ_closest));
 	if (per_sm < 1) per_sm = 1;
 	unsigned long long warps_needed = (n + 31) / 32;
 	unsigned long long ctas_needed = (warps_needed + (kTraceBlock / 32) - 1) / (kTraceBlock / 32);
@@ -125,6 +125,8 @@ int launch_trace(adypt_scene *s, const float4 *d_rays, uint64_t n, int32_t *d_tr
 	case 5: trace_kernel<false, false, 4, 8><<<grid, kTraceBlock, 0, stream>>>(p); break;
 	case 6: trace_kernel<false, false, 6, 8><<<grid, kTraceBlock, 0, stream>>>(p); break;
 	case 7: trace_kernel<false, false, 2, 6><<<grid, kTraceBlock, 0, stream>>>(p); break;
+	case 8: trace_kernel<false, false, 2, 8, true><<<grid, kTraceBlock, 0, stream>>>(p); break;
+	case 9: trace_kernel<false, false, 2, 6, true><<<grid, kTraceBlock, 0, stream>>>(p); break;
 	default: trace_kernel<false><<<grid, kTraceBlock, 0, stream>>>(p); break;
 	}
 	count_launch();
@@ -288,7 +290,7 @@ int adypt_scene_device_bytes(adypt_scene *s, uint64_t *bytes)
 int adypt_trace_configure(adypt_scene *s, int ctas_per_sm, int refill_threshold, int variant)
 {
 	if (!s) return fail(ADYPT_EINVAL, "scene is NULL");
-	if (ctas_per_sm < 0 || refill_threshold < 0 || refill_threshold > 32 || variant < 0 || variant > 7) return fail(ADYPT_EINVAL, "bad tuning value");
+	if (ctas_per_sm < 0 || refill_threshold < 0 || refill_threshold > 32 || variant < 0 || variant > 9) return fail(ADYPT_EINVAL, "bad tuning value");
 	s->ctas_per_sm = ctas_per_sm;
 	s->refill_threshold = refill_threshold;
 	s->variant = variant;
