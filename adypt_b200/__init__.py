@@ -24,7 +24,8 @@ VIEW_DIFFUSE, VIEW_SPECULAR, VIEW_EMISSIVE, VIEW_RADIANCE, VIEW_NORMAL, VIEW_POS
 
 # every symbol include/adypt_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
-    "adypt_last_error", "adypt_version", "adypt_device_count", "adypt_scene_create", "adypt_scene_destroy",
+    "adypt_last_error", "adypt_version", "adypt_device_count", "adypt_scene_create", "adypt_scene_destroy", "adypt_scene_set_textures",
+    "adypt_host_scene_load_textures", "adypt_host_scene_texture",
     "adypt_scene_read_woop", "adypt_scene_device_bytes", "adypt_trace_closest", "adypt_trace_any", "adypt_trace_stats", "adypt_launch_count",
     "adypt_trace_configure", "adypt_tracer_create", "adypt_tracer_destroy", "adypt_tracer_set_config",
     "adypt_tracer_set_bias", "adypt_tracer_get_bias", "adypt_tracer_set_camera", "adypt_camera_matrices",
@@ -48,6 +49,10 @@ class SceneDesc(C.Structure):
     _fields_ = [("device", C.c_int32), ("nodes", C.c_void_p), ("n_nodes", C.c_uint32), ("tri_indices", C.c_void_p),
                 ("n_refs", C.c_uint32), ("woop", C.c_void_p), ("triangles", C.c_void_p), ("n_tris", C.c_uint32),
                 ("materials", C.c_void_p), ("n_mats", C.c_uint32)]
+
+
+class TextureDesc(C.Structure):
+    _fields_ = [("rgb8", C.c_void_p), ("width", C.c_int32), ("height", C.c_int32)]
 
 
 class PTConfig(C.Structure):
@@ -79,6 +84,7 @@ def load_library():
         "adypt_device_count": [vp],
         "adypt_scene_create": [C.POINTER(SceneDesc), vp],
         "adypt_scene_destroy": [vp],
+        "adypt_scene_set_textures": [vp, vp, C.c_uint32],
         "adypt_scene_read_woop": [vp, vp],
         "adypt_scene_device_bytes": [vp, vp],
         "adypt_trace_closest": [vp, vp, u64, vp, vp, vp, C.c_int, vp],
@@ -215,6 +221,15 @@ class Scene:
             self._h = None
 
     __del__ = close
+
+    def set_textures(self, textures):
+        """Diffuse textures (list of (h,w,3) uint8 arrays); texture i is what material.dtex == i refers to."""
+        arrs = [np.ascontiguousarray(t, dtype=np.uint8) for t in textures]
+        descs = (TextureDesc * max(1, len(arrs)))()
+        for i, a in enumerate(arrs):
+            assert a.ndim == 3 and a.shape[2] == 3
+            descs[i] = TextureDesc(a.ctypes.data, a.shape[1], a.shape[0])
+        _check(load_library().adypt_scene_set_textures(self._h, descs, len(arrs)))
 
     def read_woop(self):
         out = np.zeros((self.n_refs, 12), dtype=np.float32)

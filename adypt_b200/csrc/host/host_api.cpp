@@ -128,6 +128,52 @@ int adypt_host_scene_get(adypt_host_scene *s, adypt_host_scene_info *o)
 	return ADYPT_OK;
 }
 
+int adypt_host_scene_load_textures(adypt_host_scene *s, uint32_t *n_loaded, uint32_t *n_failed)
+{
+	if (!s) return fail(ADYPT_EINVAL, "scene is NULL");
+	uint32_t ok = 0, bad = 0;
+	if (!s->textures_loaded) {
+		// OglScene::init_materials walks the materials in order; load_texture caches successes by file name and
+		// returns -1 for a file that fails (every time it is asked for again)
+		std::vector<int> index_of(s->diffuse_textures.size(), -2); // -2 = not tried yet
+		for (Material &m : s->mats) {
+			if (m.dtex < 0 || (size_t)m.dtex >= s->diffuse_textures.size()) continue;
+			int &slot = index_of[(size_t)m.dtex];
+			if (slot == -2) {
+				DecodedImage img;
+				if (decode_image_file(s->diffuse_textures[(size_t)m.dtex].c_str(), &img)) {
+					printf("[SCENE]Info: Loaded texture %s\n", s->diffuse_textures[(size_t)m.dtex].c_str());
+					s->textures.push_back(std::move(img));
+					slot = (int)s->textures.size() - 1;
+				} else {
+					printf("[SCENE]Err: Unable to load texture %s\n", s->diffuse_textures[(size_t)m.dtex].c_str());
+					slot = -1;
+				}
+			}
+			m.dtex = slot;
+		}
+		for (int v : index_of) {
+			if (v >= 0) ++ok;
+			else if (v == -1) ++bad;
+		}
+		s->textures_loaded = true;
+	} else
+		ok = (uint32_t)s->textures.size();
+	if (n_loaded) *n_loaded = ok;
+	if (n_failed) *n_failed = bad;
+	return ADYPT_OK;
+}
+
+int adypt_host_scene_texture(adypt_host_scene *s, uint32_t i, const uint8_t **rgb8, int32_t *width, int32_t *height)
+{
+	if (!s || !rgb8 || !width || !height) return fail(ADYPT_EINVAL, "NULL argument");
+	if (i >= s->textures.size()) return fail(ADYPT_EINVAL, "texture index out of range");
+	*rgb8 = s->textures[i].rgb.data();
+	*width = s->textures[i].width;
+	*height = s->textures[i].height;
+	return ADYPT_OK;
+}
+
 int adypt_host_scene_upload(adypt_host_scene *s, int32_t device, adypt_scene **out)
 {
 	if (!s || !out) return fail(ADYPT_EINVAL, "NULL argument");
@@ -144,7 +190,20 @@ int adypt_host_scene_upload(adypt_host_scene *s, int32_t device, adypt_scene **o
 	d.n_tris = (uint32_t)s->tris.size();
 	d.materials = s->mats.empty() ? nullptr : s->mats.data();
 	d.n_mats = (uint32_t)s->mats.size();
-	return adypt_scene_create(&d, out);
+	// textures named by the materials but never loaded: the scene then behaves like a reference build with
+	// TEXTURE_COUNT == 0 (Material::dtex is ignored by the kernels when no texture was uploaded)
+	ADYPT_TRY(adypt_scene_create(&d, out));
+	if (!s->textures.empty()) {
+		std::vector<adypt_texture> tx(s->textures.size());
+		for (size_t i = 0; i < tx.size(); ++i) tx[i] = adypt_texture{s->textures[i].rgb.data(), s->textures[i].width, s->textures[i].height};
+		const int rc = adypt_scene_set_textures(*out, tx.data(), (uint32_t)tx.size());
+		if (rc != ADYPT_OK) {
+			adypt_scene_destroy(*out);
+			*out = nullptr;
+			return rc;
+		}
+	}
+	return ADYPT_OK;
 }
 
 } // extern "C"

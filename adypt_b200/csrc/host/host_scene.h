@@ -4,10 +4,23 @@
 #include <vector>
 #include "bvh_build.h"
 
+namespace adypt {
+namespace host {
+struct DecodedImage { // RGB8, top row first (what stbi_load(..., 3) returns)
+	int width = 0, height = 0;
+	std::vector<uint8_t> rgb;
+};
+// PNG / TGA file -> RGB8; false when the file is missing or in a format that is not decoded
+bool decode_image_file(const char *path, DecodedImage *out);
+} // namespace host
+} // namespace adypt
+
 struct adypt_host_scene {
 	std::vector<adypt::Triangle> tris;
 	std::vector<adypt::Material> mats;
-	std::vector<std::string> diffuse_textures; // deduplicated names, index = Material::dtex
+	std::vector<std::string> diffuse_textures; // deduplicated names, index = Material::dtex (before textures are loaded)
+	std::vector<adypt::host::DecodedImage> textures; // after adypt_host_scene_load_textures: index = Material::dtex
+	bool textures_loaded = false;
 	adypt::host::Box box;
 	adypt::host::BinaryBvh binary;
 	adypt::host::WideBvh wide;

@@ -1,0 +1,218 @@
+// Texture file decoding for diffuse maps (map_Kd): the stand-in for stbi_load(filename, &w, &h, &n, 3) as
+// OglScene::load_texture calls it (src/Tracer/OglScene.cpp:12-43). Output: tightly packed RGB8, top row first.
+// Formats: PNG (all colour types and bit depths, Adam7 interlace; zlib does the inflate) and TGA (true-colour
+// 24/32 bpp and 8-bit grey, raw or RLE, either origin). Conversions to 3 channels follow stb_image's rules
+// (grey replicated, alpha dropped, 16-bit samples truncated to their high byte, 1/2/4-bit grey scaled by
+// 255/85/17). JPEG/BMP/PSD/GIF/HDR are not decoded: such a texture fails to load, which the reference
+// handles by giving the material texture index -1 (OglScene.cpp:27-32).
+#include <zlib.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "host_scene.h"
+
+namespace adypt {
+namespace host {
+
+namespace {
+
+bool read_file(const char *path, std::vector<uint8_t> *out)
+{
+	FILE *f = fopen(path, "rb");
+	if (!f) return false;
+	uint8_t buf[1 << 16];
+	size_t n;
+	while ((n = fread(buf, 1, sizeof(buf), f)) > 0) out->insert(out->end(), buf, buf + n);
+	fclose(f);
+	return true;
+}
+
+inline uint32_t be32(const uint8_t *p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
+
+inline int paeth(int a, int b, int c)
+{
+	const int p = a + b - c, pa = abs(p - a), pb = abs(p - b), pc = abs(p - c);
+	if (pa <= pb && pa <= pc) return a;
+	return pb <= pc ? b : c;
+}
+
+// undo PNG filtering of one (sub)image in place; returns false on a bad filter byte
+bool unfilter(uint8_t *data, uint32_t rows, size_t row_bytes, int bpp)
+{
+	const size_t stride = row_bytes + 1;
+	for (uint32_t y = 0; y < rows; ++y) {
+		uint8_t *cur = data + y * stride + 1;
+		const uint8_t *prev = y ? data + (y - 1) * stride + 1 : nullptr;
+		const int ft = data[y * stride];
+		for (size_t i = 0; i < row_bytes; ++i) {
+			const int a = i >= (size_t)bpp ? cur[i - bpp] : 0, b = prev ? prev[i] : 0, c = (prev && i >= (size_t)bpp) ? prev[i - bpp] : 0;
+			int v = cur[i];
+			switch (ft) {
+			case 0: break;
+			case 1: v += a; break;
+			case 2: v += b; break;
+			case 3: v += (a + b) >> 1; break;
+			case 4: v += paeth(a, b, c); break;
+			default: return false;
+			}
+			cur[i] = (uint8_t)v;
+		}
+	}
+	return true;
+}
+
+bool decode_png(const std::vector<uint8_t> &file, DecodedImage *img)
+{
+	static const uint8_t sig[8] = {137, 80, 78, 71, 13, 10, 26, 10};
+	if (file.size() < 33 || memcmp(file.data(), sig, 8) != 0) return false;
+	size_t pos = 8;
+	uint32_t w = 0, h = 0;
+	int depth = 0, ctype = 0, interlace = 0;
+	std::vector<uint8_t> idat, palette;
+	bool seen_ihdr = false;
+	while (pos + 12 <= file.size()) {
+		const uint32_t len = be32(&file[pos]);
+		const uint8_t *type = &file[pos + 4], *body = &file[pos + 8];
+		if (pos + 12 + (size_t)len > file.size()) return false;
+		if (!memcmp(type, "IHDR", 4)) {
+			if (len != 13) return false;
+			w = be32(body);
+			h = be32(body + 4);
+			depth = body[8];
+			ctype = body[9];
+			interlace = body[12];
+			if (body[10] != 0 || body[11] != 0 || interlace > 1) return false;
+			seen_ihdr = true;
+		} else if (!memcmp(type, "PLTE", 4)) palette.assign(body, body + len);
+		else if (!memcmp(type, "IDAT", 4)) idat.insert(idat.end(), body, body + len);
+		else if (!memcmp(type, "IEND", 4)) break;
+		pos += 12 + (size_t)len;
+	}
+	if (!seen_ihdr || w == 0 || h == 0 || w > (1u << 24) || h > (1u << 24)) return false;
+	int channels;
+	switch (ctype) {
+	case 0: channels = 1; break;
+	case 2: channels = 3; break;
+	case 3: channels = 1; break;
+	case 4: channels = 2; break;
+	case 6: channels = 4; break;
+	default: return false;
+	}
+	if (!(depth == 8 || depth == 16 || ((ctype == 0 || ctype == 3) && (depth == 1 || depth == 2 || depth == 4)))) return false;
+	if (ctype == 3 && (depth == 16 || palette.empty())) return false;
+	const int bits_pp = channels * depth, bpp = (bits_pp + 7) / 8;
+
+	// pass geometry: one pass for plain images, seven for Adam7
+	struct Pass { uint32_t x0, y0, dx, dy, w, h; size_t row_bytes, offset; };
+	std::vector<Pass> passes;
+	size_t total = 0;
+	if (!interlace) passes.push_back(Pass{0, 0, 1, 1, w, h, 0, 0});
+	else {
+		static const uint32_t X0[7] = {0, 4, 0, 2, 0, 1, 0}, Y0[7] = {0, 0, 4, 0, 2, 0, 1}, DX[7] = {8, 8, 4, 4, 2, 2, 1}, DY[7] = {8, 8, 8, 4, 4, 2, 2};
+		for (int p = 0; p < 7; ++p) {
+			const uint32_t pw = (w - X0[p] + DX[p] - 1) / DX[p], ph = (h - Y0[p] + DY[p] - 1) / DY[p];
+			if (w > X0[p] && h > Y0[p] && pw && ph) passes.push_back(Pass{X0[p], Y0[p], DX[p], DY[p], pw, ph, 0, 0});
+		}
+	}
+	for (Pass &p : passes) {
+		p.row_bytes = ((size_t)p.w * bits_pp + 7) / 8;
+		p.offset = total;
+		total += (p.row_bytes + 1) * p.h;
+	}
+	std::vector<uint8_t> raw(total);
+	uLongf got = (uLongf)total;
+	const int zr = uncompress(raw.data(), &got, idat.data(), (uLong)idat.size());
+	if ((zr != Z_OK && zr != Z_BUF_ERROR) || got < total) return false;
+
+	img->width = (int)w;
+	img->height = (int)h;
+	img->rgb.assign((size_t)w * h * 3, 0);
+	for (const Pass &p : passes) {
+		uint8_t *d = raw.data() + p.offset;
+		if (!unfilter(d, p.h, p.row_bytes, bpp)) return false;
+		for (uint32_t y = 0; y < p.h; ++y) {
+			const uint8_t *row = d + y * (p.row_bytes + 1) + 1;
+			for (uint32_t x = 0; x < p.w; ++x) {
+				uint8_t s[4] = {0, 0, 0, 0}; // up to four 8-bit samples of this pixel
+				if (depth == 8) for (int c = 0; c < channels; ++c) s[c] = row[(size_t)x * channels + c];
+				else if (depth == 16) for (int c = 0; c < channels; ++c) s[c] = row[((size_t)x * channels + c) * 2]; // high byte
+				else {
+					const size_t bit = (size_t)x * depth;
+					const int v = (row[bit >> 3] >> (8 - depth - (bit & 7))) & ((1 << depth) - 1);
+					s[0] = (uint8_t)(ctype == 3 ? v : v * (depth == 1 ? 255 : depth == 2 ? 85 : 17));
+				}
+				uint8_t *o = &img->rgb[(((size_t)p.y0 + (size_t)y * p.dy) * w + p.x0 + (size_t)x * p.dx) * 3];
+				if (ctype == 3) {
+					const size_t i = (size_t)s[0] * 3;
+					if (i + 2 >= palette.size()) return false;
+					o[0] = palette[i]; o[1] = palette[i + 1]; o[2] = palette[i + 2];
+				} else if (channels <= 2) o[0] = o[1] = o[2] = s[0];
+				else { o[0] = s[0]; o[1] = s[1]; o[2] = s[2]; }
+			}
+		}
+	}
+	return true;
+}
+
+bool decode_tga(const std::vector<uint8_t> &f, DecodedImage *img)
+{
+	if (f.size() < 18) return false;
+	const int id_len = f[0], cmap_type = f[1], type = f[2];
+	const int w = f[12] | (f[13] << 8), h = f[14] | (f[15] << 8), bpp = f[16], desc = f[17];
+	const bool rle = type == 10 || type == 11, grey = type == 3 || type == 11;
+	if (cmap_type != 0 || !(type == 2 || type == 3 || type == 10 || type == 11)) return false; // colour-mapped TGAs not handled
+	if (w <= 0 || h <= 0 || !((grey && bpp == 8) || (!grey && (bpp == 24 || bpp == 32)))) return false;
+	const int nb = bpp / 8;
+	size_t pos = 18 + (size_t)id_len;
+	img->width = w;
+	img->height = h;
+	img->rgb.assign((size_t)w * h * 3, 0);
+	const size_t npix = (size_t)w * h;
+	uint8_t px[4] = {0, 0, 0, 0};
+	size_t i = 0;
+	int run = 0;
+	bool run_is_rle = false;
+	while (i < npix) {
+		bool read_pixel = true;
+		if (rle) {
+			if (run == 0) {
+				if (pos >= f.size()) return false;
+				const int c = f[pos++];
+				run = 1 + (c & 127);
+				run_is_rle = (c & 128) != 0;
+			} else if (run_is_rle)
+				read_pixel = false;
+		}
+		if (read_pixel) {
+			if (pos + (size_t)nb > f.size()) return false;
+			memcpy(px, &f[pos], (size_t)nb);
+			pos += (size_t)nb;
+		}
+		const size_t y = i / (size_t)w, x = i % (size_t)w;
+		const size_t yy = (desc & 0x20) ? y : (size_t)h - 1 - y; // bit 5 set = top-left origin
+		const size_t xx = (desc & 0x10) ? (size_t)w - 1 - x : x;
+		uint8_t *o = &img->rgb[(yy * (size_t)w + xx) * 3];
+		if (grey) o[0] = o[1] = o[2] = px[0];
+		else { o[0] = px[2]; o[1] = px[1]; o[2] = px[0]; } // BGR(A) on disk
+		++i;
+		if (rle) --run;
+	}
+	return true;
+}
+
+} // namespace
+
+bool decode_image_file(const char *path, DecodedImage *img)
+{
+	std::vector<uint8_t> file;
+	if (!read_file(path, &file)) return false;
+	if (decode_png(file, img)) return true;
+	const size_t n = strlen(path);
+	if (n > 4 && (!strcmp(path + n - 4, ".tga") || !strcmp(path + n - 4, ".TGA"))) return decode_tga(file, img); // TGA has no magic number
+	return false;
+}
+
+} // namespace host
+} // namespace adypt

@@ -3,6 +3,7 @@
 #include "traverse.cuh"
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 namespace adypt {
 
@@ -152,6 +153,8 @@ static void free_scene(adypt_scene *s)
 	cudaFree(s->d_tri_indices);
 	cudaFree(s->d_tris);
 	cudaFree(s->d_mats);
+	cudaFree(s->d_texels);
+	cudaFree(s->d_tex_table);
 	cudaFree(s->d_counters);
 	s->stage_in.release();
 	s->stage_out.release();
@@ -262,6 +265,45 @@ int adypt_scene_create(const adypt_scene_desc *d, adypt_scene **out)
 	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->occ_closest, trace_kernel<false>, kTraceBlock, 0);
 	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->occ_any, trace_kernel<true>, kTraceBlock, 0);
 	*out = s;
+	return ADYPT_OK;
+}
+
+int adypt_scene_set_textures(adypt_scene *s, const adypt_texture *tex, uint32_t n)
+{
+	if (!s || (n && !tex)) return fail(ADYPT_EINVAL, "NULL argument");
+	DeviceGuard g(s->device);
+	ADYPT_CUDA(cudaDeviceSynchronize());
+	cudaFree(s->d_texels);
+	cudaFree(s->d_tex_table);
+	s->d_texels = nullptr;
+	s->d_tex_table = nullptr;
+	s->n_textures = 0;
+	if (n == 0) return ADYPT_OK;
+	std::vector<int4> table(n);
+	size_t total = 0;
+	for (uint32_t i = 0; i < n; ++i) {
+		if (!tex[i].rgb8 || tex[i].width <= 0 || tex[i].height <= 0) return fail(ADYPT_EINVAL, "bad texture");
+		if (total + (size_t)tex[i].width * (size_t)tex[i].height > 0x7fffffffull) return fail(ADYPT_ERANGE, "more than 2^31 texels");
+		table[i] = make_int4((int)total, tex[i].width, tex[i].height, 0);
+		total += (size_t)tex[i].width * (size_t)tex[i].height;
+	}
+	std::vector<uchar4> texels(total);
+	for (uint32_t i = 0; i < n; ++i) {
+		const size_t np = (size_t)tex[i].width * (size_t)tex[i].height;
+		uchar4 *dst = texels.data() + table[i].x;
+		for (size_t k = 0; k < np; ++k) dst[k] = make_uchar4(tex[i].rgb8[3 * k], tex[i].rgb8[3 * k + 1], tex[i].rgb8[3 * k + 2], 255);
+	}
+	// a material may only name a texture that exists
+	std::vector<Material> mats(s->n_mats);
+	if (s->n_mats) ADYPT_CUDA(cudaMemcpy(mats.data(), s->d_mats, (size_t)s->n_mats * 64u, cudaMemcpyDeviceToHost));
+	for (const Material &m : mats)
+		if (m.dtex < -1 || m.dtex >= (int32_t)n) return fail(ADYPT_EINVAL, "a material's diffuse texture index is out of range");
+	ADYPT_CUDA(cudaMalloc((void **)&s->d_texels, total * 4u));
+	ADYPT_CUDA(cudaMalloc((void **)&s->d_tex_table, (size_t)n * sizeof(int4)));
+	ADYPT_CUDA(cudaMemcpy(s->d_texels, texels.data(), total * 4u, cudaMemcpyHostToDevice));
+	ADYPT_CUDA(cudaMemcpy(s->d_tex_table, table.data(), (size_t)n * sizeof(int4), cudaMemcpyHostToDevice));
+	s->n_textures = n;
+	s->device_bytes += total * 4u + (size_t)n * sizeof(int4);
 	return ADYPT_OK;
 }
 

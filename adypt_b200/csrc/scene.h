@@ -12,6 +12,9 @@ struct adypt_scene {
 	int32_t *d_tri_indices = nullptr;  // n_refs
 	uint8_t *d_tris = nullptr;         // n_tris * 100
 	adypt::Material *d_mats = nullptr; // n_mats
+	uchar4 *d_texels = nullptr;        // all textures back to back, RGBX8
+	int4 *d_tex_table = nullptr;       // per texture: (first texel, width, height, 0)
+	uint32_t n_textures = 0;           // TEXTURE_COUNT
 	unsigned long long *d_counters = nullptr; // ring of work counters for the persistent kernels
 	unsigned counter_cursor = 0;
 	int ctas_per_sm = 0;       // 0 = occupancy query

@@ -112,6 +112,8 @@ __global__ void k_sobol(const uint32_t *__restrict__ dirs, int dims, int first_s
 struct ShadeBuffers {
 	const uint8_t *__restrict__ tris;        // 100-byte records
 	const Material *__restrict__ mats;
+	const uchar4 *__restrict__ texels;       // diffuse textures, RGBX8 (nullptr when TEXTURE_COUNT == 0)
+	const int4 *__restrict__ tex_table;      // (first texel, width, height, -)
 	const uchar2 *__restrict__ bias;         // uSobolBiasImg
 	const float *__restrict__ sobol;         // [S][2*max_bounce]
 	// primary hit cache (uPrimaryTmpImg): x = tri id bits, zw = uv
@@ -137,6 +139,42 @@ __device__ __forceinline__ V3 bary(const float *a, const float *b, const float *
 {
 	const float w = 1.0f - u - v;
 	return v3(a[0] * u + b[0] * v + c[0] * w, a[1] * u + b[1] * v + c[1] * w, a[2] * u + b[2] * v + c[2] * w);
+}
+
+// texture(sampler2D, st).rgb with GL_REPEAT, GL_LINEAR, one level (OglScene.cpp:33-38): the OpenGL 4.5 bilinear
+// rule (spec 8.14.3) evaluated in fp32, left to right; texel = byte / 255
+__device__ __forceinline__ float wrap_index(float i, float n)
+{
+	float m = i - n * floorf(i / n);
+	return (m >= n || !(m >= 0.0f)) ? 0.0f : m;
+}
+__device__ __forceinline__ V3 texel_rgb(const uchar4 *__restrict__ base, int w, float i, float j)
+{
+	const uchar4 c = base[(int)j * w + (int)i];
+	return v3((float)c.x / 255.0f, (float)c.y / 255.0f, (float)c.z / 255.0f);
+}
+__device__ __forceinline__ V3 sample_texture(const uchar4 *__restrict__ texels, const int4 t, float s, float tt)
+{
+	const float fw = (float)t.y, fh = (float)t.z;
+	const float u = s * fw - 0.5f, v = tt * fh - 0.5f;
+	const float fu = floorf(u), fv = floorf(v);
+	const float a = u - fu, b = v - fv;
+	const float i0 = wrap_index(fu, fw), i1 = wrap_index(fu + 1.0f, fw), j0 = wrap_index(fv, fh), j1 = wrap_index(fv + 1.0f, fh);
+	const uchar4 *base = texels + t.x;
+	const V3 c00 = texel_rgb(base, t.y, i0, j0), c10 = texel_rgb(base, t.y, i1, j0), c01 = texel_rgb(base, t.y, i0, j1), c11 = texel_rgb(base, t.y, i1, j1);
+	const float w00 = (1.0f - a) * (1.0f - b), w10 = a * (1.0f - b), w01 = (1.0f - a) * b, w11 = a * b;
+	return c00 * w00 + c10 * w10 + c01 * w01 + c11 * w11;
+}
+
+// diffuse colour of FetchInfo (pathtracer.glsl:87-98) / primaryray.glsl:59-71
+__device__ __forceinline__ V3 diffuse_of(const uchar4 *__restrict__ texels, const int4 *__restrict__ tex_table, const Material &m, const float *t, float u, float v)
+{
+	if (texels != nullptr && m.dtex != -1) {
+		const float w = 1.0f - u - v;
+		const float s = t[18] * u + t[20] * v + t[22] * w, tt = t[19] * u + t[21] * v + t[23] * w;
+		return sample_texture(texels, tex_table[m.dtex], s, tt);
+	}
+	return v3(m.dr, m.dg, m.db);
 }
 
 __device__ __forceinline__ V3 sample_hemisphere(float rx, float ry, float e) // :52-64
@@ -171,7 +209,7 @@ __device__ __forceinline__ bool shade_segment(const ShadeBuffers &B, const PTArg
 	const Material m = B.mats[matid];
 	V3 normal = normalize(bary(t + 9, t + 12, t + 15, u, v));
 	origin = bary(t, t + 3, t + 6, u, v); // :138
-	const V3 emissive = v3(m.er, m.eg, m.eb), diffuse = v3(m.dr, m.dg, m.db), specular = v3(m.sr, m.sg, m.sb);
+	const V3 emissive = v3(m.er, m.eg, m.eb), diffuse = diffuse_of(B.texels, B.tex_table, m, t, u, v), specular = v3(m.sr, m.sg, m.sb);
 	ret = ret + color * emissive;
 	if (b == A.max_bounce - 1) return false; // the loop ends here; the sampled direction would never be used
 	if (m.illum < 6 && dot(dir, normal) > 0.0f) normal = -normal; // :141-142
@@ -353,8 +391,9 @@ __global__ void k_resolve_sum(const float4 *__restrict__ sum, float4 *__restrict
 }
 
 // primaryray.glsl main() :46-94 after the intersection (TEXTURE_COUNT == 0)
-__global__ void k_view(const uint8_t *__restrict__ tris, const Material *__restrict__ mats, const int32_t *__restrict__ hit_tri,
-                       const float2 *__restrict__ hit_uv, int type, unsigned npix, float4 *__restrict__ out)
+__global__ void k_view(const uint8_t *__restrict__ tris, const Material *__restrict__ mats, const uchar4 *__restrict__ texels,
+                       const int4 *__restrict__ tex_table, const int32_t *__restrict__ hit_tri, const float2 *__restrict__ hit_uv, int type,
+                       unsigned npix, float4 *__restrict__ out)
 {
 	for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x) {
 		const int32_t tri = hit_tri[i];
@@ -363,7 +402,7 @@ __global__ void k_view(const uint8_t *__restrict__ tris, const Material *__restr
 			const float *t = (const float *)(tris + (size_t)tri * 100u);
 			const Material m = mats[*(const int32_t *)(t + 24)];
 			const float2 uv = hit_uv[i];
-			if (type == 0) c = v3(m.dr, m.dg, m.db);
+			if (type == 0) c = diffuse_of(texels, tex_table, m, t, uv.x, uv.y);
 			else if (type == 1) c = v3(m.sr, m.sg, m.sb);
 			else if (type == 2) c = v3(m.er, m.eg, m.eb);
 			else if (type == 4) c = normalize(bary(t + 9, t + 12, t + 15, uv.x, uv.y));
@@ -515,7 +554,7 @@ int run_batch(adypt_tracer *t, int first, int n, bool sum_mode)
 	count_launch();
 	ADYPT_CUDA(cudaMemsetAsync(t->d_counts, 0, (size_t)(c.max_bounce + 1) * sizeof(unsigned long long), t->stream));
 	ShadeBuffers B;
-	B.tris = s->d_tris; B.mats = s->d_mats; B.bias = t->d_bias; B.sobol = t->d_sobol;
+	B.tris = s->d_tris; B.mats = s->d_mats; B.texels = s->d_texels; B.tex_table = s->d_tex_table; B.bias = t->d_bias; B.sobol = t->d_sobol;
 	B.prim_tri = t->d_prim_tri; B.prim_uv = t->d_prim_uv;
 	B.in_rays = nullptr; B.in_tri = t->d_hit_tri; B.in_uv = t->d_hit_uv; B.in_count = nullptr;
 	B.out_rays = t->d_rays[1]; B.out_count = t->d_counts + 1;
@@ -666,7 +705,7 @@ int adypt_tracer_primary(adypt_tracer *t, int32_t viewer_type)
 	k_generate<<<grid_for(t->npix, 256, s->sm_count), 256, 0, t->stream>>>(t->cam, t->width, t->height, 0.0f, 0.0f, t->d_rays[0]);
 	count_launch();
 	ADYPT_TRY(launch_trace(s, t->d_rays[0], t->npix, t->d_hit_tri, nullptr, t->d_hit_uv, nullptr, t->stream));
-	k_view<<<grid_for(t->npix, 256, s->sm_count), 256, 0, t->stream>>>(s->d_tris, s->d_mats, t->d_hit_tri, t->d_hit_uv, viewer_type, t->npix, t->d_result);
+	k_view<<<grid_for(t->npix, 256, s->sm_count), 256, 0, t->stream>>>(s->d_tris, s->d_mats, s->d_texels, s->d_tex_table, t->d_hit_tri, t->d_hit_uv, viewer_type, t->npix, t->d_result);
 	count_launch();
 	ADYPT_CUDA(cudaGetLastError());
 	t->host_segments += t->npix;

@@ -79,6 +79,10 @@ def _lib():
         l.adypt_host_scene_upload.argtypes = [vp, C.c_int32, vp]
         for n in ("load_obj", "from_triangles", "destroy", "build_bvh", "load_bvh", "save_bvh", "get", "upload"):
             getattr(l, "adypt_host_scene_" + n).restype = C.c_int
+        l.adypt_host_scene_load_textures.argtypes = [vp, vp, vp]
+        l.adypt_host_scene_load_textures.restype = C.c_int
+        l.adypt_host_scene_texture.argtypes = [vp, C.c_uint32, vp, vp, vp]
+        l.adypt_host_scene_texture.restype = C.c_int
         l.adypt_config_set_default.argtypes = [vp]
         l.adypt_config_load.argtypes = [C.c_char_p, vp]
         l.adypt_config_to_json.argtypes = [vp, vp, C.c_uint64, vp]
@@ -167,6 +171,19 @@ class HostScene:
 
     def positions(self):
         return self.tris[:, :36].copy().view(np.float32).reshape(-1, 3, 3)
+
+    def load_textures(self):
+        """Decode the materials' map_Kd files and renumber Material::dtex like OglScene::init_materials.
+        Returns (n_loaded, n_failed); the decoded images are then in .textures ((h,w,3) uint8 arrays)."""
+        ok, bad = C.c_uint32(0), C.c_uint32(0)
+        _check(_lib().adypt_host_scene_load_textures(self._h, C.byref(ok), C.byref(bad)))
+        self.textures = []
+        for i in range(ok.value):
+            p, w, h = C.c_void_p(), C.c_int32(), C.c_int32()
+            _check(_lib().adypt_host_scene_texture(self._h, i, C.byref(p), C.byref(w), C.byref(h)))
+            self.textures.append(_copy(p.value, w.value * h.value * 3, np.uint8).reshape(h.value, w.value, 3))
+        self._refresh()
+        return ok.value, bad.value
 
     def upload(self, device: int = 0) -> Scene:
         """OglScene::Initialize(scene, wbvh) (Instance.cpp:33)."""

@@ -78,6 +78,16 @@ typedef struct {
 } adypt_scene_desc;
 
 int adypt_scene_create(const adypt_scene_desc *desc, adypt_scene **out);
+/* Diffuse textures: replaces OglScene::load_texture + the bindless handle table (OglScene.cpp:12-43, 85-90).
+ * Texture i is what material.dtex == i refers to: width*height RGB8 texels, first row first (stbi_load order).
+ * Sampling reproduces texture(sampler2D, uv).rgb with GL_REPEAT / GL_LINEAR / no mip-maps
+ * (pathtracer.glsl:87-98, OglScene.cpp:33-38) as an explicit fp32 bilinear blend. With zero textures the scene
+ * behaves like the reference compiled with TEXTURE_COUNT == 0 (dtex is ignored). Call before creating tracers. */
+typedef struct {
+	const uint8_t *rgb8;
+	int32_t width, height;
+} adypt_texture;
+int adypt_scene_set_textures(adypt_scene *scene, const adypt_texture *textures, uint32_t n_textures);
 int adypt_scene_destroy(adypt_scene *scene);
 /* copies the device Woop array (n_refs * 12 floats) back to the host, for parity checks */
 int adypt_scene_read_woop(adypt_scene *scene, float *out);
@@ -220,6 +230,12 @@ int adypt_host_scene_build_bvh(adypt_host_scene *scene, const adypt_bvh_config *
 int adypt_host_scene_load_bvh(adypt_host_scene *scene, const char *bvh_path, const adypt_bvh_config *expected);
 int adypt_host_scene_save_bvh(adypt_host_scene *scene, const char *bvh_path, const adypt_bvh_config *config);
 int adypt_host_scene_get(adypt_host_scene *scene, adypt_host_scene_info *info);
+/* Decodes the map_Kd files the OBJ's materials name (PNG, TGA) and renumbers Material::dtex the way
+ * OglScene::init_materials does: index among the textures that loaded, -1 when loading failed. Returns the
+ * number loaded / failed through the out-parameters (either may be NULL). adypt_host_scene_upload sends them along. */
+int adypt_host_scene_load_textures(adypt_host_scene *scene, uint32_t *n_loaded, uint32_t *n_failed);
+/* texture i of the host scene after adypt_host_scene_load_textures (RGB8, first row first) */
+int adypt_host_scene_texture(adypt_host_scene *scene, uint32_t i, const uint8_t **rgb8, int32_t *width, int32_t *height);
 /* OglScene::Initialize(scene, wbvh) (Instance.cpp:33): uploads to `device`, Woop rows built on the GPU */
 int adypt_host_scene_upload(adypt_host_scene *scene, int32_t device, adypt_scene **out);
 

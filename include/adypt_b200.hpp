@@ -189,6 +189,7 @@ struct CudaScene {
 	{
 		adypt_scene_destroy(m_handle);
 		m_handle = nullptr;
+		adypt_host_scene_load_textures(scene.m_handle, nullptr, nullptr); // init_materials -> load_texture (OglScene.cpp:51-91)
 		if (adypt_host_scene_upload(scene.m_handle, m_device, &m_handle) != ADYPT_OK) printf("[SCENE]Err: %s\n", adypt_last_error());
 	}
 };

@@ -41,8 +41,8 @@ def lib():
         l.oracle_sobol_directions.argtypes = [C.c_uint32, vp]
         l.oracle_sobol_sequence.argtypes = [C.c_uint32, C.c_uint32, vp]
         l.oracle_sobol_at.argtypes = [C.c_uint32, C.c_uint32, vp]
-        l.oracle_pt_render.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, C.POINTER(PTConfig), vp, i32, i32, vp, vp, vp, i32, i32]
-        l.oracle_primary_view.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, i32]
+        l.oracle_pt_render.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, C.POINTER(PTConfig), vp, i32, i32, vp, vp, vp, i32, i32, i32, vp, vp]
+        l.oracle_primary_view.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, i32, i32, vp, vp]
         l.oracle_det_sincos.argtypes = [vp, u64, vp, vp]
         l.oracle_det_pow.argtypes = [vp, vp, u64, vp]
         _lib = l
@@ -141,8 +141,18 @@ def sobol_at(dim, index):
     return o
 
 
+def _textures(textures):
+    """list of (h,w,3) uint8 arrays -> (n, pointer array, wh array, keepalive)"""
+    if not textures:
+        return 0, None, None, None
+    arrs = [_c(t, np.uint8) for t in textures]
+    ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+    wh = np.array([[a.shape[1], a.shape[0]] for a in arrs], dtype=np.int32)
+    return len(arrs), ptrs, wh, arrs
+
+
 def pt_render(bvh, origin, inv_proj, inv_view, width, height, cfg: dict, bias_rg8, first_spp, n_spp,
-              out_rgba=None, primary_tmp=None, nthreads=0, sum_mode=False):
+              out_rgba=None, primary_tmp=None, nthreads=0, sum_mode=False, textures=None):
     """bvh: object with nodes/tri_indices/woop/tris/mats arrays. Returns (out_rgba, primary_tmp, counters)."""
     c = PTConfig(cfg["max_bounce"], cfg["subpixel"], cfg["tmp_lifetime"], cfg["ray_tmin"], cfg["clamp"],
                  (C.c_float * 3)(*cfg["sun"]))
@@ -155,22 +165,24 @@ def pt_render(bvh, origin, inv_proj, inv_view, width, height, cfg: dict, bias_rg
     ip, iv = _c(inv_proj, np.float32), _c(inv_view, np.float32)
     bias = _c(bias_rg8, np.uint8)
     cnt = np.zeros(5, dtype=np.uint64)
+    nt, tp, twh, _keep = _textures(textures)
     nodes, ti, woop = _c(bvh.nodes, np.uint8), _c(bvh.tri_indices, np.int32), _c(bvh.woop, np.float32)
     tris, mats = _c(bvh.tris, np.uint8), _c(bvh.mats, np.uint8)
     rc = lib().oracle_pt_render(_p(nodes), _p(ti), _p(woop), _p(tris), _p(mats), _p(o), _p(ip), _p(iv), width, height,
-                                C.byref(c), _p(bias), first_spp, n_spp, _p(out_rgba), _p(primary_tmp), _p(cnt), nthreads, int(sum_mode))
+                                C.byref(c), _p(bias), first_spp, n_spp, _p(out_rgba), _p(primary_tmp), _p(cnt), nthreads, int(sum_mode), nt, tp, _p(twh))
     if rc != 0:
         raise RuntimeError("oracle_pt_render failed")
     return out_rgba, primary_tmp, dict(nodes=int(cnt[0]), tris=int(cnt[1]), max_stack=int(cnt[2]), hits=int(cnt[3]), segments=int(cnt[4]))
 
 
-def primary_view(bvh, origin, tmin, inv_proj, inv_view, width, height, vtype, nthreads=0):
+def primary_view(bvh, origin, tmin, inv_proj, inv_view, width, height, vtype, nthreads=0, textures=None):
     ot = np.array([origin[0], origin[1], origin[2], tmin], dtype=np.float32)
     ip, iv = _c(inv_proj, np.float32), _c(inv_view, np.float32)
     out = np.zeros((width * height, 4), dtype=np.float32)
+    nt, tp, twh, _keep = _textures(textures)
     nodes, ti, woop = _c(bvh.nodes, np.uint8), _c(bvh.tri_indices, np.int32), _c(bvh.woop, np.float32)
     tris, mats = _c(bvh.tris, np.uint8), _c(bvh.mats, np.uint8)
-    lib().oracle_primary_view(_p(nodes), _p(ti), _p(woop), _p(tris), _p(mats), _p(ot), _p(ip), _p(iv), width, height, vtype, _p(out), nthreads)
+    lib().oracle_primary_view(_p(nodes), _p(ti), _p(woop), _p(tris), _p(mats), _p(ot), _p(ip), _p(iv), width, height, vtype, _p(out), nthreads, nt, tp, _p(twh))
     return out
 
 

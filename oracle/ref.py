@@ -48,6 +48,8 @@ def lib():
         l.ref_config_load.argtypes = [C.c_char_p, C.c_void_p]
         l.ref_config_roundtrip_json.restype = C.c_int
         l.ref_config_roundtrip_json.argtypes = [C.c_char_p, C.c_char_p, C.c_uint32]
+        l.ref_load_image_rgb8.restype = C.c_int
+        l.ref_load_image_rgb8.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
         _lib = l
     return _lib
 
@@ -174,3 +176,13 @@ def config_roundtrip_json(path: str):
     buf = C.create_string_buffer(1 << 16)
     n = lib().ref_config_roundtrip_json(path.encode(), buf, len(buf))
     return buf.value.decode() if n >= 0 else None
+
+
+def load_image_rgb8(path: str):
+    """stbi_load(path, ..., 3) of the reference's vendored stb_image -> (h,w,3) uint8 array, or None on failure."""
+    w, h = C.c_int(0), C.c_int(0)
+    buf = np.zeros(1 << 26, dtype=np.uint8)
+    rc = lib().ref_load_image_rgb8(path.encode(), C.byref(w), C.byref(h), buf.ctypes.data, buf.size)
+    if rc != 0:
+        return None
+    return buf[: w.value * h.value * 3].reshape(h.value, w.value, 3).copy()

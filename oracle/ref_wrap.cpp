@@ -29,6 +29,8 @@
 #include "BVH/WideBVHBuilder.hpp"
 #include "InstanceConfig.hpp"
 #include <glm/gtc/matrix_transform.hpp>
+#define STB_IMAGE_IMPLEMENTATION
+#include <stb_image.h> // the reference's texture decoder (OglScene.cpp:9-10, 24), vendored under dep/
 
 static_assert(sizeof(WideBVHNode) == 80, "CWBVH node ABI");
 static_assert(sizeof(Triangle) == 100, "Triangle ABI");
@@ -196,6 +198,23 @@ const char *ref_scene_dtex_name(void *h, uint32_t i)
 {
 	RefScene *s = (RefScene *)h;
 	return i < s->dtex_names.size() ? s->dtex_names[i].c_str() : nullptr;
+}
+
+// stbi_load(filename, &w, &h, &channels, 3) exactly as OglScene::load_texture calls it (OglScene.cpp:24).
+// Copies width*height*3 bytes into out (capacity cap); returns 0, -1 on decode failure, -2 if cap is too small.
+int ref_load_image_rgb8(const char *path, int *width, int *height, unsigned char *out, unsigned long long cap)
+{
+	int w = 0, h = 0, ch = 0;
+	unsigned char *data = stbi_load(path, &w, &h, &ch, 3);
+	if (!data) return -1;
+	*width = w;
+	*height = h;
+	const unsigned long long need = (unsigned long long)w * h * 3;
+	int rc = 0;
+	if (need <= cap) memcpy(out, data, need);
+	else rc = -2;
+	stbi_image_free(data);
+	return rc;
 }
 
 // glm::inverse(mat4) of the reference's vendored glm (dep/glm/detail/func_matrix.inl:294-351),
