@@ -3,6 +3,7 @@
 //
 //   adypt_headless scene.config [--spp N] [--out result.exr] [--fp16] [--seed S] [--device D]
 //                  [--viewer diffuse|specular|emissive|normal|position] [--per-frame] [--no-bvh-cache] [--keep-config]
+//                  [--preview-every N]   (progressive preview: also writes <out>.<spp>spp.exr every N samples)
 //
 // Same file formats as the reference (.config JSON, OBJ/MTL, .bvh cache); --spp/--seed/--out are new (the
 // reference renders until the user stops it and seeds from std::random_device).
@@ -24,7 +25,7 @@ int main(int argc, char **argv)
 {
 	if (argc < 2) return usage();
 	const char *config = nullptr, *out = "result.exr", *viewer = nullptr;
-	int spp = 64, device = 0;
+	int spp = 64, device = 0, preview_every = 0;
 	bool fp16 = false, per_frame = false, cache = true, keep = false;
 	unsigned long long seed = 0;
 	for (int i = 1; i < argc; ++i) {
@@ -36,6 +37,7 @@ int main(int argc, char **argv)
 		else if (!strcmp(a, "--seed")) seed = strtoull(next(), nullptr, 10);
 		else if (!strcmp(a, "--device")) device = atoi(next());
 		else if (!strcmp(a, "--viewer")) viewer = next();
+		else if (!strcmp(a, "--preview-every")) preview_every = atoi(next());
 		else if (!strcmp(a, "--per-frame")) per_frame = true; // one Trace(true) per sample, like the viewer's main loop
 		else if (!strcmp(a, "--no-bvh-cache")) cache = false;
 		else if (!strcmp(a, "--keep-config")) keep = true;    // do not rewrite the .config on exit
@@ -65,7 +67,18 @@ int main(int argc, char **argv)
 	if (!viewer) {
 		instance.m_enable_pt_flag = true;
 		const auto t0 = std::chrono::steady_clock::now();
-		if (per_frame)
+		if (preview_every > 0) {
+			for (int done = 0; done < spp;) {
+				const int n = spp - done < preview_every ? spp - done : preview_every;
+				instance.Update(n);
+				done += n;
+				if (done < spp) {
+					char name[1200];
+					snprintf(name, sizeof(name), "%s.%dspp.exr", out, done);
+					instance.m_path_tracer.SaveResult(name, fp16); // like the showcase renders' "<scene>-<spp>spp.exr"
+				}
+			}
+		} else if (per_frame)
 			for (int s = 0; s < spp; ++s) instance.Update(1);
 		else
 			instance.Update(spp);

@@ -384,6 +384,8 @@ int adypt_trace_closest(adypt_scene *s, const float *rays, uint64_t n, int32_t *
 	if (n == 0) return ADYPT_OK;
 	if (!rays || !tri) return fail(ADYPT_EINVAL, "rays/tri is NULL");
 	if (memspace != ADYPT_MEM_HOST && memspace != ADYPT_MEM_DEVICE) return fail(ADYPT_EINVAL, "bad memspace");
+	if (memspace == ADYPT_MEM_DEVICE && (((uintptr_t)rays & 15u) || ((uintptr_t)tri & 3u) || ((uintptr_t)t & 3u) || ((uintptr_t)uv & 7u)))
+		return fail(ADYPT_EINVAL, "device arrays must be aligned: rays 16 B, tri/t 4 B, uv 8 B");
 	DeviceGuard g(s->device);
 	if (memspace == ADYPT_MEM_DEVICE)
 		return launch_trace(s, (const float4 *)rays, n, tri, t, (float2 *)uv, nullptr, (cudaStream_t)stream);
@@ -431,6 +433,7 @@ int adypt_trace_any(adypt_scene *s, const float *rays, uint64_t n, uint8_t *occl
 	if (n == 0) return ADYPT_OK;
 	if (!rays || !occluded) return fail(ADYPT_EINVAL, "rays/occluded is NULL");
 	if (memspace != ADYPT_MEM_HOST && memspace != ADYPT_MEM_DEVICE) return fail(ADYPT_EINVAL, "bad memspace");
+	if (memspace == ADYPT_MEM_DEVICE && ((uintptr_t)rays & 15u)) return fail(ADYPT_EINVAL, "device rays must be 16-byte aligned");
 	DeviceGuard g(s->device);
 	if (memspace == ADYPT_MEM_DEVICE)
 		return launch_trace(s, (const float4 *)rays, n, nullptr, nullptr, nullptr, occluded, (cudaStream_t)stream);

@@ -33,20 +33,30 @@ def ray_range_for_rank(n: int, rank: int, world: int):
     return begin, begin + base + (1 if rank < rem else 0)
 
 
-def render_sharded(tracer, total_spp: int, rank: int, world: int, all_reduce_sum):
+def render_sharded(tracer, total_spp: int, rank: int, world: int, all_reduce_sum, preview_every: int = 0, preview=None):
     """Render this rank's blocks into the tracer's sum accumulator, reduce across ranks, resolve.
 
     tracer: object with .config.tmp_lifetime (or .tmp_lifetime), clear_sum(), accumulate(first, n), resolve_sum().
     all_reduce_sum: callable() that sums the tracer's accumulator over all ranks in place
     (torch.distributed.all_reduce on the tensor wrapping adypt_tracer_sum_buffer; a no-op when world == 1).
+    preview_every / preview: progressive-preview cadence for interactive front ends. After every
+    `preview_every` blocks of THIS rank, preview(blocks_done) is called on every rank (it is collective): the
+    callee reduces a COPY of the accumulator (the accumulator itself keeps growing, so it must not be reduced in
+    place) and shows sum.xyz / sum.w. Ranks with fewer blocks still join every preview so the collective matches.
     Returns the number of samples this rank rendered.
     """
     L = getattr(tracer, "tmp_lifetime", None) or tracer.config.tmp_lifetime
     tracer.clear_sum()
     mine = 0
-    for first, n in blocks_for_rank(total_spp, L, rank, world):
-        tracer.accumulate(first, n)
-        mine += n
+    my_blocks = blocks_for_rank(total_spp, L, rank, world)
+    most = max(len(blocks_for_rank(total_spp, L, r, world)) for r in range(world))
+    for i in range(most):
+        if i < len(my_blocks):
+            first, n = my_blocks[i]
+            tracer.accumulate(first, n)
+            mine += n
+        if preview is not None and preview_every > 0 and (i + 1) % preview_every == 0 and i + 1 < most:
+            preview(i + 1)
     if world > 1:
         all_reduce_sum()
     tracer.resolve_sum()

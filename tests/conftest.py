@@ -72,30 +72,49 @@ def cpu():
 
 
 @pytest.fixture(scope="session")
-def c1(refmod):
-    """C1: 65 536-triangle sphere lattice through the reference OBJ -> SBVH -> CWBVH pipeline."""
+def c1_ref(refmod):
+    """C1 through the REFERENCE's OBJ -> SBVH -> CWBVH pipeline (oracle/_ref)."""
     from adypt_b200 import workloads as W
     mesh = W.sphere_lattice(5)
-    bvh = refmod.build(mesh.write_obj(CACHE))
-    return mesh, bvh
+    return mesh, refmod.build(mesh.write_obj(CACHE))
+
+
+def _own_build(mesh, cpu):
+    """Scene arrays from the product's own host stages (byte-identical to the reference's, see
+    test_host_builder.py) + Woop rows from the oracle, so GPU parity tests need no reference library."""
+    from adypt_b200 import host
+    hs = host.HostScene.from_triangles(mesh.positions(), mesh.face_mat, host.materials_array(mesh.materials))
+    os.makedirs(CACHE, exist_ok=True)
+    path = os.path.join(CACHE, mesh.name + ".bvh")
+    if not hs.load_bvh(path):
+        hs.build_bvh()
+        hs.save_bvh(path)
+    hs.woop = cpu.build_woop(hs.tris, hs.tri_indices)
+    return hs
 
 
 @pytest.fixture(scope="session")
-def city_small(refmod):
+def c1(cpu):
+    """C1: 65 536-triangle sphere lattice."""
+    from adypt_b200 import workloads as W
+    mesh = W.sphere_lattice(5)
+    return mesh, _own_build(mesh, cpu)
+
+
+@pytest.fixture(scope="session")
+def city_small(cpu):
     """A 24x24-cell city (~17k triangles) with every material type: quick C2/C3 stand-in."""
     from adypt_b200 import workloads as W
     mesh = W.city(24, 1, mixed_materials=True)
-    bvh = refmod.build(mesh.write_obj(CACHE))
-    return mesh, bvh
+    return mesh, _own_build(mesh, cpu)
 
 
 @pytest.fixture(scope="session")
-def c2(refmod):
-    """C2: ~1.0M-triangle box city (reference build takes ~20 s the first time, cached afterwards)."""
+def c2(cpu):
+    """C2: ~1.0M-triangle box city (own builder: ~8-16 s the first time, .bvh-cached afterwards)."""
     from adypt_b200 import workloads as W
     mesh = W.city(183, 1)
-    bvh = refmod.build(mesh.write_obj(CACHE))
-    return mesh, bvh
+    return mesh, _own_build(mesh, cpu)
 
 
 def gpu_available():

@@ -99,6 +99,16 @@ def test_scheduling_knobs_do_not_change_results(A, cpu):
     assert np.array_equal(p["tri"], base["tri"][perm]) and np.array_equal(bits(p["t"]), bits(base["t"][perm]))
 
 
+def test_device_pointer_alignment_is_checked(A):
+    import torch
+    g = load_golden("tiny_strip")
+    sc = A.Scene(g.nodes, g.tri_indices, g.woop)
+    buf = torch.zeros(8 * 64 + 1, dtype=torch.float32, device="cuda")
+    tri = torch.empty(64, dtype=torch.int32, device="cuda")
+    with pytest.raises(A.AdyptError):
+        sc.trace_closest(buf[1:], tri, None, None)  # 4-byte offset: not 16-byte aligned
+
+
 def test_scene_validation_rejects_out_of_range_indices(A):
     g = load_golden("tiny_strip")
     bad = g.nodes.copy()

@@ -44,8 +44,8 @@ def test_builder_parameters_byte_identical(refmod, params):
     same_as_reference(host.build_scene(mesh, host.BvhConfig.make(*params)), b)
 
 
-def test_c1_byte_identical_and_matches_committed_digest(c1):
-    mesh, b = c1
+def test_c1_byte_identical_and_matches_committed_digest(c1_ref):
+    mesh, b = c1_ref
     hs = host.build_scene(mesh)
     same_as_reference(hs, b)
     h = json.load(open(os.path.join(GOLDEN, "hashes.json")))["c1"]

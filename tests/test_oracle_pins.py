@@ -57,14 +57,14 @@ def test_woop_matches_reference_golden(cpu, name):
     assert np.array_equal(bits(w), bits(g.woop))
 
 
-def test_woop_c1_live(cpu, c1):
-    _, b = c1
+def test_woop_c1_live(cpu, c1_ref):
+    _, b = c1_ref
     assert np.array_equal(bits(cpu.build_woop(b.tris, b.tri_indices)), bits(b.woop))
 
 
-def test_reference_arrays_hashes_c1(c1):
+def test_reference_arrays_hashes_c1(c1_ref):
     """The reference builder run here reproduces the committed digests of its node / index / Woop arrays."""
-    _, b = c1
+    _, b = c1_ref
     h = json.load(open(os.path.join(GOLDEN, "hashes.json")))["c1"]
     assert (b.n_tris, b.n_nodes, b.n_refs) == (h["n_tris"], h["n_nodes"], h["n_refs"])
     assert fnv1a(b.nodes) == h["nodes"]

@@ -75,7 +75,16 @@ def _worker(rank, world, port, out_path):
         t = torch.from_numpy(tr.sum)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
 
-    mine = sharding.render_sharded(tr, SPP, rank, world, all_reduce)
+    previews = []
+
+    def preview(blocks_done):
+        t = torch.from_numpy(tr.sum.copy())  # reduce a COPY: the accumulator keeps growing
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        previews.append((blocks_done, float(t[:, 3].min()), float(t[:, 3].max())))
+
+    mine = sharding.render_sharded(tr, SPP, rank, world, all_reduce, preview_every=1, preview=preview)
+    # 5 blocks over 2 ranks: rank 0 has 3, rank 1 has 2 -> previews after rounds 1 and 2 with 16 and 32 samples/pixel
+    assert [p[0] for p in previews] == [1, 2] and previews[0][1:] == (16.0, 16.0) and previews[1][1:] == (32.0, 32.0)
     counts = torch.tensor([mine])
     dist.all_reduce(counts)
     if rank == 0:
