@@ -1,0 +1,26 @@
+#!/usr/bin/env python3
+"""Runs the closest-hit kernel `variant` on the C2 ray set a few times (for ncu: -k regex:trace_kernel -s 3 -c 1)."""
+import os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import adypt_b200 as A
+from adypt_b200 import host, workloads as W
+
+variant = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+mesh = W.city(183, 1)
+hs = host.build_scene(mesh)
+sc = hs.upload(0)
+tr = A.Tracer(sc, A.PTConfig.make(), 1000, 1000, bias_seed=7)
+cam = W.city_camera(183); tr.look(cam['position'], cam['yaw'], cam['pitch'], cam['fov'])
+prim = tr.primary_rays(); ph = sc.trace_closest(prim)
+rays = W.bounce_rays(mesh.positions(), prim, ph['tri'], ph['uv'])
+n = rays.shape[0]
+d_rays = torch.from_numpy(rays).cuda()
+d_tri = torch.empty(n, dtype=torch.int32, device='cuda'); d_t = torch.empty(n, dtype=torch.float32, device='cuda'); d_uv = torch.empty((n, 2), dtype=torch.float32, device='cuda')
+sc.configure(0, 0, variant)
+for _ in range(reps):
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(); sc.trace_closest(d_rays, d_tri, d_t, d_uv, stream=torch.cuda.current_stream().cuda_stream); e1.record(); torch.cuda.synchronize()
+    print('variant', variant, 'ms', e0.elapsed_time(e1))
