@@ -12,6 +12,10 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <future>
+#include <string>
+#include <thread>
+#include <unistd.h>
 
 namespace adypt {
 namespace host {
@@ -83,10 +87,21 @@ public:
 	SbvhBuilder(const Triangle *tris, size_t n, const Box &scene, const BvhConfig &cfg, BinaryBvh *out)
 	    : tris_(tris), n_(n), scene_(scene), cfg_(cfg), out_(out) {}
 
+	// sub-builder for one subtree: its own reference stack and node array, merged by the parent afterwards
+	SbvhBuilder(const SbvhBuilder &parent, std::vector<Ref> &&refs, BinaryBvh *out)
+	    : tris_(parent.tris_), n_(parent.n_), scene_(parent.scene_), cfg_(parent.cfg_), out_(out), refs_(std::move(refs)),
+	      min_overlap_(parent.min_overlap_), fork_depth_(parent.fork_depth_) {}
+
 	void run()
 	{
 		out_->nodes.clear();
 		out_->leaf_count = 0;
+		// Subtrees are independent (a node only touches its own references, which sit on top of the stack), so
+		// the top levels fork: each child gets a copy of its reference range and builds into a private node
+		// array; the parent appends right subtree then left subtree and rebases their child indices. The
+		// output is the sequential builder's, byte for byte, whatever the thread timing.
+		const unsigned hw = std::thread::hardware_concurrency();
+		fork_depth_ = hw >= 32 ? 6 : hw >= 8 ? 5 : hw >= 4 ? 4 : hw >= 2 ? 2 : 0;
 		refs_.reserve(n_ * 2);
 		refs_.resize(n_);
 		for (size_t i = 0; i < n_; ++i) {
@@ -108,6 +123,8 @@ private:
 	std::vector<Ref> refs_;
 	std::vector<Box> suffix_; // boxes accumulated from the right
 	float min_overlap_ = 0.f;
+	int fork_depth_ = 0;                         // fork subtrees down to this depth ...
+	static constexpr int kForkMinRefs = 16384;   // ... while they hold at least this many references
 	static constexpr int kBins = 32; // kSpatialBinNum, SBVHBuilder.hpp:16
 
 	float tri_cost(int count) const { return cfg_.triangle_sah * count; } // InstanceConfig.hpp:18
@@ -315,6 +332,31 @@ private:
 			left.box = os.left;
 			right.count = s.count - os.left_count;
 			right.box = os.right;
+		}
+		if (depth < fork_depth_ && s.count >= kForkMinRefs) {
+			// layout on the stack after either split: [left references][right references]
+			const size_t base = refs_.size() - (size_t)(left.count + right.count);
+			std::vector<Ref> lrefs(refs_.begin() + (long)base, refs_.begin() + (long)base + left.count);
+			std::vector<Ref> rrefs(refs_.begin() + (long)base + left.count, refs_.end());
+			refs_.resize(base);
+			BinaryBvh lout, rout;
+			SbvhBuilder lb(*this, std::move(lrefs), &lout), rb(*this, std::move(rrefs), &rout);
+			auto fut = std::async(std::launch::async, [&rb, right, depth]() { rb.build(right, depth + 1); });
+			lb.build(left, depth + 1);
+			fut.get();
+			auto append = [this](const BinaryBvh &sub) {
+				const int start = (int)out_->nodes.size();
+				out_->nodes.reserve(out_->nodes.size() + sub.nodes.size());
+				for (BinaryNode n : sub.nodes) {
+					if (n.left != -1) n.left += start;
+					out_->nodes.push_back(n);
+				}
+				out_->leaf_count += sub.leaf_count;
+				return start;
+			};
+			append(rout); // right child lands at node + 1
+			out_->nodes[node].left = append(lout);
+			return node;
 		}
 		build(right, depth + 1); // right child lands at node + 1
 		const int l = build(left, depth + 1);
@@ -603,7 +645,10 @@ static const char kMagic[] = "CWBVH_1.0"; // WideBVH.hpp:32, written with its te
 
 bool save_bvh_file(const char *path, const WideBvh &bvh, const BvhConfig &cfg)
 {
-	FILE *f = fopen(path, "wb");
+	// written next to the target and renamed into place, so a concurrent reader (several ranks sharing one
+	// cache directory) never sees a half-written file
+	const std::string tmp = std::string(path) + ".tmp." + std::to_string((long)getpid());
+	FILE *f = fopen(tmp.c_str(), "wb");
 	if (!f) return false;
 	const uint32_t n_idx = (uint32_t)bvh.tri_indices.size();
 	bool ok = fwrite(kMagic, 1, sizeof(kMagic), f) == sizeof(kMagic);
@@ -611,7 +656,10 @@ bool save_bvh_file(const char *path, const WideBvh &bvh, const BvhConfig &cfg)
 	ok = ok && fwrite(&n_idx, 4, 1, f) == 1;
 	ok = ok && (n_idx == 0 || fwrite(bvh.tri_indices.data(), 4, n_idx, f) == n_idx);
 	ok = ok && (bvh.nodes.empty() || fwrite(bvh.nodes.data(), sizeof(Node), bvh.nodes.size(), f) == bvh.nodes.size());
-	return (fclose(f) == 0) && ok;
+	ok = (fclose(f) == 0) && ok;
+	if (ok) ok = rename(tmp.c_str(), path) == 0;
+	if (!ok) remove(tmp.c_str());
+	return ok;
 }
 
 bool load_bvh_file(const char *path, const BvhConfig &expected, WideBvh *out)

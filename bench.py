@@ -35,7 +35,7 @@ def log(*a):
     print("[bench]", *a, file=sys.stderr, flush=True)
 
 
-def build_inputs(mixed=False):
+def build_inputs(mixed=False, rank=0, barrier=None):
     """C2 scene arrays from the product's own host stages (adypt_b200.host): Triangle[] assembly and the
     from-scratch SBVH -> CWBVH builder, byte-identical to the reference's src/BVH pipeline (tests/
     test_host_builder.py). The node/index arrays are cached in the reference's own .bvh format
@@ -45,11 +45,15 @@ def build_inputs(mixed=False):
     hs = host.HostScene.from_triangles(mesh.positions(), mesh.face_mat, host.materials_array(mesh.materials))
     os.makedirs(CACHE, exist_ok=True)
     bvh_path = os.path.join(CACHE, mesh.name + ".bvh")
+    if barrier is not None and rank != 0:
+        barrier()  # rank 0 builds and caches first; the others then load the .bvh instead of building it N times
     if not hs.load_bvh(bvh_path):
         t0 = time.perf_counter()
         hs.build_bvh()
         log(f"built CWBVH in {time.perf_counter() - t0:.1f} s")
         hs.save_bvh(bvh_path)
+    if barrier is not None and rank == 0:
+        barrier()
     return mesh, hs
 
 
@@ -164,7 +168,7 @@ def run_native(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     A.load_library()
 
-    mesh, bvh = build_inputs()
+    mesh, bvh = build_inputs(rank=rank, barrier=dist.barrier if dist is not None else None)
     scene = bvh.upload(local_rank)  # OglScene::Initialize: Woop rows are built on the GPU
     tracer = A.Tracer(scene, A.PTConfig.make(), PRIMARY, PRIMARY, bias_seed=7)
     cam = W.city_camera(CELLS)
@@ -261,7 +265,7 @@ def run_native(args, rank, world, local_rank):
            "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks,
            "target": {"Mrays/s": 1500.0, "met": value / world >= 1500.0}}
     if not args.no_aux:
-        out["aux"] = path_tracer_aux(A, torch, dist, local_rank, world)
+        out["aux"] = path_tracer_aux(A, torch, dist, rank, local_rank, world)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cb, counters, ns = cpu_leg(bvh, rays)
         out["cpu_baseline"] = cb
@@ -274,11 +278,11 @@ def run_native(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
-def path_tracer_aux(A, torch, dist, local_rank, world):
+def path_tracer_aux(A, torch, dist, rank, local_rank, world):
     """Second half of BASELINE.json's metric: 1080p path samples/s (configs[2], "C3"): the same city with
     glossy / mirror / glass / emissive boxes, 1920x1080, maxBounce 5 (4 bounces), 64 spp, no Russian roulette
     (the reference has none). Each rank renders the full image (weak scaling); wall clock around sample()+sync."""
-    mesh, hs = build_inputs(mixed=True)
+    mesh, hs = build_inputs(mixed=True, rank=rank, barrier=dist.barrier if dist is not None else None)
     scene = hs.upload(local_rank)
     w, h, spp = 1920, 1080, 64
     tr = A.Tracer(scene, A.PTConfig.make(sun=(1.0, 1.0, 1.0)), w, h, bias_seed=7)
