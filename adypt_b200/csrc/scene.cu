@@ -89,17 +89,6 @@ __global__ void build_woop_kernel(const uint8_t *__restrict__ tris, const int32_
 	woop[3 * (size_t)i + 2] = make_float4(inv[1][0], inv[1][1], inv[1][2], inv[1][3]);
 }
 
-// reference layout (m0, m1, m2) -> device layout (m0, (m1.x m2.x m1.y m2.y), (m1.z m2.z m1.w m2.w)), in place
-// (see woop_test in traverse.cuh: u and v rows side by side for packed FMAs)
-__global__ void interleave_woop_kernel(float4 *__restrict__ woop, uint32_t n_refs)
-{
-	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n_refs) return;
-	const float4 m1 = woop[3 * (size_t)i + 1], m2 = woop[3 * (size_t)i + 2];
-	woop[3 * (size_t)i + 1] = make_float4(m1.x, m2.x, m1.y, m2.y);
-	woop[3 * (size_t)i + 2] = make_float4(m1.z, m2.z, m1.w, m2.w);
-}
-
 // ------------------------------------------------------------------------------------------------
 int launch_trace(adypt_scene *s, const float4 *d_rays, uint64_t n, int32_t *d_tri, float *d_t, float2 *d_uv, uint8_t *d_occ,
                  cudaStream_t stream, const unsigned long long *d_n)
@@ -121,7 +110,7 @@ int launch_trace(adypt_scene *s, const float4 *d_rays, uint64_t n, int32_t *d_tr
 	p.magic = 0x4B000000u;
 	p.counter = s->d_counters + (s->counter_cursor++ % kCounterRing);
 	p.refill_threshold = s->refill_threshold > 0 ? s->refill_threshold : 28;
-	int per_sm = s->ctas_per_sm > 0 ? s->ctas_per_sm : (any ? s->occ_any : ((s->variant == 1 || s->variant == 7 || s->variant == 11) ? 6 : (s->variant == 10 || s->variant == 13) ? 7 : s->occ_closest));
+	int per_sm = s->ctas_per_sm > 0 ? s->ctas_per_sm : (any ? s->occ_any : ((s->variant == 1 || s->variant == 7 || s->variant == 9) ? 6 : s->occ_closest));
 	if (per_sm < 1) per_sm = 1;
 	unsigned long long warps_needed = (n + 31) / 32;
 	unsigned long long ctas_needed = (warps_needed + (kTraceBlock / 32) - 1) / (kTraceBlock / 32);
@@ -137,12 +126,8 @@ int launch_trace(adypt_scene *s, const float4 *d_rays, uint64_t n, int32_t *d_tr
 	case 5: trace_kernel<false, false, 4, 8><<<grid, kTraceBlock, 0, stream>>>(p); break;
 	case 6: trace_kernel<false, false, 6, 8><<<grid, kTraceBlock, 0, stream>>>(p); break;
 	case 7: trace_kernel<false, false, 2, 6><<<grid, kTraceBlock, 0, stream>>>(p); break;
-	case 8: trace_kernel<false, false, 2, 8, true, false><<<grid, kTraceBlock, 0, stream>>>(p); break; // cooperative triangle tests
-	case 10: trace_kernel<false, false, 2, 7, false, true><<<grid, kTraceBlock, 0, stream>>>(p); break;
-	case 11: trace_kernel<false, false, 2, 6, false, true><<<grid, kTraceBlock, 0, stream>>>(p); break;
-	case 12: trace_kernel<false, false, 0, 8, false, true><<<grid, kTraceBlock, 0, stream>>>(p); break;
-	case 13: trace_kernel<false, false, 0, 7, false, true><<<grid, kTraceBlock, 0, stream>>>(p); break;
-	case 9: trace_kernel<false, false, 2, 8, false, false><<<grid, kTraceBlock, 0, stream>>>(p); break; // scalar FFMA (no f32x2)
+	case 8: trace_kernel<false, false, 2, 8, true><<<grid, kTraceBlock, 0, stream>>>(p); break;
+	case 9: trace_kernel<false, false, 2, 6, true><<<grid, kTraceBlock, 0, stream>>>(p); break;
 	default: trace_kernel<false><<<grid, kTraceBlock, 0, stream>>>(p); break;
 	}
 	count_launch();
@@ -275,12 +260,6 @@ int adypt_scene_create(const adypt_scene_desc *d, adypt_scene **out)
 		cudaError_t e = cudaDeviceSynchronize();
 		if (e != cudaSuccess) { free_scene(s); return fail(ADYPT_ECUDA, std::string("build_woop_kernel: ") + cudaGetErrorString(e)); }
 	}
-	if (d->n_refs) {
-		interleave_woop_kernel<<<(d->n_refs + 255) / 256, 256>>>(s->d_woop, d->n_refs);
-		count_launch();
-		cudaError_t e = cudaDeviceSynchronize();
-		if (e != cudaSuccess) { free_scene(s); return fail(ADYPT_ECUDA, std::string("interleave_woop_kernel: ") + cudaGetErrorString(e)); }
-	}
 #undef UP
 	if (cudaMalloc((void **)&s->d_counters, (kCounterRing + 4) * sizeof(unsigned long long)) != cudaSuccess) { free_scene(s); return fail(ADYPT_ENOMEM, "cudaMalloc counters"); }
 	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->occ_closest, trace_kernel<false>, kTraceBlock, 0);
@@ -340,12 +319,6 @@ int adypt_scene_read_woop(adypt_scene *s, float *out)
 	if (!s || !out) return fail(ADYPT_EINVAL, "scene/out is NULL");
 	DeviceGuard g(s->device);
 	ADYPT_CUDA(cudaMemcpy(out, s->d_woop, (size_t)s->n_refs * 48u, cudaMemcpyDeviceToHost));
-	for (size_t i = 0; i < s->n_refs; ++i) { // device layout -> the reference's (m0, m1, m2)
-		float *w = out + i * 12;
-		const float a[8] = {w[4], w[5], w[6], w[7], w[8], w[9], w[10], w[11]};
-		w[4] = a[0]; w[5] = a[2]; w[6] = a[4]; w[7] = a[6];
-		w[8] = a[1]; w[9] = a[3]; w[10] = a[5]; w[11] = a[7];
-	}
 	return ADYPT_OK;
 }
 
@@ -359,7 +332,7 @@ int adypt_scene_device_bytes(adypt_scene *s, uint64_t *bytes)
 int adypt_trace_configure(adypt_scene *s, int ctas_per_sm, int refill_threshold, int variant)
 {
 	if (!s) return fail(ADYPT_EINVAL, "scene is NULL");
-	if (ctas_per_sm < 0 || refill_threshold < 0 || refill_threshold > 32 || variant < 0 || variant > 13) return fail(ADYPT_EINVAL, "bad tuning value");
+	if (ctas_per_sm < 0 || refill_threshold < 0 || refill_threshold > 32 || variant < 0 || variant > 9) return fail(ADYPT_EINVAL, "bad tuning value");
 	s->ctas_per_sm = ctas_per_sm;
 	s->refill_threshold = refill_threshold;
 	s->variant = variant;

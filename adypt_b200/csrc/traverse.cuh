@@ -11,9 +11,6 @@
 // intrinsics), with fused multiply-add exactly where the oracle has fmaf(): the 48 slab evaluations per
 // node and the Woop dot chains.
 //
-// Arithmetic: the slab evaluations and the Woop dot chains use sm_100's packed fp32x2 instructions (FFMA2 /
-// FADD2 / FMUL2) -- same IEEE results, half the issue slots.
-//
 // Memory: node = 5 x LDG.128 and Woop = 3 x LDG.128 through the read-only path (L1 + L2; C1/C2 BVHs are
 // L2-resident on B200), traversal stack = SSTACK entries per lane in shared memory ([entry][thread], so a
 // warp's 8-byte accesses are conflict-free) with a local-memory overflow that real scenes never reach.
@@ -79,77 +76,6 @@ __device__ __forceinline__ float byte_to_float(uint32_t word, uint32_t magic)
 }
 
 // one group of four children (one 32-bit lane of each quantised plane), traversal.glsl:86-143 / :145-202
-// ---- packed fp32x2 arithmetic (new on sm_100: FADD2 / FMUL2 / FFMA2 operate on an aligned register pair and
-// take scalar operands as broadcasts). Each half is an ordinary IEEE round-to-nearest operation, so results are
-// bit-identical to the scalar code; the point is HALF the issue slots for the 48 slab evaluations per node and
-// for the Woop dot chains, in a kernel that is instruction-issue bound.
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pack2(float lo, float hi)
-{
-	f32x2 r;
-	asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-	return r;
-}
-__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
-{
-	f32x2 r;
-	asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-	return r;
-}
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b)
-{
-	f32x2 r;
-	asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-	return r;
-}
-__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b)
-{
-	f32x2 r;
-	asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-	return r;
-}
-
-// (float)byte for bytes K and K+1 of `word` as a pair
-template <int K, bool CVT>
-__device__ __forceinline__ f32x2 bytes_to_float2(uint32_t word, uint32_t magic)
-{
-	if (CVT) return pack2(byte_to_float_cvt<K>(word), byte_to_float_cvt<K + 1>(word));
-	uint32_t a, b;
-	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(a) : "r"(word), "r"(magic), "n"(0x7540 | K));
-	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(b) : "r"(word), "r"(magic), "n"(0x7540 | (K + 1)));
-	return add2(pack2(__uint_as_float(a), __uint_as_float(b)), pack2(-8388608.0f, -8388608.0f));
-}
-
-// children K and K+1 of one group: the six planes as three packed FMAs per bound
-template <int K, int CVT_PLANES>
-__device__ __forceinline__ uint32_t test_child_pair(uint32_t child_bits4, uint32_t bit_index4, uint32_t s_lox, uint32_t s_loy, uint32_t s_loz,
-                                                    uint32_t s_hix, uint32_t s_hiy, uint32_t s_hiz, float aix, float aiy, float aiz,
-                                                    float aox, float aoy, float aoz, float tmin, float hit_t, uint32_t magic)
-{
-	const f32x2 ax = pack2(aix, aix), ay = pack2(aiy, aiy), az = pack2(aiz, aiz);
-	const f32x2 bx = pack2(aox, aox), by = pack2(aoy, aoy), bz = pack2(aoz, aoz);
-	float txmin0, txmin1, tymin0, tymin1, tzmin0, tzmin1, txmax0, txmax1, tymax0, tymax1, tzmax0, tzmax1;
-	unpack2(fma2(bytes_to_float2<K, (CVT_PLANES > 0)>(s_lox, magic), ax, bx), txmin0, txmin1);
-	unpack2(fma2(bytes_to_float2<K, (CVT_PLANES > 2)>(s_loy, magic), ay, by), tymin0, tymin1);
-	unpack2(fma2(bytes_to_float2<K, (CVT_PLANES > 4)>(s_loz, magic), az, bz), tzmin0, tzmin1);
-	unpack2(fma2(bytes_to_float2<K, (CVT_PLANES > 1)>(s_hix, magic), ax, bx), txmax0, txmax1);
-	unpack2(fma2(bytes_to_float2<K, (CVT_PLANES > 3)>(s_hiy, magic), ay, by), tymax0, tymax1);
-	unpack2(fma2(bytes_to_float2<K, (CVT_PLANES > 5)>(s_hiz, magic), az, bz), tzmax0, tzmax1);
-	uint32_t hitmask = 0u;
-	{
-		const float ctmin = fmaxf(fmaxf(txmin0, tymin0), fmaxf(tzmin0, tmin));
-		const float ctmax = fminf(fminf(txmax0, tymax0), fminf(tzmax0, hit_t));
-		if (ctmin <= ctmax) hitmask |= ((child_bits4 >> (8 * K)) & 0xffu) << ((bit_index4 >> (8 * K)) & 0xffu);
-	}
-	{
-		const float ctmin = fmaxf(fmaxf(txmin1, tymin1), fmaxf(tzmin1, tmin));
-		const float ctmax = fminf(fminf(txmax1, tymax1), fminf(tzmax1, hit_t));
-		if (ctmin <= ctmax) hitmask |= ((child_bits4 >> (8 * (K + 1))) & 0xffu) << ((bit_index4 >> (8 * (K + 1))) & 0xffu);
-	}
-	return hitmask;
-}
-
 template <int K, int CVT_PLANES>
 __device__ __forceinline__ uint32_t test_child(uint32_t child_bits4, uint32_t bit_index4, uint32_t s_lox, uint32_t s_loy, uint32_t s_loz,
                                                uint32_t s_hix, uint32_t s_hiy, uint32_t s_hiz, float aix, float aiy, float aiz,
@@ -171,7 +97,7 @@ __device__ __forceinline__ uint32_t test_child(uint32_t child_bits4, uint32_t bi
 	return 0u;
 }
 
-template <int CVT_PLANES, bool PACKED>
+template <int CVT_PLANES>
 __device__ __forceinline__ uint32_t test_children4(uint32_t meta4, uint32_t octinv4, uint32_t s_lox, uint32_t s_loy,
                                                    uint32_t s_loz, uint32_t s_hix, uint32_t s_hiy, uint32_t s_hiz,
                                                    float aix, float aiy, float aiz, float aox, float aoy, float aoz,
@@ -181,50 +107,8 @@ __device__ __forceinline__ uint32_t test_children4(uint32_t meta4, uint32_t octi
 	const uint32_t bit_index4 = (meta4 ^ (octinv4 & ((is_inner4 >> 4) * 0xffu))) & 0x1f1f1f1fu;
 	const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
 #define ADYPT_CHILD(K) test_child<K, CVT_PLANES>(child_bits4, bit_index4, s_lox, s_loy, s_loz, s_hix, s_hiy, s_hiz, aix, aiy, aiz, aox, aoy, aoz, tmin, hit_t, magic)
-#define ADYPT_PAIR(K) test_child_pair<K, CVT_PLANES>(child_bits4, bit_index4, s_lox, s_loy, s_loz, s_hix, s_hiy, s_hiz, aix, aiy, aiz, aox, aoy, aoz, tmin, hit_t, magic)
-	if (PACKED) return ADYPT_PAIR(0) | ADYPT_PAIR(2);
 	return ADYPT_CHILD(0) | ADYPT_CHILD(1) | ADYPT_CHILD(2) | ADYPT_CHILD(3);
 #undef ADYPT_CHILD
-#undef ADYPT_PAIR
-}
-
-// Woop rows of one leaf reference in DEVICE layout (scene.cu interleaves the reference's 3 x vec4 at upload):
-//   w0 = m0 = (row2.xyz, -row2.w)            -> t
-//   w1 = (m1.x, m2.x, m1.y, m2.y), w2 = (m1.z, m2.z, m1.w, m2.w)   -> u and v side by side,
-// so that (m1.c, m2.c) are adjacent registers after two LDG.128 and the u/v dot chains run as packed FMAs with
-// the ray component as broadcast operand; the t row pairs (origin.c, dir.c) against a broadcast m0.c.
-// Operation order per value is exactly dot3_fma's: x*mx, then fma y, then fma z (traversal.glsl:221-231).
-template <bool PACKED>
-__device__ __forceinline__ void woop_test(const float4 w0, const float4 w1, const float4 w2, float ox, float oy, float oz, float dx,
-                                          float dy, float dz, float &tt, float &tu, float &tv)
-{
-	if (PACKED) {
-		float so, sd;
-		f32x2 p0 = mul2(pack2(ox, dx), pack2(w0.x, w0.x));
-		p0 = fma2(pack2(oy, dy), pack2(w0.y, w0.y), p0);
-		p0 = fma2(pack2(oz, dz), pack2(w0.z, w0.z), p0);
-		unpack2(p0, so, sd);
-		const float toz = __fsub_rn(w0.w, so);
-		const float tidz = __frcp_rn(sd);
-		tt = __fmul_rn(toz, tidz);
-		f32x2 po = mul2(pack2(w1.x, w1.y), pack2(ox, ox));
-		po = fma2(pack2(w1.z, w1.w), pack2(oy, oy), po);
-		po = fma2(pack2(w2.x, w2.y), pack2(oz, oz), po);
-		po = add2(pack2(w2.z, w2.w), po); // (tox, toy)
-		f32x2 pd = mul2(pack2(w1.x, w1.y), pack2(dx, dx));
-		pd = fma2(pack2(w1.z, w1.w), pack2(dy, dy), pd);
-		pd = fma2(pack2(w2.x, w2.y), pack2(dz, dz), pd);
-		unpack2(fma2(pack2(tt, tt), pd, po), tu, tv);
-	} else {
-		const float4 m1 = make_float4(w1.x, w1.z, w2.x, w2.z), m2 = make_float4(w1.y, w1.w, w2.y, w2.w);
-		const float toz = __fsub_rn(w0.w, dot3_fma(ox, oy, oz, w0));
-		const float tidz = __frcp_rn(dot3_fma(dx, dy, dz, w0));
-		tt = __fmul_rn(toz, tidz);
-		const float tox = __fadd_rn(m1.w, dot3_fma(ox, oy, oz, m1));
-		tu = __fmaf_rn(tt, dot3_fma(dx, dy, dz, m1), tox);
-		const float toy = __fadd_rn(m2.w, dot3_fma(ox, oy, oz, m2));
-		tv = __fmaf_rn(tt, dot3_fma(dx, dy, dz, m2), toy);
-	}
 }
 
 constexpr int kCoopPerLane = 3;                   // triangles a lane hands to the warp per round (one 3-triangle leaf)
@@ -237,7 +121,7 @@ constexpr int kCoopSlots = 32 * kCoopPerLane;      // work items per warp and ro
 // reference's strict comparisons. Arithmetic and per-ray order are unchanged -- only which lane evaluates a
 // test differs -- so results stay bit-identical, while the test body runs at ~13/32 instead of 3.6/32 lanes
 // and the Woop loads of a node step are issued as one batch instead of one dependent batch per triangle.
-template <bool ANY, bool STATS = false, int CVT_PLANES = 2, int MIN_CTAS = 8, bool COOP = false, bool PACKED = true>
+template <bool ANY, bool STATS = false, int CVT_PLANES = 2, int MIN_CTAS = 8, bool COOP = false>
 __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const TraceParams p)
 {
 	const uint32_t magic = p.magic;
@@ -340,11 +224,11 @@ __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const Trac
 					const bool nx = idx < 0.0f, ny = idy < 0.0f, nz = idz < 0.0f;
 					// planes: n2 = (lox.lo, lox.hi, loy.lo, loy.hi) n3 = (loz.lo, loz.hi, hix.lo, hix.hi)
 					//         n4 = (hiy.lo, hiy.hi, hiz.lo, hiz.hi)
-					uint32_t hitmask = test_children4<CVT_PLANES, PACKED>(n1.z, octinv4,
+					uint32_t hitmask = test_children4<CVT_PLANES>(n1.z, octinv4,
 						nx ? n3.z : n2.x, ny ? n4.x : n2.z, nz ? n4.z : n3.x,
 						nx ? n2.x : n3.z, ny ? n2.z : n4.x, nz ? n3.x : n4.z,
 						aix, aiy, aiz, aox, aoy, aoz, tmin, hit_t, magic);
-					hitmask |= test_children4<CVT_PLANES, PACKED>(n1.w, octinv4,
+					hitmask |= test_children4<CVT_PLANES>(n1.w, octinv4,
 						nx ? n3.w : n2.y, ny ? n4.y : n2.w, nz ? n4.w : n3.y,
 						nx ? n2.y : n3.w, ny ? n2.w : n4.y, nz ? n3.y : n4.w,
 						aix, aiy, aiz, aox, aoy, aoz, tmin, hit_t, magic);
@@ -392,9 +276,14 @@ __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const Trac
 							const float rdx = __shfl_sync(kFullMask, dx, owner), rdy = __shfl_sync(kFullMask, dy, owner), rdz = __shfl_sync(kFullMask, dz, owner);
 							if (has) {
 								const float4 *wp = p.woop + (size_t)tr * 3u;
-								const float4 w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
-								float tt, tu, tv;
-								woop_test<PACKED>(w0, w1, w2, rox, roy, roz, rdx, rdy, rdz, tt, tu, tv);
+								const float4 m0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
+								const float toz = __fsub_rn(m0.w, dot3_fma(rox, roy, roz, m0));
+								const float tidz = __frcp_rn(dot3_fma(rdx, rdy, rdz, m0));
+								const float tt = __fmul_rn(toz, tidz);
+								const float tox = __fadd_rn(w1.w, dot3_fma(rox, roy, roz, w1));
+								const float tu = __fmaf_rn(tt, dot3_fma(rdx, rdy, rdz, w1), tox);
+								const float toy = __fadd_rn(w2.w, dot3_fma(rox, roy, roz, w2));
+								const float tv = __fmaf_rn(tt, dot3_fma(rdx, rdy, rdz, w2), toy);
 								const bool inside = tu >= 0.0f && tu <= 1.0f && tv >= 0.0f && __fadd_rn(tu, tv) <= 1.0f;
 								wk[j] = make_float4(tt, tu, tv, __int_as_float(inside ? (int)tr : -1));
 							}
@@ -421,10 +310,15 @@ __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const Trac
 					const uint32_t tr = tg.x + (uint32_t)(__ffs((int)tg.y) - 1);
 					tg.y &= tg.y - 1u;
 					const float4 *wp = p.woop + (size_t)tr * 3u;
-					const float4 w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
+					const float4 m0 = __ldg(wp), m1 = __ldg(wp + 1), m2 = __ldg(wp + 2);
 					if (STATS) ++st_tris;
-					float tt, tu, tv;
-					woop_test<PACKED>(w0, w1, w2, ox, oy, oz, dx, dy, dz, tt, tu, tv);
+					const float toz = __fsub_rn(m0.w, dot3_fma(ox, oy, oz, m0));
+					const float tidz = __frcp_rn(dot3_fma(dx, dy, dz, m0));
+					const float tt = __fmul_rn(toz, tidz);
+					const float tox = __fadd_rn(m1.w, dot3_fma(ox, oy, oz, m1));
+					const float tu = __fmaf_rn(tt, dot3_fma(dx, dy, dz, m1), tox);
+					const float toy = __fadd_rn(m2.w, dot3_fma(ox, oy, oz, m2));
+					const float tv = __fmaf_rn(tt, dot3_fma(dx, dy, dz, m2), toy);
 					if (tt > tmin && tt < hit_t && tu >= 0.0f && tu <= 1.0f && tv >= 0.0f && __fadd_rn(tu, tv) <= 1.0f) {
 						hit_t = tt;
 						if (ANY) { finished = true; break; } // :480-483
