@@ -110,12 +110,20 @@ int launch_trace(adypt_scene *s, const float4 *d_rays, uint64_t n, int32_t *d_tr
 	p.magic = 0x4B000000u;
 	p.counter = s->d_counters + (s->counter_cursor++ % kCounterRing);
 	p.refill_threshold = s->refill_threshold > 0 ? s->refill_threshold : 28;
-	int per_sm = s->ctas_per_sm > 0 ? s->ctas_per_sm : (any ? s->occ_any : ((s->variant == 1 || s->variant == 7 || s->variant == 9) ? 6 : s->occ_closest));
+	int per_sm = s->ctas_per_sm > 0 ? s->ctas_per_sm : (any ? s->occ_any : ((s->variant == 1 || s->variant == 7) ? 6 : s->occ_closest));
 	if (per_sm < 1) per_sm = 1;
 	unsigned long long warps_needed = (n + 31) / 32;
 	unsigned long long ctas_needed = (warps_needed + (kTraceBlock / 32) - 1) / (kTraceBlock / 32);
 	unsigned grid = (unsigned)s->sm_count * (unsigned)per_sm;
 	if (ctas_needed < grid) grid = (unsigned)ctas_needed;
+	// pool size: big enough to amortise the atomic, small enough that every resident warp gets several pools
+	// (a 1M-ray batch over 4736 warps would otherwise hand 3906 warps one 256-ray pool each and idle the rest)
+	{
+		const unsigned long long warps = (unsigned long long)grid * (kTraceBlock / 32);
+		unsigned long long chunk = n / (warps * 6ull);
+		chunk = (chunk / 32ull) * 32ull;
+		p.pool_chunk = (uint32_t)(chunk < 32ull ? 32ull : chunk > kPoolChunk ? kPoolChunk : chunk);
+	}
 	ADYPT_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned long long), stream));
 	if (any) trace_kernel<true><<<grid, kTraceBlock, 0, stream>>>(p);
 	else switch (s->variant) { // code-generation variants of the same algorithm (identical results); 0 = tuned default
@@ -126,8 +134,6 @@ int launch_trace(adypt_scene *s, const float4 *d_rays, uint64_t n, int32_t *d_tr
 	case 5: trace_kernel<false, false, 4, 8><<<grid, kTraceBlock, 0, stream>>>(p); break;
 	case 6: trace_kernel<false, false, 6, 8><<<grid, kTraceBlock, 0, stream>>>(p); break;
 	case 7: trace_kernel<false, false, 2, 6><<<grid, kTraceBlock, 0, stream>>>(p); break;
-	case 8: trace_kernel<false, false, 2, 8, true><<<grid, kTraceBlock, 0, stream>>>(p); break;
-	case 9: trace_kernel<false, false, 2, 6, true><<<grid, kTraceBlock, 0, stream>>>(p); break;
 	default: trace_kernel<false><<<grid, kTraceBlock, 0, stream>>>(p); break;
 	}
 	count_launch();
@@ -332,7 +338,7 @@ int adypt_scene_device_bytes(adypt_scene *s, uint64_t *bytes)
 int adypt_trace_configure(adypt_scene *s, int ctas_per_sm, int refill_threshold, int variant)
 {
 	if (!s) return fail(ADYPT_EINVAL, "scene is NULL");
-	if (ctas_per_sm < 0 || refill_threshold < 0 || refill_threshold > 32 || variant < 0 || variant > 9) return fail(ADYPT_EINVAL, "bad tuning value");
+	if (ctas_per_sm < 0 || refill_threshold < 0 || refill_threshold > 32 || variant < 0 || variant > 7) return fail(ADYPT_EINVAL, "bad tuning value");
 	s->ctas_per_sm = ctas_per_sm;
 	s->refill_threshold = refill_threshold;
 	s->variant = variant;
@@ -416,6 +422,7 @@ int adypt_trace_stats(adypt_scene *s, const float *rays, uint64_t n, int memspac
 	p.counter = s->d_counters + (s->counter_cursor++ % kCounterRing);
 	p.stats = d_stats;
 	p.magic = 0x4B000000u;
+	p.pool_chunk = kPoolChunk;
 	p.refill_threshold = s->refill_threshold > 0 ? s->refill_threshold : 28;
 	ADYPT_CUDA(cudaMemset(p.counter, 0, sizeof(unsigned long long)));
 	trace_kernel<false, true><<<(unsigned)s->sm_count * 4u, kTraceBlock>>>(p);

@@ -36,12 +36,13 @@ struct TraceParams {
 	unsigned long long *stats;              // STATS kernels only: [0] nodes visited [1] triangles tested [2] hits [3] max stack depth
 	int refill_threshold;                   // leave the traversal loop when fewer lanes than this are busy
 	uint32_t magic;                         // 0x4B000000, passed as data so ptxas keeps it in a register (see byte_to_float)
+	uint32_t pool_chunk;                    // ray indices a warp takes per atomicAdd (multiple of 32, <= kPoolChunk)
 };
 
 constexpr int kTraceBlock = 128;      // threads per CTA
 constexpr int kSmemStack = 8;         // stack entries per lane kept in shared memory
 constexpr int kLocalStack = 56;       // overflow entries (local memory); total 64 like the oracle
-constexpr unsigned kPoolChunk = 256;  // ray indices a warp takes per atomicAdd
+constexpr unsigned kPoolChunk = 256;  // most ray indices a warp takes per atomicAdd (small batches take fewer, see launch_trace)
 constexpr unsigned kFullMask = 0xffffffffu;
 
 __device__ __forceinline__ float dot3_fma(float ax, float ay, float az, const float4 m)
@@ -111,22 +112,11 @@ __device__ __forceinline__ uint32_t test_children4(uint32_t meta4, uint32_t octi
 #undef ADYPT_CHILD
 }
 
-constexpr int kCoopPerLane = 3;                   // triangles a lane hands to the warp per round (one 3-triangle leaf)
-constexpr int kCoopSlots = 32 * kCoopPerLane;      // work items per warp and round
-
-// COOP: warp-cooperative triangle testing. After a node step the warp's pending triangles (on average 13,
-// spread over a few lanes with 1-6 each) are written to a per-warp work list in shared memory, tested one per
-// lane by ALL 32 lanes (the owner's ray is fetched with shuffles), and the (t,u,v) results are handed back
-// through the same slots; every owner then applies ITS results in ascending triangle order with the
-// reference's strict comparisons. Arithmetic and per-ray order are unchanged -- only which lane evaluates a
-// test differs -- so results stay bit-identical, while the test body runs at ~13/32 instead of 3.6/32 lanes
-// and the Woop loads of a node step are issued as one batch instead of one dependent batch per triangle.
-template <bool ANY, bool STATS = false, int CVT_PLANES = 2, int MIN_CTAS = 8, bool COOP = false>
+template <bool ANY, bool STATS = false, int CVT_PLANES = 2, int MIN_CTAS = 8>
 __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const TraceParams p)
 {
 	const uint32_t magic = p.magic;
 	__shared__ uint2 s_stack[kSmemStack][kTraceBlock];
-	__shared__ float4 s_work[COOP ? kTraceBlock / 32 : 1][COOP ? kCoopSlots : 1];
 	uint2 l_stack[kLocalStack];
 
 	const unsigned tid = threadIdx.x;
@@ -155,11 +145,11 @@ __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const Trac
 		while (idle != 0 && !exhausted) {
 			if (pool_next >= pool_end) {
 				unsigned long long b = 0;
-				if (lane == 0) b = atomicAdd(p.counter, (unsigned long long)kPoolChunk);
+				if (lane == 0) b = atomicAdd(p.counter, (unsigned long long)p.pool_chunk);
 				b = __shfl_sync(kFullMask, b, 0);
 				if (b >= n_rays) { exhausted = true; break; }
 				pool_next = b;
-				pool_end = (b + kPoolChunk < n_rays) ? b + kPoolChunk : n_rays;
+				pool_end = (b + p.pool_chunk < n_rays) ? b + p.pool_chunk : n_rays;
 			}
 			const unsigned long long cand = pool_next + __popc(idle & lt_mask);
 			const bool take = !active && cand < pool_end;
@@ -239,74 +229,8 @@ __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const Trac
 					ng = make_uint2(0u, 0u);
 				}
 
-				}
 				bool finished = false;
-				if (COOP) {
-					float4 *wk = s_work[COOP ? (tid >> 5) : 0];
-					for (;;) {
-						const uint32_t m = (active && !finished) ? tg.y : 0u;
-						if (!__any_sync(kFullMask, m != 0u)) break;
-						const uint32_t m1 = m & (m - 1u), m2 = m1 & (m1 - 1u), m3 = m2 & (m2 - 1u);
-						const uint32_t take = m & ~m3; // the lowest (up to) three set bits
-						const int cnt = __popc(take);
-						int incl = cnt;
-#pragma unroll
-						for (int d = 1; d < 32; d <<= 1) {
-							const int v = __shfl_up_sync(kFullMask, incl, d);
-							if ((int)lane >= d) incl += v;
-						}
-						const int excl = incl - cnt, total = __shfl_sync(kFullMask, incl, 31);
-						{
-							uint32_t mm = take;
-							int pos = excl;
-							while (mm != 0u) {
-								const uint32_t b = (uint32_t)(__ffs((int)mm) - 1);
-								mm &= mm - 1u;
-								wk[pos++] = make_float4(__uint_as_float(lane), __uint_as_float(tg.x + b), 0.0f, 0.0f);
-							}
-						}
-						__syncwarp();
-						for (int j0 = 0; j0 < total; j0 += 32) {
-							const int j = j0 + (int)lane;
-							const bool has = j < total;
-							const float4 item = has ? wk[j] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-							const int owner = (int)__float_as_uint(item.x);
-							const uint32_t tr = __float_as_uint(item.y);
-							const float rox = __shfl_sync(kFullMask, ox, owner), roy = __shfl_sync(kFullMask, oy, owner), roz = __shfl_sync(kFullMask, oz, owner);
-							const float rdx = __shfl_sync(kFullMask, dx, owner), rdy = __shfl_sync(kFullMask, dy, owner), rdz = __shfl_sync(kFullMask, dz, owner);
-							if (has) {
-								const float4 *wp = p.woop + (size_t)tr * 3u;
-								const float4 m0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
-								const float toz = __fsub_rn(m0.w, dot3_fma(rox, roy, roz, m0));
-								const float tidz = __frcp_rn(dot3_fma(rdx, rdy, rdz, m0));
-								const float tt = __fmul_rn(toz, tidz);
-								const float tox = __fadd_rn(w1.w, dot3_fma(rox, roy, roz, w1));
-								const float tu = __fmaf_rn(tt, dot3_fma(rdx, rdy, rdz, w1), tox);
-								const float toy = __fadd_rn(w2.w, dot3_fma(rox, roy, roz, w2));
-								const float tv = __fmaf_rn(tt, dot3_fma(rdx, rdy, rdz, w2), toy);
-								const bool inside = tu >= 0.0f && tu <= 1.0f && tv >= 0.0f && __fadd_rn(tu, tv) <= 1.0f;
-								wk[j] = make_float4(tt, tu, tv, __int_as_float(inside ? (int)tr : -1));
-							}
-						}
-						__syncwarp();
-						for (int k = 0; k < cnt; ++k) { // ascending triangle order, strict comparisons (:235)
-							const float4 r = wk[excl + k];
-							const int id = __float_as_int(r.w);
-							if (id >= 0 && r.x > tmin && r.x < hit_t) {
-								hit_t = r.x;
-								if (ANY) { finished = true; break; }
-								hit_u = r.y;
-								hit_v = r.z;
-								hit_idx = id;
-							}
-						}
-						if (STATS) st_tris += (unsigned long long)cnt;
-						tg.y &= ~take;
-						__syncwarp();
-					}
-				}
-				if (active) {
-				while (!COOP && tg.y != 0u) { // :213-243
+				while (tg.y != 0u) { // :213-243
 					const uint32_t tr = tg.x + (uint32_t)(__ffs((int)tg.y) - 1);
 					tg.y &= tg.y - 1u;
 					const float4 *wp = p.woop + (size_t)tr * 3u;
