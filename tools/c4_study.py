@@ -17,8 +17,9 @@ def timed(fn, n=5):
     return float(np.median(ts))
 
 def main():
-    cells = int(sys.argv[1]) if len(sys.argv) > 1 else 577
-    reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+    args = [a for a in sys.argv[1:] if not a.startswith('--')]
+    cells = int(args[0]) if len(args) > 0 else 577
+    reps = int(args[1]) if len(args) > 1 else 5
     mesh = W.city(cells, 1)
     hs = host.HostScene.from_triangles(mesh.positions(), mesh.face_mat, host.materials_array(mesh.materials))
     cache = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), ".cache", "scenes", mesh.name + ".bvh")
@@ -43,12 +44,27 @@ def main():
     ns = shadow.shape[0]
     d_sh = torch.from_numpy(shadow).cuda(); d_occ = torch.empty(ns, dtype=torch.uint8, device='cuda')
     ms_any = timed(lambda: sc.trace_any(d_sh, d_occ, stream=st), reps)
+    check = {}
+    if "--check" in sys.argv:  # parity at C4 size (test infrastructure: the oracle is the checker)
+        from oracle import cpu
+        woop = cpu.build_woop(hs.tris, hs.tri_indices)
+        assert np.array_equal(sc.read_woop().view(np.uint32), woop.view(np.uint32))
+        sl = slice(2_000_000, 2_250_000)
+        o = cpu.trace_closest(hs.nodes, hs.tri_indices, woop, rays[sl])
+        t = d_t.cpu().numpy()
+        check = {"oracle_slice_rays": 250000, "ids_equal": float((tri[sl] == o["tri"]).mean()), "t_bit_equal": float((t[sl].view(np.uint32) == o["t"].view(np.uint32)).mean()),
+                 "uv_bit_equal": float((uv[sl].view(np.uint32) == o["uv"].view(np.uint32)).all(axis=1).mean()), "oracle_max_stack": o["counters"]["max_stack"]}
+        d_any = torch.empty(n, dtype=torch.uint8, device='cuda')
+        sc.trace_any(d_rays, d_any, stream=st); torch.cuda.synchronize()
+        check["any_equals_closest_hit_all_8M"] = bool(np.array_equal(d_any.cpu().numpy() != 0, tri >= 0))
+        oa = cpu.trace_any(hs.nodes, woop, shadow[:250000])
+        check["shadow_any_equal"] = float((d_occ.cpu().numpy()[:250000] == oa["occluded"]).mean())
     bpr = 80.0 * stats['nodes'] / n + 48.0 * stats['tris'] / n + 4.0 * stats['hits'] / n + 48.0
     print(json.dumps({"config": f"C4: cells={cells}", "triangles": int(mesh.n_tris), "refs": int(hs.tri_indices.size), "nodes": int(hs.nodes.shape[0]),
                       "bvh_bytes": int(hs.nodes.shape[0] * 80 + hs.tri_indices.size * 52), "scene_device_bytes": sc.device_bytes(), "build_or_load_s": build_s,
                       "closest": {"rays": n, "ms": ms_closest, "Mrays_per_s": n / ms_closest / 1e3, "nodes_per_ray": stats['nodes'] / n, "tris_per_ray": stats['tris'] / n,
                                   "hit_fraction": stats['hits'] / n, "max_stack": stats['max_stack'], "bytes_per_ray": bpr, "algorithmic_GBps": bpr * n / ms_closest / 1e6},
-                      "any": {"rays": ns, "ms": ms_any, "Mrays_per_s": ns / ms_any / 1e3, "occluded_fraction": float(d_occ.float().mean().item())}}))
+                      "any": {"rays": ns, "ms": ms_any, "Mrays_per_s": ns / ms_any / 1e3, "occluded_fraction": float(d_occ.float().mean().item())}, "parity": check}))
 
 if __name__ == '__main__':
     main()
