@@ -28,7 +28,7 @@ EXPORTS = [
     "adypt_host_scene_load_textures", "adypt_host_scene_texture",
     "adypt_scene_read_woop", "adypt_scene_device_bytes", "adypt_trace_closest", "adypt_trace_any", "adypt_trace_stats", "adypt_launch_count",
     "adypt_trace_configure", "adypt_tracer_create", "adypt_tracer_destroy", "adypt_tracer_set_config",
-    "adypt_tracer_set_bias", "adypt_tracer_get_bias", "adypt_tracer_set_camera", "adypt_camera_matrices",
+    "adypt_tracer_set_bias", "adypt_tracer_get_bias", "adypt_tracer_set_sun_visibility", "adypt_tracer_set_camera", "adypt_camera_matrices",
     "adypt_tracer_primary", "adypt_tracer_sample", "adypt_tracer_accumulate", "adypt_tracer_sum_buffer",
     "adypt_tracer_clear_sum", "adypt_tracer_resolve_sum", "adypt_tracer_spp", "adypt_tracer_read",
     "adypt_tracer_result_buffer", "adypt_tracer_save_exr", "adypt_tracer_sync", "adypt_tracer_primary_rays",
@@ -97,6 +97,7 @@ def load_library():
         "adypt_tracer_set_config": [vp, C.POINTER(PTConfig)],
         "adypt_tracer_set_bias": [vp, vp],
         "adypt_tracer_get_bias": [vp, vp],
+        "adypt_tracer_set_sun_visibility": [vp, i32, vp],
         "adypt_tracer_set_camera": [vp, vp, vp, vp],
         "adypt_camera_matrices": [C.c_float, C.c_float, C.c_float, i32, i32, vp, vp],
         "adypt_tracer_primary": [vp, i32],
@@ -319,6 +320,11 @@ class Tracer:
         out = np.zeros((self.height, self.width, 2), dtype=np.uint8)
         _check(load_library().adypt_tracer_get_bias(self._h, out.ctypes.data))
         return out
+
+    def set_sun_visibility(self, enabled: bool, direction=(0.6, 1.0, 0.2)):
+        """Connect stage: the any-hit sun test the reference has commented out (pathtracer.glsl:132)."""
+        d = np.ascontiguousarray(direction, dtype=np.float32)
+        _check(load_library().adypt_tracer_set_sun_visibility(self._h, int(enabled), d.ctypes.data))
 
     def set_camera(self, projection, view, position):
         """SetCamera(projection, view, position) (OglPathTracer.cpp:27-32)."""

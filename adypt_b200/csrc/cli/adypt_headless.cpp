@@ -4,6 +4,7 @@
 //   adypt_headless scene.config [--spp N] [--out result.exr] [--fp16] [--seed S] [--device D]
 //                  [--viewer diffuse|specular|emissive|normal|position] [--per-frame] [--no-bvh-cache] [--keep-config]
 //                  [--preview-every N]   (progressive preview: also writes <out>.<spp>spp.exr every N samples)
+//                  [--sun-visibility]    (connect stage: the any-hit sun test of pathtracer.glsl:132)
 //
 // Same file formats as the reference (.config JSON, OBJ/MTL, .bvh cache); --spp/--seed/--out are new (the
 // reference renders until the user stops it and seeds from std::random_device).
@@ -26,7 +27,7 @@ int main(int argc, char **argv)
 	if (argc < 2) return usage();
 	const char *config = nullptr, *out = "result.exr", *viewer = nullptr;
 	int spp = 64, device = 0, preview_every = 0;
-	bool fp16 = false, per_frame = false, cache = true, keep = false;
+	bool fp16 = false, per_frame = false, cache = true, keep = false, sun_visibility = false;
 	unsigned long long seed = 0;
 	for (int i = 1; i < argc; ++i) {
 		const char *a = argv[i];
@@ -38,6 +39,7 @@ int main(int argc, char **argv)
 		else if (!strcmp(a, "--device")) device = atoi(next());
 		else if (!strcmp(a, "--viewer")) viewer = next();
 		else if (!strcmp(a, "--preview-every")) preview_every = atoi(next());
+		else if (!strcmp(a, "--sun-visibility")) sun_visibility = true; // the shader's commented-out any-hit sun test (pathtracer.glsl:132)
 		else if (!strcmp(a, "--per-frame")) per_frame = true; // one Trace(true) per sample, like the viewer's main loop
 		else if (!strcmp(a, "--no-bvh-cache")) cache = false;
 		else if (!strcmp(a, "--keep-config")) keep = true;    // do not rewrite the .config on exit
@@ -53,6 +55,10 @@ int main(int argc, char **argv)
 	instance.m_path_tracer.m_bias_seed = seed;
 	if (!instance.InitializeFromFile(config)) return 1;
 
+	if (sun_visibility) {
+		const float dir[3] = {0.6f, 1.0f, 0.2f};
+		adypt_tracer_set_sun_visibility(instance.m_path_tracer.Handle(), 1, dir);
+	}
 	instance.m_enable_pt_flag = false;
 	if (viewer) {
 		static const char *names[] = {"diffuse", "specular", "emissive", "radiance", "normal", "position"};

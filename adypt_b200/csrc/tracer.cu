@@ -18,6 +18,7 @@
 // (the library is built with -fmad=false), sqrt and division are IEEE, and sin/cos/pow are the deterministic
 // double-precision recipes of detmath.cuh -- so images match the CPU oracle bit for bit.
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <vector>
 #include "detmath.cuh"
@@ -131,6 +132,10 @@ struct ShadeBuffers {
 	float4 *__restrict__ color;              // throughput
 	float4 *__restrict__ ret;                // radiance so far; final value once the path ends
 	unsigned long long *segments;            // statistics
+	// connect stage (optional): shadow rays towards a fixed sun direction for paths that left the scene
+	float4 *__restrict__ conn_rays;          // nullptr when the stage is off
+	unsigned long long *conn_count;
+	float sun_dir[3];
 };
 
 __device__ __forceinline__ V3 load3(const float *p) { return v3(p[0], p[1], p[2]); }
@@ -195,14 +200,23 @@ __device__ __forceinline__ V3 align_direction(V3 dir, V3 target) // :66-71
 	return u * dir.x + v * dir.y + target * dir.z;
 }
 
+enum SegmentResult { kEnded = 0, kContinues = 1, kConnects = 2 };
+
 // One segment of Render's loop body after the intersection (pathtracer.glsl:130-201).
-// Returns true when the path continues with (origin, dir); false when it has ended (ret is final).
-__device__ __forceinline__ bool shade_segment(const ShadeBuffers &B, const PTArgs &A, int b, int32_t tri_idx, float u, float v, float rx,
+// kContinues: the path goes on with (origin, dir). kEnded: ret is final. kConnects (only when the connect
+// stage is on): the path left the scene; `color` now holds the sun contribution that is added to ret iff the
+// shadow ray from `origin` towards the sun is unoccluded -- the test the reference carries commented out at
+// pathtracer.glsl:132.
+__device__ __forceinline__ SegmentResult shade_segment(const ShadeBuffers &B, const PTArgs &A, int b, int32_t tri_idx, float u, float v, float rx,
                                               float ry, V3 &origin, V3 &dir, V3 &color, V3 &ret)
 {
 	if (tri_idx == -1) { // :130-135
+		if (B.conn_rays != nullptr) {
+			color = color * v3(A.sun[0], A.sun[1], A.sun[2]);
+			return kConnects;
+		}
 		ret = ret + color * v3(A.sun[0], A.sun[1], A.sun[2]);
-		return false;
+		return kEnded;
 	}
 	const float *t = (const float *)(B.tris + (size_t)tri_idx * 100u);
 	const int32_t matid = *(const int32_t *)(t + 24);
@@ -211,7 +225,7 @@ __device__ __forceinline__ bool shade_segment(const ShadeBuffers &B, const PTArg
 	origin = bary(t, t + 3, t + 6, u, v); // :138
 	const V3 emissive = v3(m.er, m.eg, m.eb), diffuse = diffuse_of(B.texels, B.tex_table, m, t, u, v), specular = v3(m.sr, m.sg, m.sb);
 	ret = ret + color * emissive;
-	if (b == A.max_bounce - 1) return false; // the loop ends here; the sampled direction would never be used
+	if (b == A.max_bounce - 1) return kEnded; // the loop ends here; the sampled direction would never be used
 	if (m.illum < 6 && dot(dir, normal) > 0.0f) normal = -normal; // :141-142
 
 	bool do_diffuse = false;
@@ -221,7 +235,7 @@ __device__ __forceinline__ bool shade_segment(const ShadeBuffers &B, const PTArg
 		if (e > 0.3f) {
 			const V3 r = reflect(dir, normal), s = sample_hemisphere(rx, ry, e);
 			dir = align_direction(s, r);
-			if (dot(dir, normal) < 0.0f) return false;
+			if (dot(dir, normal) < 0.0f) return kEnded;
 			color = color * (diffuse + specular * detmath::pow(dot(dir, r), e));
 		} else
 			do_diffuse = true;
@@ -263,7 +277,7 @@ __device__ __forceinline__ bool shade_segment(const ShadeBuffers &B, const PTArg
 		dir = align_direction(sample_hemisphere(rx, ry, 0.0f), normal);
 		color = color * diffuse;
 	}
-	return true;
+	return kContinues;
 }
 
 // warp-aggregated append: returns this lane's slot in the output queue (valid when `keep`)
@@ -290,7 +304,7 @@ __global__ void __launch_bounds__(256) k_shade_primary(ShadeBuffers B, PTArgs A,
 	const int dims = 2 * A.max_bounce;
 	for (unsigned long long r = 0; r < rounds; ++r) {
 		const unsigned long long id = r * stride + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-		bool keep = false;
+		bool keep = false, conn = false;
 		V3 origin = v3(cam.origin[0], cam.origin[1], cam.origin[2]), dir = v3(0, 0, 0), color = v3(1.f, 1.f, 1.f), ret = v3(0.f, 0.f, 0.f);
 		if (id < total) {
 			const unsigned pix = (unsigned)(id % npix), s = (unsigned)(id / npix);
@@ -299,14 +313,23 @@ __global__ void __launch_bounds__(256) k_shade_primary(ShadeBuffers B, PTArgs A,
 			const float rx = fract(B.sobol[s * dims + 0] + (float)bb.x / 255.0f);
 			const float ry = fract(B.sobol[s * dims + 1] + (float)bb.y / 255.0f);
 			const float2 uv = B.prim_uv[pix];
-			keep = shade_segment(B, A, 0, B.prim_tri[pix], uv.x, uv.y, rx, ry, origin, dir, color, ret);
+			const SegmentResult res = shade_segment(B, A, 0, B.prim_tri[pix], uv.x, uv.y, rx, ry, origin, dir, color, ret);
+			keep = res == kContinues;
+			conn = res == kConnects; // origin is still the camera position
 			B.ret[id] = make_float4(ret.x, ret.y, ret.z, 0.0f);
-			if (keep) B.color[id] = make_float4(color.x, color.y, color.z, 0.0f);
+			if (keep || conn) B.color[id] = make_float4(color.x, color.y, color.z, 0.0f);
 		}
 		const unsigned long long slot = queue_append(keep, B.out_count);
 		if (keep) {
 			B.out_rays[2 * slot] = make_float4(origin.x, origin.y, origin.z, cam.tmin);
 			B.out_rays[2 * slot + 1] = make_float4(dir.x, dir.y, dir.z, __uint_as_float((unsigned)id));
+		}
+		if (B.conn_rays != nullptr) {
+			const unsigned long long cs = queue_append(conn, B.conn_count);
+			if (conn) {
+				B.conn_rays[2 * cs] = make_float4(origin.x, origin.y, origin.z, cam.tmin);
+				B.conn_rays[2 * cs + 1] = make_float4(B.sun_dir[0], B.sun_dir[1], B.sun_dir[2], __uint_as_float((unsigned)id));
+			}
 		}
 	}
 }
@@ -322,7 +345,7 @@ __global__ void __launch_bounds__(256) k_shade_bounce(ShadeBuffers B, PTArgs A, 
 	if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(B.segments, total);
 	for (unsigned long long r = 0; r < rounds; ++r) {
 		const unsigned long long q = r * stride + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-		bool keep = false;
+		bool keep = false, conn = false;
 		V3 origin = v3(0, 0, 0), dir = v3(0, 0, 0), color = v3(0, 0, 0), ret = v3(0, 0, 0);
 		unsigned id = 0;
 		if (q < total) {
@@ -337,15 +360,45 @@ __global__ void __launch_bounds__(256) k_shade_bounce(ShadeBuffers B, PTArgs A, 
 			color = v3(c4.x, c4.y, c4.z);
 			ret = v3(r4.x, r4.y, r4.z);
 			const float2 uv = B.in_uv[q];
-			keep = shade_segment(B, A, b, B.in_tri[q], uv.x, uv.y, rx, ry, origin, dir, color, ret);
+			const SegmentResult res = shade_segment(B, A, b, B.in_tri[q], uv.x, uv.y, rx, ry, origin, dir, color, ret);
+			keep = res == kContinues;
+			conn = res == kConnects;
+			if (conn) { // the shadow ray starts where this segment started: the previous hit point
+				const float4 r0 = B.in_rays[2 * q];
+				origin = v3(r0.x, r0.y, r0.z);
+			}
 			B.ret[id] = make_float4(ret.x, ret.y, ret.z, 0.0f);
-			if (keep) B.color[id] = make_float4(color.x, color.y, color.z, 0.0f);
+			if (keep || conn) B.color[id] = make_float4(color.x, color.y, color.z, 0.0f);
 		}
 		const unsigned long long slot = queue_append(keep, B.out_count);
 		if (keep) {
 			B.out_rays[2 * slot] = make_float4(origin.x, origin.y, origin.z, tmin);
 			B.out_rays[2 * slot + 1] = make_float4(dir.x, dir.y, dir.z, __uint_as_float(id));
 		}
+		if (B.conn_rays != nullptr) {
+			const unsigned long long cs = queue_append(conn, B.conn_count);
+			if (conn) {
+				B.conn_rays[2 * cs] = make_float4(origin.x, origin.y, origin.z, tmin);
+				B.conn_rays[2 * cs + 1] = make_float4(B.sun_dir[0], B.sun_dir[1], B.sun_dir[2], __uint_as_float(id));
+			}
+		}
+	}
+}
+
+// connect: ret += colour * sun for every escaped path whose shadow ray reached the sun (occ == 0)
+__global__ void k_connect_apply(const float4 *__restrict__ conn_rays, const uint8_t *__restrict__ occ, const unsigned long long *count,
+                                const float4 *__restrict__ color, float4 *__restrict__ ret)
+{
+	const unsigned long long total = *count;
+	for (unsigned long long q = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; q < total; q += (unsigned long long)gridDim.x * blockDim.x) {
+		if (occ[q]) continue;
+		const unsigned id = __float_as_uint(conn_rays[2 * q + 1].w);
+		const float4 c = color[id];
+		float4 r = ret[id];
+		r.x = r.x + c.x;
+		r.y = r.y + c.y;
+		r.z = r.z + c.z;
+		ret[id] = r;
 	}
 }
 
@@ -456,7 +509,13 @@ struct adypt_tracer {
 	int32_t *d_hit_tri = nullptr;
 	float2 *d_hit_uv = nullptr;
 	float4 *d_color = nullptr, *d_ret = nullptr;
-	unsigned long long *d_counts = nullptr; // [max_bounce + 1] queue lengths, [kCountSlots-1] = segments
+	unsigned long long *d_counts = nullptr; // [max_bounce + 1] queue lengths, [kConnBase + b] connect queues, [kCountSlots-1] = segments
+	// connect stage (off by default: the reference's sun test is commented out, pathtracer.glsl:132)
+	bool sun_visibility = false;
+	float sun_dir[3] = {0.f, 0.f, 0.f};
+	float4 *d_conn_rays = nullptr;
+	uint8_t *d_conn_occ = nullptr;
+	unsigned long long conn_capacity = 0;
 	uint64_t launches_at_create = 0;
 	uint64_t host_segments = 0;  // primary segments (known on the host)
 };
@@ -464,6 +523,7 @@ struct adypt_tracer {
 namespace {
 
 constexpr int kCountSlots = 72;
+constexpr int kConnBase = 36; // d_counts[kConnBase + b]: length of bounce b's connect queue
 constexpr unsigned long long kDefaultMaxPaths = 48ull << 20;
 
 void free_tracer(adypt_tracer *t)
@@ -472,7 +532,7 @@ void free_tracer(adypt_tracer *t)
 	if (t->stream) cudaStreamSynchronize(t->stream);
 	cudaFree(t->d_result); cudaFree(t->d_sum); cudaFree(t->d_prim_tri); cudaFree(t->d_prim_uv); cudaFree(t->d_bias);
 	cudaFree(t->d_dirs); cudaFree(t->d_sobol); cudaFree(t->d_rays[0]); cudaFree(t->d_rays[1]); cudaFree(t->d_hit_tri);
-	cudaFree(t->d_hit_uv); cudaFree(t->d_color); cudaFree(t->d_ret); cudaFree(t->d_counts);
+	cudaFree(t->d_hit_uv); cudaFree(t->d_color); cudaFree(t->d_ret); cudaFree(t->d_counts); cudaFree(t->d_conn_rays); cudaFree(t->d_conn_occ);
 	if (t->stream) cudaStreamDestroy(t->stream);
 	delete t;
 }
@@ -552,7 +612,7 @@ int run_batch(adypt_tracer *t, int first, int n, bool sum_mode)
 	const int dims = 2 * c.max_bounce;
 	k_sobol<<<(dims * n + 127) / 128, 128, 0, t->stream>>>(t->d_dirs, dims, first, n, t->d_sobol);
 	count_launch();
-	ADYPT_CUDA(cudaMemsetAsync(t->d_counts, 0, (size_t)(c.max_bounce + 1) * sizeof(unsigned long long), t->stream));
+	ADYPT_CUDA(cudaMemsetAsync(t->d_counts, 0, (size_t)(kCountSlots - 1) * sizeof(unsigned long long), t->stream));
 	ShadeBuffers B;
 	B.tris = s->d_tris; B.mats = s->d_mats; B.texels = s->d_texels; B.tex_table = s->d_tex_table; B.bias = t->d_bias; B.sobol = t->d_sobol;
 	B.prim_tri = t->d_prim_tri; B.prim_uv = t->d_prim_uv;
@@ -560,9 +620,32 @@ int run_batch(adypt_tracer *t, int first, int n, bool sum_mode)
 	B.out_rays = t->d_rays[1]; B.out_count = t->d_counts + 1;
 	B.color = t->d_color; B.ret = t->d_ret; B.segments = t->d_counts + (kCountSlots - 1);
 	const unsigned long long total = (unsigned long long)n * t->npix;
+	B.conn_rays = nullptr; B.conn_count = nullptr;
+	B.sun_dir[0] = t->sun_dir[0]; B.sun_dir[1] = t->sun_dir[1]; B.sun_dir[2] = t->sun_dir[2];
+	if (t->sun_visibility) {
+		if (t->conn_capacity < total) {
+			cudaFree(t->d_conn_rays); cudaFree(t->d_conn_occ);
+			t->d_conn_rays = nullptr; t->d_conn_occ = nullptr; t->conn_capacity = 0;
+			ADYPT_CUDA(cudaMalloc((void **)&t->d_conn_rays, total * 32u));
+			ADYPT_CUDA(cudaMalloc((void **)&t->d_conn_occ, total));
+			t->conn_capacity = total;
+		}
+		B.conn_rays = t->d_conn_rays;
+		B.conn_count = t->d_counts + kConnBase;
+	}
+	// connect stage of bounce b: any-hit over the shadow rays queued by the shade kernel, then add the sun term
+	auto connect = [&](int b) -> int {
+		if (!t->sun_visibility) return ADYPT_OK;
+		ADYPT_TRY(launch_trace(s, t->d_conn_rays, total, nullptr, nullptr, nullptr, t->d_conn_occ, t->stream, t->d_counts + kConnBase + b));
+		k_connect_apply<<<grid_for(total, 256, s->sm_count), 256, 0, t->stream>>>(t->d_conn_rays, t->d_conn_occ, t->d_counts + kConnBase + b, t->d_color, t->d_ret);
+		count_launch();
+		ADYPT_CUDA(cudaGetLastError());
+		return ADYPT_OK;
+	};
 	k_shade_primary<<<grid_for(total, 256, s->sm_count), 256, 0, t->stream>>>(B, A, t->cam);
 	count_launch();
 	ADYPT_CUDA(cudaGetLastError());
+	ADYPT_TRY(connect(0));
 	int cur = 1;
 	for (int b = 1; b < c.max_bounce; ++b) {
 		// extend: queue length is read on the device
@@ -571,9 +654,11 @@ int run_batch(adypt_tracer *t, int first, int n, bool sum_mode)
 		B.in_count = t->d_counts + b;
 		B.out_rays = t->d_rays[cur ^ 1];
 		B.out_count = t->d_counts + b + 1;
+		if (t->sun_visibility) B.conn_count = t->d_counts + kConnBase + b;
 		k_shade_bounce<<<grid_for(total, 256, s->sm_count), 256, 0, t->stream>>>(B, A, b, c.ray_tmin);
 		count_launch();
 		ADYPT_CUDA(cudaGetLastError());
+		ADYPT_TRY(connect(b));
 		cur ^= 1;
 	}
 	const int g = grid_for(t->npix, 256, s->sm_count);
@@ -664,6 +749,21 @@ int adypt_tracer_set_config(adypt_tracer *t, const adypt_pt_config *config)
 	t->cfg = *config;
 	t->cam.tmin = config->ray_tmin; // update_config_args, OglPathTracer.cpp:216
 	t->prim_valid = false;
+	return ADYPT_OK;
+}
+
+int adypt_tracer_set_sun_visibility(adypt_tracer *t, int32_t enabled, const float direction[3])
+{
+	if (!t || (enabled && !direction)) return fail(ADYPT_EINVAL, "NULL argument");
+	t->sun_visibility = enabled != 0;
+	if (enabled) {
+		// normalize(vec3(...)) as the shader would (un-fused fp32, IEEE sqrt / divide)
+		const float x = direction[0], y = direction[1], z = direction[2];
+		const float inv = 1.0f / sqrtf(x * x + y * y + z * z);
+		t->sun_dir[0] = x * inv;
+		t->sun_dir[1] = y * inv;
+		t->sun_dir[2] = z * inv;
+	}
 	return ADYPT_OK;
 }
 

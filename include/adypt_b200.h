@@ -144,6 +144,12 @@ int adypt_tracer_set_config(adypt_tracer *tracer, const adypt_pt_config *config)
 int adypt_tracer_set_bias(adypt_tracer *tracer, const uint8_t *rg8);
 int adypt_tracer_get_bias(adypt_tracer *tracer, uint8_t *rg8);
 
+/* The wavefront's CONNECT stage. The reference carries a sun-visibility test in its shader, commented out
+ * (shaders/pathtracer.glsl:132): a path that leaves the scene only receives the `sun` radiance if an any-hit ray
+ * from its last origin towards normalize(vec3(0.6, 1, 0.2)) is unoccluded. enabled != 0 switches that line on
+ * (direction is normalised inside); the default, 0, is the reference's shipped behaviour. */
+int adypt_tracer_set_sun_visibility(adypt_tracer *tracer, int32_t enabled, const float direction[3]);
+
 /* OglPathTracer::SetCamera(const mat4& projection, const mat4& view, const vec3& position)
  * (OglPathTracer.cpp:27-32): column-major float[16]; the inverses are computed inside with glm::inverse's
  * arithmetic order. */

