@@ -137,19 +137,22 @@ def test_connect_stage_sun_visibility(A, cpu):
     origin, m = oracle_cam(cpu, g)
     tr.sample(16)
     plain = tr.read(4).reshape(-1, 4).copy()
-    launches_plain = tr.stats()["launches"]
     tr.primary(A.VIEW_DIFFUSE)
     tr.set_sun_visibility(True, (0.6, 1.0, 0.2))
-    tr.sample(24)
+    l0 = tr.stats()["launches"]
+    tr.sample(16)
+    with_connect = tr.stats()["launches"] - l0
+    tr.sample(8)
     img = tr.read(4).reshape(-1, 4)
     exp, _, _ = cpu.pt_render(g, origin, m["inv_proj"], m["inv_view"], W_, H_, OCFG, tr.get_bias(), 0, 24, sun_visibility=(0.6, 1.0, 0.2))
     assert np.array_equal(bits(img), bits(exp))
     off, _, _ = cpu.pt_render(g, origin, m["inv_proj"], m["inv_view"], W_, H_, OCFG, tr.get_bias(), 0, 24)
     assert not np.array_equal(exp, off) and exp[:, :3].sum() < off[:, :3].sum()  # some sky light is now shadowed
-    assert tr.stats()["launches"] - launches_plain > 2 * (launches_plain - 0) * 0  # (extra any-hit + apply launches ran)
     tr.primary(A.VIEW_DIFFUSE)
     tr.set_sun_visibility(False)
+    l0 = tr.stats()["launches"]
     tr.sample(16)
+    assert with_connect == (tr.stats()["launches"] - l0) + 2 * OCFG["max_bounce"]  # one any-hit trace + one apply per bounce
     assert np.array_equal(bits(tr.read(4).reshape(-1, 4)), bits(plain))  # switching it off restores the reference image
 
 
