@@ -130,6 +130,7 @@ __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const Trac
 
 	// per-lane ray state
 	bool active = false;
+	bool unsaved = false; // the lane's finished ray still has its result in registers (stored at the next refill)
 	unsigned long long ray_idx = 0;
 	float ox = 0, oy = 0, oz = 0, tmin = 0, dx = 0, dy = 0, dz = 0, idx = 0, idy = 0, idz = 0;
 	uint32_t octinv = 0;
@@ -142,6 +143,19 @@ __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const Trac
 	for (;;) {
 		// ---------------------------------------------------------------- refill idle lanes
 		unsigned idle = __ballot_sync(kFullMask, !active);
+		// Results of rays that finished since the last refill are written here, by all such lanes together
+		// (about 6 per pass), instead of by 1-3 lanes at the moment each ray ends.
+		if (unsaved) {
+			unsaved = false;
+			if (STATS && hit_t < 1e9f) ++st_hits;
+			if (ANY) {
+				p.out_occ[ray_idx] = (hit_t < 1e9f) ? 1 : 0;
+			} else {
+				p.out_tri[ray_idx] = hit_idx >= 0 ? __ldg(p.tri_indices + hit_idx) : -1; // :253-254
+				if (p.out_t) p.out_t[ray_idx] = hit_t;
+				if (p.out_uv) p.out_uv[ray_idx] = make_float2(hit_u, hit_v);
+			}
+		}
 		while (idle != 0 && !exhausted) {
 			if (pool_next >= pool_end) {
 				unsigned long long b = 0;
@@ -163,9 +177,9 @@ __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const Trac
 				dy = fabsf(r1.y) > ooeps ? r1.y : (r1.y >= 0.0f ? ooeps : -ooeps);
 				dz = fabsf(r1.z) > ooeps ? r1.z : (r1.z >= 0.0f ? ooeps : -ooeps);
 				const float len2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-				const float inv = __fdiv_rn(1.0f, __fsqrt_rn(len2));
+				const float inv = __frcp_rn(__fsqrt_rn(len2)); // 1/x correctly rounded == IEEE 1.0f / x
 				dx = __fmul_rn(dx, inv); dy = __fmul_rn(dy, inv); dz = __fmul_rn(dz, inv);
-				idx = __fdiv_rn(1.0f, dx); idy = __fdiv_rn(1.0f, dy); idz = __fdiv_rn(1.0f, dz);
+				idx = __frcp_rn(dx); idy = __frcp_rn(dy); idz = __frcp_rn(dz);
 				octinv = 7u - ((dx < 0.0f ? 1u : 0u) | (dy < 0.0f ? 2u : 0u) | (dz < 0.0f ? 4u : 0u));
 				hit_t = 1e9f; hit_idx = -1; hit_u = 0.0f; hit_v = 0.0f;
 				ng = make_uint2(0u, 0x80000000u);
@@ -262,14 +276,7 @@ __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const Trac
 
 				if (finished) {
 					active = false;
-					if (STATS && hit_t < 1e9f) ++st_hits;
-					if (ANY) {
-						p.out_occ[ray_idx] = (hit_t < 1e9f) ? 1 : 0;
-					} else {
-						p.out_tri[ray_idx] = hit_idx >= 0 ? __ldg(p.tri_indices + hit_idx) : -1; // :253-254
-						if (p.out_t) p.out_t[ray_idx] = hit_t;
-						if (p.out_uv) p.out_uv[ray_idx] = make_float2(hit_u, hit_v);
-					}
+					unsaved = true;
 				}
 			}
 			busy = __ballot_sync(kFullMask, active);
