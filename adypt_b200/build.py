@@ -17,7 +17,7 @@ LIB = os.path.join(LIBDIR, "libadypt_b200.so")
 BINDIR = os.path.join(HERE, "bin")
 CLI = os.path.join(BINDIR, "adypt_headless")
 
-CU_SOURCES = ["scene.cu", "tracer.cu"]
+CU_SOURCES = ["scene.cu", "tracer.cu", "group.cu"]
 CPP_SOURCES = ["hostmath.cpp", "exr.cpp", "host/bvh_build.cpp", "host/obj_loader.cpp", "host/host_api.cpp", "host/config.cpp", "host/image_decode.cpp"]
 
 NVCC_FLAGS = [
@@ -65,7 +65,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError(f"nvcc failed on {src}:\n{out}")
         if verbose:
             print(out)
-    link = [nvcc, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-lz"]
+    link = [nvcc, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-lz", "-ldl"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")

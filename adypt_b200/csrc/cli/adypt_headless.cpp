@@ -5,6 +5,7 @@
 //                  [--viewer diffuse|specular|emissive|normal|position] [--per-frame] [--no-bvh-cache] [--keep-config]
 //                  [--preview-every N]   (progressive preview: also writes <out>.<spp>spp.exr every N samples)
 //                  [--sun-visibility]    (connect stage: the any-hit sun test of pathtracer.glsl:132)
+//                  [--gpus N]            (sample-sharded over devices 0..N-1 of this box, one NCCL reduce)
 //
 // Same file formats as the reference (.config JSON, OBJ/MTL, .bvh cache); --spp/--seed/--out are new (the
 // reference renders until the user stops it and seeds from std::random_device).
@@ -22,11 +23,63 @@ static int usage()
 	return 2;
 }
 
+// --gpus N: the same load path as Instance::Initialize (Instance.cpp:10-42), then a render group instead of one tracer
+static int render_on_group(const char *config, int spp, int gpus, const char *out, bool fp16, unsigned long long seed, bool cache, bool sun_visibility)
+{
+	InstanceConfig cfg;
+	if (!cfg.LoadFromFile(config)) {
+		printf("[INSTANCE]Err: Invalid instance %s\n", config);
+		return 1;
+	}
+	Scene scene;
+	if (!scene.LoadFromFile(cfg.m_obj_filename.c_str())) {
+		printf("[INSTANCE]Err: Unable to load scene %s\n", cfg.m_obj_filename.c_str());
+		return 1;
+	}
+	WideBVH wbvh(&scene);
+	if (!cache || !wbvh.LoadFromFile(cfg.m_bvh_filename.c_str(), cfg.m_bvh_cfg)) {
+		if (!wbvh.Build(cfg.m_bvh_cfg)) return 1;
+		wbvh.SaveToFile(cfg.m_bvh_filename.c_str(), cfg.m_bvh_cfg);
+	}
+	adypt_host_scene_load_textures(scene.m_handle, nullptr, nullptr);
+	int32_t devices[64];
+	for (int i = 0; i < gpus && i < 64; ++i) devices[i] = i;
+	adypt_group *group = nullptr;
+	if (adypt_group_create(scene.m_handle, (const adypt_pt_config *)&cfg.m_pt_cfg, cfg.m_width, cfg.m_height, seed, devices, (uint32_t)gpus, &group) != ADYPT_OK) {
+		printf("[PT]ERR: %s\n", adypt_last_error());
+		return 1;
+	}
+	Camera camera;
+	camera.Initialize(&cfg.m_cam_cfg, cfg.m_width, cfg.m_height);
+	float proj[16], view[16];
+	camera.GetProjection(proj);
+	camera.GetView(view);
+	adypt_group_set_camera(group, proj, view, cfg.m_cam_cfg.m_position);
+	if (sun_visibility) {
+		const float dir[3] = {0.6f, 1.0f, 0.2f};
+		adypt_group_set_sun_visibility(group, 1, dir);
+	}
+	adypt_group_render(group, 16); // warm-up: allocations, NCCL channels
+	const auto t0 = std::chrono::steady_clock::now();
+	int rc = adypt_group_render(group, spp);
+	const double seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+	if (rc != ADYPT_OK) {
+		printf("[PT]ERR: %s\n", adypt_last_error());
+		return 1;
+	}
+	if (adypt_group_save_exr(group, out, fp16 ? 1 : 0) != ADYPT_OK) printf("[PT]ERR: %s\n", adypt_last_error());
+	else printf("[PT]INFO: Saved image to %s\n", out);
+	printf("{\"spp\": %d, \"width\": %d, \"height\": %d, \"gpus\": %d, \"seconds\": %.6f, \"samples_per_s\": %.1f, \"out\": \"%s\"}\n", spp, cfg.m_width,
+	       cfg.m_height, gpus, seconds, (double)cfg.m_width * cfg.m_height * spp / seconds, out);
+	adypt_group_destroy(group);
+	return 0;
+}
+
 int main(int argc, char **argv)
 {
 	if (argc < 2) return usage();
 	const char *config = nullptr, *out = "result.exr", *viewer = nullptr;
-	int spp = 64, device = 0, preview_every = 0;
+	int spp = 64, device = 0, preview_every = 0, gpus = 1;
 	bool fp16 = false, per_frame = false, cache = true, keep = false, sun_visibility = false;
 	unsigned long long seed = 0;
 	for (int i = 1; i < argc; ++i) {
@@ -37,6 +90,7 @@ int main(int argc, char **argv)
 		else if (!strcmp(a, "--fp16")) fp16 = true;
 		else if (!strcmp(a, "--seed")) seed = strtoull(next(), nullptr, 10);
 		else if (!strcmp(a, "--device")) device = atoi(next());
+		else if (!strcmp(a, "--gpus")) gpus = atoi(next()); // sample-sharded over devices 0..N-1, one NCCL reduce
 		else if (!strcmp(a, "--viewer")) viewer = next();
 		else if (!strcmp(a, "--preview-every")) preview_every = atoi(next());
 		else if (!strcmp(a, "--sun-visibility")) sun_visibility = true; // the shader's commented-out any-hit sun test (pathtracer.glsl:132)
@@ -47,6 +101,8 @@ int main(int argc, char **argv)
 		else config = a;
 	}
 	if (!config || spp < 0) return usage();
+
+	if (gpus > 1 && !viewer) return render_on_group(config, spp, gpus, out, fp16, seed, cache, sun_visibility);
 
 	Instance instance;
 	instance.m_device = device;

@@ -880,6 +880,13 @@ int adypt_tracer_spp(adypt_tracer *t, int32_t *spp)
 	return ADYPT_OK;
 }
 
+int adypt_tracer_stream(adypt_tracer *t, void **stream)
+{
+	if (!t || !stream) return fail(ADYPT_EINVAL, "NULL argument");
+	*stream = (void *)t->stream;
+	return ADYPT_OK;
+}
+
 int adypt_tracer_sync(adypt_tracer *t)
 {
 	if (!t) return fail(ADYPT_EINVAL, "tracer is NULL");

@@ -194,6 +194,49 @@ class HostScene:
         return s
 
 
+class RenderGroup:
+    """adypt_group_*: one process driving several GPUs (sample-sharded render + one NCCL reduce)."""
+
+    def __init__(self, host_scene: HostScene, config, width: int, height: int, devices, bias_seed: int = 0):
+        l = _lib()
+        vp = C.c_void_p
+        l.adypt_group_create.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_uint64, vp, C.c_uint32, vp]
+        l.adypt_group_destroy.argtypes = [vp]
+        l.adypt_group_set_camera.argtypes = [vp, vp, vp, vp]
+        l.adypt_group_set_sun_visibility.argtypes = [vp, C.c_int32, vp]
+        l.adypt_group_render.argtypes = [vp, C.c_int32]
+        l.adypt_group_read.argtypes = [vp, vp, C.c_int32]
+        l.adypt_group_save_exr.argtypes = [vp, C.c_char_p, C.c_int32]
+        self.width, self.height = width, height
+        devs = np.ascontiguousarray(devices, dtype=np.int32)
+        self._h = C.c_void_p()
+        _check(l.adypt_group_create(host_scene._h, C.byref(config), width, height, bias_seed, devs.ctypes.data, devs.size, C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib().adypt_group_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def look(self, position, yaw, pitch, fov):
+        from . import camera_matrices
+        p, v = camera_matrices(fov, yaw, pitch, self.width, self.height)
+        o = np.ascontiguousarray(position, dtype=np.float32)
+        _check(_lib().adypt_group_set_camera(self._h, p.ctypes.data, v.ctypes.data, o.ctypes.data))
+
+    def render(self, total_spp: int):
+        _check(_lib().adypt_group_render(self._h, total_spp))
+
+    def read(self, channels=4):
+        out = np.empty((self.height, self.width, channels), dtype=np.float32)
+        _check(_lib().adypt_group_read(self._h, out.ctypes.data, channels))
+        return out
+
+    def save_exr(self, path: str, fp16: bool = False):
+        _check(_lib().adypt_group_save_exr(self._h, path.encode(), int(fp16)))
+
+
 def build_scene(mesh, config: BvhConfig | None = None) -> HostScene:
     """workloads.SceneMesh -> HostScene with its CWBVH built (Instance.cpp:12-24 without the OBJ detour)."""
     hs = HostScene.from_triangles(mesh.positions(), mesh.face_mat, materials_array(mesh.materials))

@@ -246,6 +246,24 @@ int adypt_host_scene_texture(adypt_host_scene *scene, uint32_t i, const uint8_t 
 int adypt_host_scene_upload(adypt_host_scene *scene, int32_t device, adypt_scene **out);
 
 /* ------------------------------------------------------------------------------------------------
+ * Render group: one process driving several GPUs of a box (not in the reference, which is single-GPU).
+ * Sample-index sharding as in SURVEY.md 8e: blocks of tmpLifetime samples round-robin over the devices, scene
+ * replicated, ONE ncclReduce of the W*H*4-float sum accumulator to the first device, which resolves the image.
+ * NCCL is loaded with dlopen on first use; a one-device group does not need it. The per-process alternative
+ * (one rank per GPU, torch.distributed) is tools/render_sharded.py. */
+typedef struct adypt_group adypt_group;
+int adypt_group_create(adypt_host_scene *scene, const adypt_pt_config *config, int32_t width, int32_t height, uint64_t bias_seed,
+                       const int32_t *devices, uint32_t n_devices, adypt_group **out);
+int adypt_group_destroy(adypt_group *group);
+int adypt_group_set_camera(adypt_group *group, const float projection[16], const float view[16], const float position[3]);
+int adypt_group_set_sun_visibility(adypt_group *group, int32_t enabled, const float direction[3]);
+int adypt_group_render(adypt_group *group, int32_t total_spp); /* samples [0, total_spp); blocks until the image is resolved */
+int adypt_group_read(adypt_group *group, float *out, int32_t channels);
+int adypt_group_save_exr(adypt_group *group, const char *filename, int32_t save_as_fp16);
+/* the CUDA stream a tracer enqueues its work on (a cudaStream_t), for callers that add their own device work */
+int adypt_tracer_stream(adypt_tracer *tracer, void **stream);
+
+/* ------------------------------------------------------------------------------------------------
  * The .config instance file: InstanceConfig (src/InstanceConfig.hpp:12-48). Same JSON schema, the same
  * acceptance rules (every key mandatory; "Float" values must be written as doubles -- 45.0, not 45 -- exactly
  * as rapidjson's IsFloat demands, InstanceConfig.cpp:17-18) and the same PrettyWriter text on output. */

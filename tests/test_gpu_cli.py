@@ -84,3 +84,31 @@ def test_cli_reports_bad_config(tmp_path):
     p.write_text('{"width": 10}')
     r = subprocess.run([CLI, str(p)], capture_output=True, text=True)
     assert r.returncode == 1 and "[PARSER]ERR" in r.stdout and "[INSTANCE]Err: Invalid instance" in r.stdout
+
+
+@pytest.mark.gpu
+def test_render_group_matches_single_gpu(A, tmp_path):
+    """adypt_group_*: one process, N devices, blocks round-robin + one NCCL reduce. With one device the image equals
+    the sum-mode render exactly; with two (when the box has them) it equals it up to float summation order."""
+    mesh, cfg, path = make_instance(tmp_path)
+    hs = host.HostScene.from_obj(cfg.obj_filename.decode()).build_bvh()
+    tr = A.Tracer(hs.upload(0), cfg.pt, cfg.width, cfg.height, bias_seed=7)
+    tr.look(tuple(cfg.cam.position), cfg.cam.yaw, cfg.cam.pitch, cfg.cam.fov)
+    tr.sample(40)
+    mean = tr.read(4)
+    ndev = A.device_count()
+    for devices in ([[0], [0, 1]] if ndev >= 2 else [[0]]):
+        g = host.RenderGroup(hs, cfg.pt, cfg.width, cfg.height, devices, bias_seed=7)
+        g.look(tuple(cfg.cam.position), cfg.cam.yaw, cfg.cam.pitch, cfg.cam.fov)
+        g.render(40)
+        img = g.read(4)
+        assert float(np.sqrt(((img - mean) ** 2).mean())) < 1e-6
+        assert np.all(img[..., 3] == 1.0)
+        g.close()
+    if ndev >= 2:
+        out = str(tmp_path / "g.exr")
+        r = subprocess.run([CLI, path, "--spp", "40", "--seed", "7", "--gpus", "2", "--out", out, "--keep-config"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        e = read_exr(out)
+        got = np.stack([e["data"]["R"], e["data"]["G"], e["data"]["B"]], axis=2)
+        assert float(np.sqrt(((got - mean[..., :3]) ** 2).mean())) < 1e-6
