@@ -220,7 +220,10 @@ class Scene:
 
     def close(self):
         if getattr(self, "_h", None):
-            load_library().adypt_scene_destroy(self._h)
+            try:
+                load_library().adypt_scene_destroy(self._h)
+            except Exception:  # interpreter shutdown: module globals may already be gone
+                pass
             self._h = None
 
     __del__ = close
@@ -304,7 +307,10 @@ class Tracer:
 
     def close(self):
         if getattr(self, "_h", None):
-            load_library().adypt_tracer_destroy(self._h)
+            try:
+                load_library().adypt_tracer_destroy(self._h)
+            except Exception:
+                pass
             self._h = None
 
     __del__ = close

@@ -1,6 +1,7 @@
 // Scene upload, GPU Woop construction and the batch traversal entry points of the C-ABI.
 #include "scene.h"
 #include "traverse.cuh"
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -360,7 +361,11 @@ static int trace_host(adypt_scene *s, const float *rays, uint64_t n, int32_t *tr
 		for (int i = 0; i < 3; ++i) ADYPT_CUDA(cudaStreamCreateWithFlags(&s->pipe[i], cudaStreamNonBlocking));
 	ADYPT_CUDA(cudaStreamSynchronize(user_stream)); // earlier work queued by the caller on its stream comes first
 	uint8_t *o = s->stage_out.as<uint8_t>();
-	const uint64_t chunk = 1u << 20;
+	static const uint64_t chunk = []() -> uint64_t { // rays per pipeline stage (tunable for experiments)
+		const char *e = getenv("ADYPT_HOST_CHUNK");
+		const long v = e ? atol(e) : 0;
+		return v >= 1024 ? (uint64_t)v : (uint64_t)(1u << 19);
+	}();
 	int k = 0;
 	for (uint64_t b = 0; b < n; b += chunk, ++k) {
 		const uint64_t m = (n - b < chunk) ? n - b : chunk;

@@ -135,7 +135,10 @@ class HostScene:
 
     def close(self):
         if getattr(self, "_h", None):
-            _lib().adypt_host_scene_destroy(self._h)
+            try:
+                _lib().adypt_host_scene_destroy(self._h)
+            except Exception:
+                pass
             self._h = None
 
     __del__ = close
@@ -214,7 +217,10 @@ class RenderGroup:
 
     def close(self):
         if getattr(self, "_h", None):
-            _lib().adypt_group_destroy(self._h)
+            try:
+                _lib().adypt_group_destroy(self._h)
+            except Exception:
+                pass
             self._h = None
 
     __del__ = close
