@@ -91,8 +91,8 @@ __device__ __forceinline__ uint32_t test_child(uint32_t child_bits4, uint32_t bi
 	const float ctmin = fmaxf(fmaxf(txmin, tymin), fmaxf(tzmin, tmin));
 	const float ctmax = fminf(fminf(txmax, tymax), fminf(tzmax, hit_t));
 	if (ctmin <= ctmax) {
-		const uint32_t bits = __byte_perm(child_bits4, 0u, 0x4440u | (uint32_t)K); // byte K, zero-extended: one PRMT
-		const uint32_t idx = (bit_index4 >> (8 * K)) & 0x1fu;                        // the shifter only reads 5 bits
+		const uint32_t bits = (child_bits4 >> (8 * K)) & 0xffu;
+		const uint32_t idx = (bit_index4 >> (8 * K)) & 0xffu;
 		return bits << idx;
 	}
 	return 0u;
