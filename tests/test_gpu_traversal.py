@@ -181,3 +181,45 @@ def test_c2_incoherent_rays(A, cpu, c2):
     assert torch.equal(again, d_tri)
     host = sc.trace_closest(rays[:500_000])
     assert np.array_equal(host["tri"], tri[:500_000]) and np.array_equal(bits(host["t"]), bits(t[:500_000]))
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_fuzz_triangle_soups(A, cpu, seed):
+    """Random triangle soups with the nasty cases mixed in -- degenerate (zero-area) triangles whose Woop rows are
+    inf/NaN, coplanar duplicates (exact ties in t), slivers, huge and tiny triangles, axis-aligned quads sharing
+    edges -- built by the product's own builder, traced on the GPU and by the oracle: ids, t, uv and any-hit bits
+    must be identical for rays from everywhere, including rays that start on the geometry."""
+    from adypt_b200 import host, workloads as W
+    rng = np.random.default_rng(seed)
+    n = 3000
+    c = rng.uniform(-4, 4, size=(n, 1, 3))
+    tri = c + rng.normal(0, 1, size=(n, 3, 3)) * rng.choice([0.01, 0.2, 1.5], size=(n, 1, 1))
+    tri[:50, 2] = tri[:50, 1]                       # degenerate: two equal corners
+    tri[50:100, 1] = (tri[50:100, 0] + tri[50:100, 2]) * 0.5  # degenerate: collinear
+    tri[100:200] = tri[200:300]                     # exact duplicates
+    tri[300:400, :, 2] = 0.5                        # coplanar in z = 0.5
+    tri[400:420] *= 50.0                            # huge
+    tri = np.round(tri * 64) / 64                   # snap to a grid: many exactly shared coordinates
+    pos = tri.astype(np.float32)
+    mats = host.materials_array(W.tiny_scene("strip").materials)
+    hs = host.HostScene.from_triangles(pos, np.zeros(n, dtype=np.int32), mats).build_bvh()
+    woop = cpu.build_woop(hs.tris, hs.tri_indices)
+    sc = hs.upload(0)
+    got_woop = sc.read_woop()
+    assert np.array_equal(got_woop.view(np.uint32), woop.view(np.uint32))  # incl. the inf / NaN rows of degenerate triangles
+    rays = W.random_rays(60000, hs.aabb[:3] - 1, hs.aabb[3:] + 1, seed=seed)
+    on = W.random_rays(20000, [-1, -1, -1], [1, 1, 1], seed=seed + 10)   # origins ON triangles (bounce-like rays)
+    k = rng.integers(0, n, size=20000)
+    bary = rng.dirichlet([1, 1, 1], size=20000).astype(np.float32)
+    on[:, :3] = (pos[k] * bary[:, :, None]).sum(axis=1)
+    axis = W.random_rays(3000, hs.aabb[:3], hs.aabb[3:], seed=seed + 20)  # exactly axis-parallel directions
+    axis[:, 4:7] = np.eye(3, dtype=np.float32)[rng.integers(0, 3, size=3000)] * rng.choice([-1.0, 1.0], size=(3000, 1)).astype(np.float32)
+    rays = np.concatenate([rays, on, axis])
+    g = sc.trace_closest(rays)
+    o = cpu.trace_closest(hs.nodes, hs.tri_indices, woop, rays)
+    assert np.array_equal(g["tri"], o["tri"])
+    assert np.array_equal(bits(g["t"]), bits(o["t"])) and np.array_equal(bits(g["uv"]), bits(o["uv"]))
+    assert np.array_equal(sc.trace_any(rays), cpu.trace_any(hs.nodes, woop, rays)["occluded"])
+    assert 0.05 < (g["tri"] >= 0).mean() < 0.99
+    assert sc.trace_stats(rays)["max_stack"] == o["counters"]["max_stack"]
+    assert sc.trace_stats(rays)["nodes"] == o["counters"]["nodes"] and sc.trace_stats(rays)["tris"] == o["counters"]["tris"]
