@@ -111,7 +111,7 @@ int launch_trace(adypt_scene *s, const float4 *d_rays, uint64_t n, int32_t *d_tr
 	p.magic = 0x4B000000u;
 	p.counter = s->d_counters + (s->counter_cursor++ % kCounterRing);
 	p.refill_threshold = s->refill_threshold > 0 ? s->refill_threshold : 28;
-	int per_sm = s->ctas_per_sm > 0 ? s->ctas_per_sm : (any ? s->occ_any : ((s->variant == 1 || s->variant == 7) ? 6 : s->occ_closest));
+	int per_sm = s->ctas_per_sm > 0 ? s->ctas_per_sm : (any ? s->occ_any : s->occ_closest);
 	if (per_sm < 1) per_sm = 1;
 	unsigned long long warps_needed = (n + 31) / 32;
 	unsigned long long ctas_needed = (warps_needed + (kTraceBlock / 32) - 1) / (kTraceBlock / 32);
@@ -126,15 +126,22 @@ int launch_trace(adypt_scene *s, const float4 *d_rays, uint64_t n, int32_t *d_tr
 		p.pool_chunk = (uint32_t)(chunk < 32ull ? 32ull : chunk > kPoolChunk ? kPoolChunk : chunk);
 	}
 	ADYPT_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned long long), stream));
-	if (any) trace_kernel<true><<<grid, kTraceBlock, 0, stream>>>(p);
-	else switch (s->variant) { // code-generation variants of the same algorithm (identical results); 0 = tuned default
-	case 1: trace_kernel<false, false, 0, 6><<<grid, kTraceBlock, 0, stream>>>(p); break;
-	case 2: trace_kernel<false, false, 0, 8><<<grid, kTraceBlock, 0, stream>>>(p); break;
-	case 3: trace_kernel<false, false, 1, 8><<<grid, kTraceBlock, 0, stream>>>(p); break;
-	case 4: trace_kernel<false, false, 3, 8><<<grid, kTraceBlock, 0, stream>>>(p); break;
-	case 5: trace_kernel<false, false, 4, 8><<<grid, kTraceBlock, 0, stream>>>(p); break;
-	case 6: trace_kernel<false, false, 6, 8><<<grid, kTraceBlock, 0, stream>>>(p); break;
-	case 7: trace_kernel<false, false, 2, 6><<<grid, kTraceBlock, 0, stream>>>(p); break;
+	// code-generation variants of the same algorithm (identical results); 0 = tuned default: 4 conversion planes on
+	// the I2F pipe, 8 CTAs/SM, triangle batch 2 (closest-hit: with both fetches up front)
+	if (any) switch (s->variant) {
+	case 1: trace_kernel<true, false, 2, 8, 0><<<grid, kTraceBlock, 0, stream>>>(p); break;
+	case 2: trace_kernel<true, false, 2, 8, 2><<<grid, kTraceBlock, 0, stream>>>(p); break;
+	case 5: trace_kernel<true, false, 4, 8, 12><<<grid, kTraceBlock, 0, stream>>>(p); break;
+	default: trace_kernel<true><<<grid, kTraceBlock, 0, stream>>>(p); break;
+	}
+	else switch (s->variant) {
+	case 1: trace_kernel<false, false, 2, 8, 0><<<grid, kTraceBlock, 0, stream>>>(p); break; // unbounded triangle loop
+	case 2: trace_kernel<false, false, 2, 8, 2><<<grid, kTraceBlock, 0, stream>>>(p); break;
+	case 3: trace_kernel<false, false, 2, 8, 12><<<grid, kTraceBlock, 0, stream>>>(p); break;
+	case 4: trace_kernel<false, false, 3, 8, 12><<<grid, kTraceBlock, 0, stream>>>(p); break;
+	case 5: trace_kernel<false, false, 4, 8, 2><<<grid, kTraceBlock, 0, stream>>>(p); break;
+	case 6: trace_kernel<false, false, 5, 8, 12><<<grid, kTraceBlock, 0, stream>>>(p); break;
+	case 7: trace_kernel<false, false, 4, 8, 1><<<grid, kTraceBlock, 0, stream>>>(p); break;
 	default: trace_kernel<false><<<grid, kTraceBlock, 0, stream>>>(p); break;
 	}
 	count_launch();

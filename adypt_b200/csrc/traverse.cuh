@@ -57,7 +57,8 @@ __device__ __forceinline__ float dot3_fma(float ax, float ay, float az, const fl
 //    selectors get re-materialised in registers for every use (45 IMAD.U32 per node step in profile r1a).
 //  * CVT: I2F.U8 with a byte selector: one instruction, but on the quarter-rate conversion pipe.
 // CVT_PLANES (0..6) of the six quantised planes use CVT, the rest MAGIC, to balance the pipes. Measured on B200
-// (profiles/r1_tuning.md): 2 CVT planes at 8 CTAs/SM (64 registers) is fastest; all-MAGIC and all-CVT both lose.
+// (profiles/README.md, r1n_tune_tribatch.log): with the bounded triangle batch, 4 CVT planes at 8 CTAs/SM (64
+// registers) is fastest; all-MAGIC and all-CVT both lose.
 template <int K>
 __device__ __forceinline__ float byte_to_float_magic(uint32_t word, uint32_t magic)
 {
@@ -112,7 +113,12 @@ __device__ __forceinline__ uint32_t test_children4(uint32_t meta4, uint32_t octi
 #undef ADYPT_CHILD
 }
 
-template <bool ANY, bool STATS = false, int CVT_PLANES = 2, int MIN_CTAS = 8>
+// TRI_BATCH: 0 = a lane tests all triangles of its group before the warp moves on (the GLSL's loop shape);
+// K > 0 = at most K triangle tests per lane and round, lanes with triangles left skip their next node step until
+// the group is empty; 12 = K 2 with both triangles' rows fetched before the first test. Only the warp-level
+// interleaving differs: each ray's own sequence of node steps and triangle tests -- and therefore every result and
+// counter -- is the same. A warp no longer waits for its one lane with nine triangles: -12 % time on C2.
+template <bool ANY, bool STATS = false, int CVT_PLANES = 4, int MIN_CTAS = 8, int TRI_BATCH = (ANY ? 2 : 12)>
 __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const TraceParams p)
 {
 	const uint32_t magic = p.magic;
@@ -197,7 +203,9 @@ __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const Trac
 		unsigned busy;
 		do {
 			if (active) {
-				if (ng.y > 0x00ffffffu) {
+				if (TRI_BATCH > 0 && tg.y != 0u) {
+					// triangles left over from the previous round: no node step yet
+				} else if (ng.y > 0x00ffffffu) {
 					// n <- closest child of G (:50-67)
 					const uint32_t imask = ng.y;
 					const uint32_t bit = 31u - (uint32_t)__clz((int)ng.y);
@@ -244,29 +252,50 @@ __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const Trac
 				}
 
 				bool finished = false;
-				while (tg.y != 0u) { // :213-243
+				// Woop test of leaf reference TR with rows M0..M2 (:221-241)
+#define ADYPT_WOOP_TEST(TR, M0, M1, M2) \
+	do { \
+		if (STATS) ++st_tris; \
+		const float toz = __fsub_rn(M0.w, dot3_fma(ox, oy, oz, M0)); \
+		const float tidz = __frcp_rn(dot3_fma(dx, dy, dz, M0)); \
+		const float tt = __fmul_rn(toz, tidz); \
+		const float tox = __fadd_rn(M1.w, dot3_fma(ox, oy, oz, M1)); \
+		const float tu = __fmaf_rn(tt, dot3_fma(dx, dy, dz, M1), tox); \
+		const float toy = __fadd_rn(M2.w, dot3_fma(ox, oy, oz, M2)); \
+		const float tv = __fmaf_rn(tt, dot3_fma(dx, dy, dz, M2), toy); \
+		if (tt > tmin && tt < hit_t && tu >= 0.0f && tu <= 1.0f && tv >= 0.0f && __fadd_rn(tu, tv) <= 1.0f) { \
+			hit_t = tt; \
+			if (ANY) finished = true; /* :480-483 */ \
+			else { hit_u = tu; hit_v = tv; hit_idx = (int32_t)(TR); } \
+		} \
+	} while (0)
+				if (TRI_BATCH == 12) {
+					// batch of two with both fetches in flight before the first test
+					if (tg.y != 0u) {
+						const uint32_t tr0 = tg.x + (uint32_t)(__ffs((int)tg.y) - 1);
+						tg.y &= tg.y - 1u;
+						const bool two = tg.y != 0u;
+						const uint32_t tr1 = tg.x + (uint32_t)(__ffs((int)tg.y) - 1);
+						tg.y &= tg.y - 1u; // no-op on 0
+						const float4 *wa = p.woop + (size_t)tr0 * 3u;
+						const float4 *wb = p.woop + (size_t)(two ? tr1 : tr0) * 3u;
+						const float4 a0 = __ldg(wa), a1 = __ldg(wa + 1), a2 = __ldg(wa + 2);
+						const float4 b0 = __ldg(wb), b1 = __ldg(wb + 1), b2 = __ldg(wb + 2);
+						ADYPT_WOOP_TEST(tr0, a0, a1, a2);
+						if (two && !(ANY && finished)) ADYPT_WOOP_TEST(tr1, b0, b1, b2);
+					}
+				} else
+				for (int batch = 0; tg.y != 0u && (TRI_BATCH == 0 || batch < TRI_BATCH); ++batch) { // :213-243
 					const uint32_t tr = tg.x + (uint32_t)(__ffs((int)tg.y) - 1);
 					tg.y &= tg.y - 1u;
 					const float4 *wp = p.woop + (size_t)tr * 3u;
 					const float4 m0 = __ldg(wp), m1 = __ldg(wp + 1), m2 = __ldg(wp + 2);
-					if (STATS) ++st_tris;
-					const float toz = __fsub_rn(m0.w, dot3_fma(ox, oy, oz, m0));
-					const float tidz = __frcp_rn(dot3_fma(dx, dy, dz, m0));
-					const float tt = __fmul_rn(toz, tidz);
-					const float tox = __fadd_rn(m1.w, dot3_fma(ox, oy, oz, m1));
-					const float tu = __fmaf_rn(tt, dot3_fma(dx, dy, dz, m1), tox);
-					const float toy = __fadd_rn(m2.w, dot3_fma(ox, oy, oz, m2));
-					const float tv = __fmaf_rn(tt, dot3_fma(dx, dy, dz, m2), toy);
-					if (tt > tmin && tt < hit_t && tu >= 0.0f && tu <= 1.0f && tv >= 0.0f && __fadd_rn(tu, tv) <= 1.0f) {
-						hit_t = tt;
-						if (ANY) { finished = true; break; } // :480-483
-						hit_u = tu;
-						hit_v = tv;
-						hit_idx = (int32_t)tr;
-					}
+					ADYPT_WOOP_TEST(tr, m0, m1, m2);
+					if (ANY && finished) break;
 				}
+#undef ADYPT_WOOP_TEST
 
-				if (!finished && ng.y <= 0x00ffffffu) { // :245-250
+				if (!finished && (TRI_BATCH == 0 || tg.y == 0u) && ng.y <= 0x00ffffffu) { // :245-250
 					if (sp == 0) finished = true;
 					else {
 						--sp;

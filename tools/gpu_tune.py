@@ -28,7 +28,7 @@ def main():
     st = torch.cuda.current_stream().cuda_stream
     base = None
     res = {}
-    for variant in (0, 2, 4):
+    for variant in (0, 1, 3, 5):
         for thr in (24, 28, 32):
             for ctas in (0,):
                 sc.configure(ctas, thr, variant)
@@ -43,8 +43,11 @@ def main():
     mn, md = timed(lambda: sc.trace_closest(d_prim, d_tri[:1000000], d_t[:1000000], d_uv[:1000000], stream=st))
     print(f'C2-scene 1M primary rays: {mn:.3f} ms {1e3/mn:.0f} Mrays/s')
     occ = torch.empty(n, dtype=torch.uint8, device='cuda')
-    mn, md = timed(lambda: sc.trace_any(d_rays, occ, stream=st))
-    print(f'any-hit 8M: {mn:.3f} ms {n/mn/1e3:.0f} Mrays/s')
+    for v in (0, 1, 5):
+        sc.configure(0, best[1], v)
+        mn, md = timed(lambda: sc.trace_any(d_rays, occ, stream=st))
+        print(f'any-hit 8M variant {v}: {mn:.3f} ms {n/mn/1e3:.0f} Mrays/s')
+    sc.configure(0, best[1], best[0])
     # path tracer, C3-like
     mesh3 = W.city(183, 1, mixed_materials=True)
     hs3 = host.build_scene(mesh3); sc3 = hs3.upload(0); sc3.configure(0, best[1], best[0])
