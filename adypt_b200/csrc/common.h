@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <string>
 #include "../../include/adypt_b200.h"
+#include "guard.h"
 
 #ifndef ADYPT_NO_FMAD
 #error "build with -fmad=false -DADYPT_NO_FMAD: the FP policy forbids implicit multiply-add contraction"

@@ -10,6 +10,7 @@
 #include <string>
 #include <vector>
 #include "../../include/adypt_b200.h"
+#include "guard.h"
 
 namespace {
 
@@ -63,6 +64,7 @@ uint16_t float_to_half(float f)
 
 extern "C" int adypt_write_exr(const char *filename, const float *rgb, int32_t width, int32_t height, int32_t save_as_fp16)
 {
+	return adypt::guarded([&]() -> int {
 	if (!filename || !rgb || width <= 0 || height <= 0) return ADYPT_EINVAL;
 	const int bpc = save_as_fp16 ? 2 : 4; // bytes per channel sample
 	std::vector<uint8_t> hdr;
@@ -155,4 +157,5 @@ extern "C" int adypt_write_exr(const char *filename, const float *rgb, int32_t w
 	ok = ok && fwrite(body.data(), 1, body.size(), f) == body.size();
 	ok = (fclose(f) == 0) && ok;
 	return ok ? ADYPT_OK : ADYPT_EIO;
+	});
 }

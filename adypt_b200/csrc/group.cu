@@ -61,6 +61,7 @@ extern "C" {
 
 int adypt_group_destroy(adypt_group *g)
 {
+	return guarded([&]() -> int {
 	if (!g) return ADYPT_OK;
 	for (ncclComm_t c : g->comms)
 		if (c) g_nccl.CommDestroy(c);
@@ -68,11 +69,13 @@ int adypt_group_destroy(adypt_group *g)
 	for (adypt_scene *s : g->scenes) adypt_scene_destroy(s);
 	delete g;
 	return ADYPT_OK;
+	});
 }
 
 int adypt_group_create(adypt_host_scene *scene, const adypt_pt_config *config, int32_t width, int32_t height, uint64_t bias_seed,
                        const int32_t *devices, uint32_t n_devices, adypt_group **out)
 {
+	return guarded([&]() -> int {
 	if (!scene || !config || !devices || !out || n_devices == 0) return fail(ADYPT_EINVAL, "NULL argument or empty device list");
 	*out = nullptr;
 	adypt_group *g = new adypt_group;
@@ -107,25 +110,31 @@ int adypt_group_create(adypt_host_scene *scene, const adypt_pt_config *config, i
 	}
 	*out = g;
 	return ADYPT_OK;
+	});
 }
 
 int adypt_group_set_camera(adypt_group *g, const float projection[16], const float view[16], const float position[3])
 {
+	return guarded([&]() -> int {
 	if (!g) return fail(ADYPT_EINVAL, "group is NULL");
 	for (adypt_tracer *t : g->tracers) ADYPT_TRY(adypt_tracer_set_camera(t, projection, view, position));
 	return ADYPT_OK;
+	});
 }
 
 int adypt_group_set_sun_visibility(adypt_group *g, int32_t enabled, const float direction[3])
 {
+	return guarded([&]() -> int {
 	if (!g) return fail(ADYPT_EINVAL, "group is NULL");
 	for (adypt_tracer *t : g->tracers) ADYPT_TRY(adypt_tracer_set_sun_visibility(t, enabled, direction));
 	return ADYPT_OK;
+	});
 }
 
 // Renders samples [0, total_spp) across the group and leaves the resolved image on the first device.
 int adypt_group_render(adypt_group *g, int32_t total_spp)
 {
+	return guarded([&]() -> int {
 	if (!g || total_spp <= 0) return fail(ADYPT_EINVAL, "bad argument");
 	const int n = (int)g->tracers.size(), L = g->tmp_lifetime;
 	for (adypt_tracer *t : g->tracers) ADYPT_TRY(adypt_tracer_clear_sum(t));
@@ -153,18 +162,23 @@ int adypt_group_render(adypt_group *g, int32_t total_spp)
 	for (adypt_tracer *t : g->tracers) ADYPT_TRY(adypt_tracer_sync(t));
 	g->spp = total_spp;
 	return ADYPT_OK;
+	});
 }
 
 int adypt_group_read(adypt_group *g, float *out, int32_t channels)
 {
+	return guarded([&]() -> int {
 	if (!g) return fail(ADYPT_EINVAL, "group is NULL");
 	return adypt_tracer_read(g->tracers[0], out, channels);
+	});
 }
 
 int adypt_group_save_exr(adypt_group *g, const char *filename, int32_t save_as_fp16)
 {
+	return guarded([&]() -> int {
 	if (!g) return fail(ADYPT_EINVAL, "group is NULL");
 	return adypt_tracer_save_exr(g->tracers[0], filename, save_as_fp16);
+	});
 }
 
 } // extern "C"

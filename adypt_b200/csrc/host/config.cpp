@@ -294,6 +294,7 @@ extern "C" {
 
 int adypt_config_set_default(adypt_instance_config *c)
 {
+	return adypt::guarded([&]() -> int {
 	if (!c) return fail(ADYPT_EINVAL, "config is NULL");
 	memset(c, 0, sizeof(*c));
 	c->width = 1280; // InstanceConfig.hpp:37
@@ -312,10 +313,12 @@ int adypt_config_set_default(adypt_instance_config *c)
 	c->cam.mouse_sensitive = 0.3f;
 	c->cam.fov = 45.0f;
 	return ADYPT_OK;
+	});
 }
 
 int adypt_config_load(const char *path, adypt_instance_config *c)
 {
+	return adypt::guarded([&]() -> int {
 	if (!path || !c) return fail(ADYPT_EINVAL, "NULL argument");
 	std::ifstream in(path);
 	if (!in.is_open()) return fail(ADYPT_EIO, std::string("cannot open ") + path);
@@ -390,10 +393,12 @@ int adypt_config_load(const char *path, adypt_instance_config *c)
 	NEED_VEC3(cam, "position", "cam_obj", out.cam.position)
 	*c = out;
 	return ADYPT_OK;
+	});
 }
 
 int adypt_config_to_json(const adypt_instance_config *c, char *buf, uint64_t cap, uint64_t *needed)
 {
+	return adypt::guarded([&]() -> int {
 	if (!c) return fail(ADYPT_EINVAL, "config is NULL");
 	std::string o;
 	const std::string I1 = "    ", I2 = "        ", I3 = "            ";
@@ -435,10 +440,12 @@ int adypt_config_to_json(const adypt_instance_config *c, char *buf, uint64_t cap
 		memcpy(buf, o.c_str(), o.size() + 1);
 	}
 	return ADYPT_OK;
+	});
 }
 
 int adypt_config_save(const adypt_instance_config *c, const char *path)
 {
+	return adypt::guarded([&]() -> int {
 	if (!c || !path) return fail(ADYPT_EINVAL, "NULL argument");
 	uint64_t need = 0;
 	adypt_config_to_json(c, nullptr, 0, &need);
@@ -448,6 +455,7 @@ int adypt_config_save(const adypt_instance_config *c, const char *path)
 	if (!out.is_open()) return fail(ADYPT_EIO, std::string("cannot write ") + path);
 	out << s.c_str();
 	return out.good() ? ADYPT_OK : fail(ADYPT_EIO, std::string("cannot write ") + path);
+	});
 }
 
 } // extern "C"

@@ -2,6 +2,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstring>
+#include <memory>
 #include "../common.h"
 #include "host_scene.h"
 
@@ -29,9 +30,10 @@ extern "C" {
 int adypt_host_scene_from_triangles(const float *positions, const int32_t *material_ids, uint32_t n_tris, const void *materials64,
                                     uint32_t n_mats, adypt_host_scene **out)
 {
+	return guarded([&]() -> int {
 	if (!positions || !material_ids || !out || n_tris == 0) return fail(ADYPT_EINVAL, "positions/material_ids/out is NULL or n_tris is 0");
 	if (n_mats && !materials64) return fail(ADYPT_EINVAL, "materials is NULL");
-	adypt_host_scene *s = new adypt_host_scene;
+	std::unique_ptr<adypt_host_scene> s(new adypt_host_scene);
 	s->tris.resize(n_tris);
 	for (uint32_t i = 0; i < n_tris; ++i) {
 		Triangle &t = s->tris[i];
@@ -41,40 +43,40 @@ int adypt_host_scene_from_triangles(const float *positions, const int32_t *mater
 		flat_normal(t.p[0], t.p[1], t.p[2], n);
 		for (int k = 0; k < 3; ++k) memcpy(t.n[k], n, 12);
 		t.matid = material_ids[i];
-		if (n_mats && (t.matid < 0 || (uint32_t)t.matid >= n_mats)) {
-			delete s;
-			return fail(ADYPT_EINVAL, "material id out of range");
-		}
+		if (n_mats && (t.matid < 0 || (uint32_t)t.matid >= n_mats)) return fail(ADYPT_EINVAL, "material id out of range");
 	}
 	s->mats.resize(n_mats);
 	if (n_mats) memcpy(s->mats.data(), materials64, (size_t)n_mats * 64);
 	s->box = scene_box(s->tris.data(), s->tris.size());
-	*out = s;
+	*out = s.release();
 	return ADYPT_OK;
+	});
 }
 
 int adypt_host_scene_load_obj(const char *obj_path, adypt_host_scene **out)
 {
+	return guarded([&]() -> int {
 	if (!obj_path || !out) return fail(ADYPT_EINVAL, "NULL argument");
-	adypt_host_scene *s = new adypt_host_scene;
-	const std::string err = load_obj(obj_path, s);
-	if (!err.empty()) {
-		delete s;
-		return fail(ADYPT_EIO, err);
-	}
+	std::unique_ptr<adypt_host_scene> s(new adypt_host_scene);
+	const std::string err = load_obj(obj_path, s.get());
+	if (!err.empty()) return fail(ADYPT_EIO, err);
 	s->box = scene_box(s->tris.data(), s->tris.size());
-	*out = s;
+	*out = s.release();
 	return ADYPT_OK;
+	});
 }
 
 int adypt_host_scene_destroy(adypt_host_scene *s)
 {
+	return guarded([&]() -> int {
 	delete s;
 	return ADYPT_OK;
+	});
 }
 
 int adypt_host_scene_build_bvh(adypt_host_scene *s, const adypt_bvh_config *c)
 {
+	return guarded([&]() -> int {
 	if (!s || !c) return fail(ADYPT_EINVAL, "NULL argument");
 	if (s->tris.empty()) return fail(ADYPT_EINVAL, "scene has no triangles");
 	BvhConfig cfg;
@@ -85,10 +87,12 @@ int adypt_host_scene_build_bvh(adypt_host_scene *s, const adypt_bvh_config *c)
 	if (!build_wide(s->binary, cfg, &s->wide))
 		return fail(ADYPT_EINVAL, "a one-triangle scene has no wide BVH (the reference builder reads out of bounds there)");
 	return ADYPT_OK;
+	});
 }
 
 int adypt_host_scene_load_bvh(adypt_host_scene *s, const char *path, const adypt_bvh_config *c)
 {
+	return guarded([&]() -> int {
 	if (!s || !path || !c) return fail(ADYPT_EINVAL, "NULL argument");
 	BvhConfig cfg;
 	cfg.max_spatial_depth = c->max_spatial_depth;
@@ -97,10 +101,12 @@ int adypt_host_scene_load_bvh(adypt_host_scene *s, const char *path, const adypt
 	s->binary.nodes.clear();
 	if (!load_bvh_file(path, cfg, &s->wide)) return fail(ADYPT_EIO, std::string("no usable .bvh cache at ") + path);
 	return ADYPT_OK;
+	});
 }
 
 int adypt_host_scene_save_bvh(adypt_host_scene *s, const char *path, const adypt_bvh_config *c)
 {
+	return guarded([&]() -> int {
 	if (!s || !path || !c) return fail(ADYPT_EINVAL, "NULL argument");
 	BvhConfig cfg;
 	cfg.max_spatial_depth = c->max_spatial_depth;
@@ -108,10 +114,12 @@ int adypt_host_scene_save_bvh(adypt_host_scene *s, const char *path, const adypt
 	cfg.node_sah = c->node_sah;
 	if (!save_bvh_file(path, s->wide, cfg)) return fail(ADYPT_EIO, std::string("cannot write ") + path);
 	return ADYPT_OK;
+	});
 }
 
 int adypt_host_scene_get(adypt_host_scene *s, adypt_host_scene_info *o)
 {
+	return guarded([&]() -> int {
 	if (!s || !o) return fail(ADYPT_EINVAL, "NULL argument");
 	o->n_tris = (uint32_t)s->tris.size();
 	o->n_mats = (uint32_t)s->mats.size();
@@ -126,10 +134,12 @@ int adypt_host_scene_get(adypt_host_scene *s, adypt_host_scene_info *o)
 	memcpy(o->aabb, s->box.lo, 12);
 	memcpy(o->aabb + 3, s->box.hi, 12);
 	return ADYPT_OK;
+	});
 }
 
 int adypt_host_scene_load_textures(adypt_host_scene *s, uint32_t *n_loaded, uint32_t *n_failed)
 {
+	return guarded([&]() -> int {
 	if (!s) return fail(ADYPT_EINVAL, "scene is NULL");
 	uint32_t ok = 0, bad = 0;
 	if (!s->textures_loaded) {
@@ -162,20 +172,24 @@ int adypt_host_scene_load_textures(adypt_host_scene *s, uint32_t *n_loaded, uint
 	if (n_loaded) *n_loaded = ok;
 	if (n_failed) *n_failed = bad;
 	return ADYPT_OK;
+	});
 }
 
 int adypt_host_scene_texture(adypt_host_scene *s, uint32_t i, const uint8_t **rgb8, int32_t *width, int32_t *height)
 {
+	return guarded([&]() -> int {
 	if (!s || !rgb8 || !width || !height) return fail(ADYPT_EINVAL, "NULL argument");
 	if (i >= s->textures.size()) return fail(ADYPT_EINVAL, "texture index out of range");
 	*rgb8 = s->textures[i].rgb.data();
 	*width = s->textures[i].width;
 	*height = s->textures[i].height;
 	return ADYPT_OK;
+	});
 }
 
 int adypt_host_scene_upload(adypt_host_scene *s, int32_t device, adypt_scene **out)
 {
+	return guarded([&]() -> int {
 	if (!s || !out) return fail(ADYPT_EINVAL, "NULL argument");
 	if (s->wide.nodes.empty()) return fail(ADYPT_EINVAL, "build or load a BVH first");
 	adypt_scene_desc d;
@@ -204,6 +218,7 @@ int adypt_host_scene_upload(adypt_host_scene *s, int32_t device, adypt_scene **o
 		}
 	}
 	return ADYPT_OK;
+	});
 }
 
 } // extern "C"

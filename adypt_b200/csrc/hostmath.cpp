@@ -6,6 +6,7 @@
 #include <cstring>
 #include <mutex>
 #include "../../include/adypt_b200.h"
+#include "guard.h"
 
 namespace adypt {
 
@@ -165,7 +166,9 @@ void fill_bias(uint64_t seed, uint64_t n_bytes, uint8_t *out)
 extern "C" int adypt_camera_matrices(float fov_deg, float yaw_deg, float pitch_deg, int32_t width, int32_t height,
                                      float projection[16], float view[16])
 {
+	return adypt::guarded([&]() -> int {
 	if (!projection || !view || width <= 0 || height <= 0) return ADYPT_EINVAL;
 	adypt::camera_matrices(fov_deg, yaw_deg, pitch_deg, width, height, projection, view);
 	return ADYPT_OK;
+	});
 }

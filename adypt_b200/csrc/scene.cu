@@ -188,6 +188,7 @@ int adypt_version(void) { return ADYPT_B200_VERSION; }
 
 int adypt_device_count(int *count)
 {
+	return guarded([&]() -> int {
 	if (!count) return fail(ADYPT_EINVAL, "count is NULL");
 	int n = 0;
 	cudaError_t e = cudaGetDeviceCount(&n);
@@ -197,17 +198,21 @@ int adypt_device_count(int *count)
 	}
 	*count = n;
 	return ADYPT_OK;
+	});
 }
 
 int adypt_launch_count(uint64_t *launches)
 {
+	return guarded([&]() -> int {
 	if (!launches) return fail(ADYPT_EINVAL, "launches is NULL");
 	*launches = g_launches.load();
 	return ADYPT_OK;
+	});
 }
 
 int adypt_scene_create(const adypt_scene_desc *d, adypt_scene **out)
 {
+	return guarded([&]() -> int {
 	if (!d || !out) return fail(ADYPT_EINVAL, "desc/out is NULL");
 	*out = nullptr;
 	if (!d->nodes || d->n_nodes == 0) return fail(ADYPT_EINVAL, "scene needs at least the root node");
@@ -280,10 +285,12 @@ int adypt_scene_create(const adypt_scene_desc *d, adypt_scene **out)
 	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->occ_any, trace_kernel<true>, kTraceBlock, 0);
 	*out = s;
 	return ADYPT_OK;
+	});
 }
 
 int adypt_scene_set_textures(adypt_scene *s, const adypt_texture *tex, uint32_t n)
 {
+	return guarded([&]() -> int {
 	if (!s || (n && !tex)) return fail(ADYPT_EINVAL, "NULL argument");
 	DeviceGuard g(s->device);
 	ADYPT_CUDA(cudaDeviceSynchronize());
@@ -319,38 +326,47 @@ int adypt_scene_set_textures(adypt_scene *s, const adypt_texture *tex, uint32_t 
 	s->n_textures = n;
 	s->device_bytes += total * 4u + (size_t)n * sizeof(int4);
 	return ADYPT_OK;
+	});
 }
 
 int adypt_scene_destroy(adypt_scene *scene)
 {
+	return guarded([&]() -> int {
 	if (!scene) return ADYPT_OK;
 	free_scene(scene);
 	return ADYPT_OK;
+	});
 }
 
 int adypt_scene_read_woop(adypt_scene *s, float *out)
 {
+	return guarded([&]() -> int {
 	if (!s || !out) return fail(ADYPT_EINVAL, "scene/out is NULL");
 	DeviceGuard g(s->device);
 	ADYPT_CUDA(cudaMemcpy(out, s->d_woop, (size_t)s->n_refs * 48u, cudaMemcpyDeviceToHost));
 	return ADYPT_OK;
+	});
 }
 
 int adypt_scene_device_bytes(adypt_scene *s, uint64_t *bytes)
 {
+	return guarded([&]() -> int {
 	if (!s || !bytes) return fail(ADYPT_EINVAL, "scene/bytes is NULL");
 	*bytes = s->device_bytes;
 	return ADYPT_OK;
+	});
 }
 
 int adypt_trace_configure(adypt_scene *s, int ctas_per_sm, int refill_threshold, int variant)
 {
+	return guarded([&]() -> int {
 	if (!s) return fail(ADYPT_EINVAL, "scene is NULL");
 	if (ctas_per_sm < 0 || refill_threshold < 0 || refill_threshold > 32 || variant < 0 || variant > 7) return fail(ADYPT_EINVAL, "bad tuning value");
 	s->ctas_per_sm = ctas_per_sm;
 	s->refill_threshold = refill_threshold;
 	s->variant = variant;
 	return ADYPT_OK;
+	});
 }
 
 static int trace_host(adypt_scene *s, const float *rays, uint64_t n, int32_t *tri, float *t, float *uv, uint8_t *occ, cudaStream_t user_stream)
@@ -398,6 +414,7 @@ static int trace_host(adypt_scene *s, const float *rays, uint64_t n, int32_t *tr
 
 int adypt_trace_closest(adypt_scene *s, const float *rays, uint64_t n, int32_t *tri, float *t, float *uv, int memspace, void *stream)
 {
+	return guarded([&]() -> int {
 	if (!s) return fail(ADYPT_EINVAL, "scene is NULL");
 	if (n == 0) return ADYPT_OK;
 	if (!rays || !tri) return fail(ADYPT_EINVAL, "rays/tri is NULL");
@@ -408,10 +425,12 @@ int adypt_trace_closest(adypt_scene *s, const float *rays, uint64_t n, int32_t *
 	if (memspace == ADYPT_MEM_DEVICE)
 		return launch_trace(s, (const float4 *)rays, n, tri, t, (float2 *)uv, nullptr, (cudaStream_t)stream);
 	return trace_host(s, rays, n, tri, t, uv, nullptr, (cudaStream_t)stream);
+	});
 }
 
 int adypt_trace_stats(adypt_scene *s, const float *rays, uint64_t n, int memspace, uint64_t out[4])
 {
+	return guarded([&]() -> int {
 	if (!s || !out) return fail(ADYPT_EINVAL, "scene/out is NULL");
 	out[0] = out[1] = out[2] = out[3] = 0;
 	if (n == 0) return ADYPT_OK;
@@ -444,10 +463,12 @@ int adypt_trace_stats(adypt_scene *s, const float *rays, uint64_t n, int memspac
 	ADYPT_CUDA(cudaMemcpy(h, d_stats, sizeof(h), cudaMemcpyDeviceToHost));
 	for (int i = 0; i < 4; ++i) out[i] = h[i];
 	return ADYPT_OK;
+	});
 }
 
 int adypt_trace_any(adypt_scene *s, const float *rays, uint64_t n, uint8_t *occluded, int memspace, void *stream)
 {
+	return guarded([&]() -> int {
 	if (!s) return fail(ADYPT_EINVAL, "scene is NULL");
 	if (n == 0) return ADYPT_OK;
 	if (!rays || !occluded) return fail(ADYPT_EINVAL, "rays/occluded is NULL");
@@ -457,6 +478,7 @@ int adypt_trace_any(adypt_scene *s, const float *rays, uint64_t n, uint8_t *occl
 	if (memspace == ADYPT_MEM_DEVICE)
 		return launch_trace(s, (const float4 *)rays, n, nullptr, nullptr, nullptr, occluded, (cudaStream_t)stream);
 	return trace_host(s, rays, n, nullptr, nullptr, nullptr, occluded, (cudaStream_t)stream);
+	});
 }
 
 } // extern "C"

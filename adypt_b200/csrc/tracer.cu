@@ -692,6 +692,7 @@ extern "C" {
 int adypt_tracer_create(adypt_scene *scene, const adypt_pt_config *config, int32_t width, int32_t height, uint64_t bias_seed,
                         adypt_tracer **out)
 {
+	return guarded([&]() -> int {
 	if (!scene || !config || !out) return fail(ADYPT_EINVAL, "scene/config/out is NULL");
 	*out = nullptr;
 	if (width <= 0 || height <= 0 || (uint64_t)width * (uint64_t)height >= (1ull << 31)) return fail(ADYPT_EINVAL, "bad image size");
@@ -719,7 +720,12 @@ int adypt_tracer_create(adypt_scene *scene, const adypt_pt_config *config, int32
 	if (e == cudaSuccess) e = cudaMemset(t->d_counts, 0, kCountSlots * sizeof(unsigned long long));
 	if (e == cudaSuccess) e = cudaMemcpy(t->d_dirs, sobol_directions(), (size_t)sobol_max_dim() * 32u * 4u, cudaMemcpyHostToDevice);
 	if (e == cudaSuccess) {
-		t->h_bias.resize(np * 2u);
+		try {
+			t->h_bias.resize(np * 2u);
+		} catch (const std::bad_alloc &) {
+			free_tracer(t);
+			return fail(ADYPT_ENOMEM, "tracer allocation: out of host memory");
+		}
 		fill_bias(bias_seed, np * 2u, t->h_bias.data());
 		e = cudaMemcpy(t->d_bias, t->h_bias.data(), np * 2u, cudaMemcpyHostToDevice);
 	}
@@ -734,26 +740,32 @@ int adypt_tracer_create(adypt_scene *scene, const adypt_pt_config *config, int32
 	t->launches_at_create = g_launches.load();
 	*out = t;
 	return ADYPT_OK;
+	});
 }
 
 int adypt_tracer_destroy(adypt_tracer *t)
 {
+	return guarded([&]() -> int {
 	if (t) free_tracer(t);
 	return ADYPT_OK;
+	});
 }
 
 int adypt_tracer_set_config(adypt_tracer *t, const adypt_pt_config *config)
 {
+	return guarded([&]() -> int {
 	if (!t || !config) return fail(ADYPT_EINVAL, "tracer/config is NULL");
 	ADYPT_TRY(check_config(config));
 	t->cfg = *config;
 	t->cam.tmin = config->ray_tmin; // update_config_args, OglPathTracer.cpp:216
 	t->prim_valid = false;
 	return ADYPT_OK;
+	});
 }
 
 int adypt_tracer_set_sun_visibility(adypt_tracer *t, int32_t enabled, const float direction[3])
 {
+	return guarded([&]() -> int {
 	if (!t || (enabled && !direction)) return fail(ADYPT_EINVAL, "NULL argument");
 	t->sun_visibility = enabled != 0;
 	if (enabled) {
@@ -765,37 +777,45 @@ int adypt_tracer_set_sun_visibility(adypt_tracer *t, int32_t enabled, const floa
 		t->sun_dir[2] = z * inv;
 	}
 	return ADYPT_OK;
+	});
 }
 
 int adypt_tracer_set_bias(adypt_tracer *t, const uint8_t *rg8)
 {
+	return guarded([&]() -> int {
 	if (!t || !rg8) return fail(ADYPT_EINVAL, "tracer/rg8 is NULL");
 	DeviceGuard g(t->scene->device);
 	memcpy(t->h_bias.data(), rg8, t->h_bias.size());
 	ADYPT_CUDA(cudaStreamSynchronize(t->stream));
 	ADYPT_CUDA(cudaMemcpy(t->d_bias, rg8, t->h_bias.size(), cudaMemcpyHostToDevice));
 	return ADYPT_OK;
+	});
 }
 
 int adypt_tracer_get_bias(adypt_tracer *t, uint8_t *rg8)
 {
+	return guarded([&]() -> int {
 	if (!t || !rg8) return fail(ADYPT_EINVAL, "tracer/rg8 is NULL");
 	memcpy(rg8, t->h_bias.data(), t->h_bias.size());
 	return ADYPT_OK;
+	});
 }
 
 int adypt_tracer_set_camera(adypt_tracer *t, const float projection[16], const float view[16], const float position[3])
 {
+	return guarded([&]() -> int {
 	if (!t || !projection || !view || !position) return fail(ADYPT_EINVAL, "NULL argument");
 	t->cam.origin[0] = position[0]; t->cam.origin[1] = position[1]; t->cam.origin[2] = position[2];
 	mat4_inverse(projection, t->cam.inv_proj); // OglPathTracer.cpp:30-31
 	mat4_inverse(view, t->cam.inv_view);
 	t->prim_valid = false;
 	return ADYPT_OK;
+	});
 }
 
 int adypt_tracer_primary(adypt_tracer *t, int32_t viewer_type)
 {
+	return guarded([&]() -> int {
 	if (!t) return fail(ADYPT_EINVAL, "tracer is NULL");
 	DeviceGuard g(t->scene->device);
 	ADYPT_TRY(alloc_wavefront(t));
@@ -811,10 +831,12 @@ int adypt_tracer_primary(adypt_tracer *t, int32_t viewer_type)
 	t->host_segments += t->npix;
 	t->prim_valid = false;
 	return ADYPT_OK;
+	});
 }
 
 int adypt_tracer_sample(adypt_tracer *t, int32_t n_spp)
 {
+	return guarded([&]() -> int {
 	if (!t) return fail(ADYPT_EINVAL, "tracer is NULL");
 	if (n_spp <= 0) return ADYPT_OK;
 	DeviceGuard g(t->scene->device);
@@ -826,10 +848,12 @@ int adypt_tracer_sample(adypt_tracer *t, int32_t n_spp)
 	ADYPT_TRY(run_range(t, t->spp, n_spp, false));
 	t->spp += n_spp;
 	return ADYPT_OK;
+	});
 }
 
 int adypt_tracer_accumulate(adypt_tracer *t, int32_t first_spp, int32_t n_spp)
 {
+	return guarded([&]() -> int {
 	if (!t) return fail(ADYPT_EINVAL, "tracer is NULL");
 	if (n_spp <= 0) return ADYPT_OK;
 	if (first_spp < 0 || first_spp % t->cfg.tmp_lifetime != 0) return fail(ADYPT_EINVAL, "first_spp must be a non-negative multiple of tmpLifetime");
@@ -837,66 +861,82 @@ int adypt_tracer_accumulate(adypt_tracer *t, int32_t first_spp, int32_t n_spp)
 	t->cam.tmin = t->cfg.ray_tmin;
 	t->prim_valid = false;
 	return run_range(t, first_spp, n_spp, true);
+	});
 }
 
 int adypt_tracer_sum_buffer(adypt_tracer *t, float **device_ptr, uint64_t *n_floats)
 {
+	return guarded([&]() -> int {
 	if (!t || !device_ptr) return fail(ADYPT_EINVAL, "NULL argument");
 	*device_ptr = (float *)t->d_sum;
 	if (n_floats) *n_floats = (uint64_t)t->npix * 4u;
 	return ADYPT_OK;
+	});
 }
 
 int adypt_tracer_result_buffer(adypt_tracer *t, float **device_ptr, uint64_t *n_floats)
 {
+	return guarded([&]() -> int {
 	if (!t || !device_ptr) return fail(ADYPT_EINVAL, "NULL argument");
 	*device_ptr = (float *)t->d_result;
 	if (n_floats) *n_floats = (uint64_t)t->npix * 4u;
 	return ADYPT_OK;
+	});
 }
 
 int adypt_tracer_clear_sum(adypt_tracer *t)
 {
+	return guarded([&]() -> int {
 	if (!t) return fail(ADYPT_EINVAL, "tracer is NULL");
 	DeviceGuard g(t->scene->device);
 	ADYPT_CUDA(cudaMemsetAsync(t->d_sum, 0, (size_t)t->npix * 16u, t->stream));
 	return ADYPT_OK;
+	});
 }
 
 int adypt_tracer_resolve_sum(adypt_tracer *t)
 {
+	return guarded([&]() -> int {
 	if (!t) return fail(ADYPT_EINVAL, "tracer is NULL");
 	DeviceGuard g(t->scene->device);
 	k_resolve_sum<<<grid_for(t->npix, 256, t->scene->sm_count), 256, 0, t->stream>>>(t->d_sum, t->d_result, t->npix);
 	count_launch();
 	ADYPT_CUDA(cudaGetLastError());
 	return ADYPT_OK;
+	});
 }
 
 int adypt_tracer_spp(adypt_tracer *t, int32_t *spp)
 {
+	return guarded([&]() -> int {
 	if (!t || !spp) return fail(ADYPT_EINVAL, "NULL argument");
 	*spp = t->spp;
 	return ADYPT_OK;
+	});
 }
 
 int adypt_tracer_stream(adypt_tracer *t, void **stream)
 {
+	return guarded([&]() -> int {
 	if (!t || !stream) return fail(ADYPT_EINVAL, "NULL argument");
 	*stream = (void *)t->stream;
 	return ADYPT_OK;
+	});
 }
 
 int adypt_tracer_sync(adypt_tracer *t)
 {
+	return guarded([&]() -> int {
 	if (!t) return fail(ADYPT_EINVAL, "tracer is NULL");
 	DeviceGuard g(t->scene->device);
 	ADYPT_CUDA(cudaStreamSynchronize(t->stream));
 	return ADYPT_OK;
+	});
 }
 
 int adypt_tracer_read(adypt_tracer *t, float *out, int32_t channels)
 {
+	return guarded([&]() -> int {
 	if (!t || !out) return fail(ADYPT_EINVAL, "NULL argument");
 	if (channels != 3 && channels != 4) return fail(ADYPT_EINVAL, "channels must be 3 or 4");
 	DeviceGuard g(t->scene->device);
@@ -914,20 +954,24 @@ int adypt_tracer_read(adypt_tracer *t, float *out, int32_t channels)
 		out[3 * i + 2] = tmp[4 * i + 2];
 	}
 	return ADYPT_OK;
+	});
 }
 
 int adypt_tracer_save_exr(adypt_tracer *t, const char *filename, int32_t save_as_fp16)
 {
+	return guarded([&]() -> int {
 	if (!t || !filename) return fail(ADYPT_EINVAL, "NULL argument");
 	std::vector<float> rgb((size_t)t->npix * 3u);
 	ADYPT_TRY(adypt_tracer_read(t, rgb.data(), 3));
 	const int rc = adypt_write_exr(filename, rgb.data(), t->width, t->height, save_as_fp16);
 	if (rc != ADYPT_OK) return fail(rc, std::string("cannot write ") + filename);
 	return ADYPT_OK;
+	});
 }
 
 int adypt_tracer_primary_rays(adypt_tracer *t, float *rays, int memspace)
 {
+	return guarded([&]() -> int {
 	if (!t || !rays) return fail(ADYPT_EINVAL, "NULL argument");
 	DeviceGuard g(t->scene->device);
 	t->cam.tmin = t->cfg.ray_tmin;
@@ -943,10 +987,12 @@ int adypt_tracer_primary_rays(adypt_tracer *t, float *rays, int memspace)
 	if (memspace == ADYPT_MEM_HOST) ADYPT_CUDA(cudaMemcpyAsync(rays, dst, (size_t)t->npix * 32u, cudaMemcpyDeviceToHost, t->stream));
 	ADYPT_CUDA(cudaStreamSynchronize(t->stream));
 	return ADYPT_OK;
+	});
 }
 
 int adypt_debug_math(int32_t device, int32_t op, const float *x, const float *y, uint64_t n, float *out, float *out2)
 {
+	return guarded([&]() -> int {
 	if (!x || !out || (op == 0 && !out2) || (op == 1 && !y) || (op != 0 && op != 1)) return fail(ADYPT_EINVAL, "bad argument");
 	if (n == 0) return ADYPT_OK;
 	int ndev = 0;
@@ -967,10 +1013,12 @@ int adypt_debug_math(int32_t device, int32_t op, const float *x, const float *y,
 	cudaFree(d);
 	if (e != cudaSuccess) return fail(ADYPT_ECUDA, std::string("adypt_debug_math: ") + cudaGetErrorString(e));
 	return ADYPT_OK;
+	});
 }
 
 int adypt_tracer_stats(adypt_tracer *t, uint64_t *segments, uint64_t *launches)
 {
+	return guarded([&]() -> int {
 	if (!t) return fail(ADYPT_EINVAL, "tracer is NULL");
 	DeviceGuard g(t->scene->device);
 	unsigned long long dev = 0;
@@ -979,6 +1027,7 @@ int adypt_tracer_stats(adypt_tracer *t, uint64_t *segments, uint64_t *launches)
 	if (segments) *segments = t->host_segments + dev;
 	if (launches) *launches = g_launches.load() - t->launches_at_create;
 	return ADYPT_OK;
+	});
 }
 
 } // extern "C"

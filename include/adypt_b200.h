@@ -39,7 +39,8 @@ enum {
 	ADYPT_ECUDA = -3,   /* CUDA runtime error (message has the cudaError string) */
 	ADYPT_ENOMEM = -4,  /* allocation failed */
 	ADYPT_EIO = -5,     /* file could not be written */
-	ADYPT_ERANGE = -6   /* value outside what the implementation supports (e.g. Sobol dimensions) */
+	ADYPT_ERANGE = -6,  /* value outside what the implementation supports (e.g. Sobol dimensions) */
+	ADYPT_EINTERNAL = -7 /* an unexpected C++ exception was caught at the boundary (message has what()) */
 };
 
 /* where the buffers of a batch call live */

@@ -4,6 +4,8 @@ import ctypes as C
 import glob
 import os
 import re
+import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -110,3 +112,25 @@ def test_reader_parses_reference_showcase_exr():
     assert [c for c, _ in r["channels"]] == ["B", "G", "R"] and all(t == 1 for _, t in r["channels"])
     assert r["compression"] == 3
     assert np.isfinite(r["data"]["R"]).all() and r["data"]["R"].mean() > 0
+
+
+def test_no_exception_crosses_the_c_boundary():
+    """Every extern "C" body runs inside guarded(): a std::bad_alloc inside the library comes back as ADYPT_ENOMEM
+    with a message instead of terminating the host process. Provoked in a child process with a 4 GiB address-space
+    limit and a 200 M-triangle request (the 20 GB vector resize fails before any input is read)."""
+    code = r"""
+import ctypes as C, resource, sys
+sys.path.insert(0, %r)
+import numpy as np
+import adypt_b200 as A
+from adypt_b200 import host
+lib = host._lib()
+pos = np.zeros((4, 9), dtype=np.float32); mid = np.zeros(4, dtype=np.int32); mats = np.zeros((1, 64), dtype=np.uint8)
+resource.setrlimit(resource.RLIMIT_AS, (4 << 30, 4 << 30))
+h = C.c_void_p()
+rc = lib.adypt_host_scene_from_triangles(pos.ctypes.data, mid.ctypes.data, 200_000_000, mats.ctypes.data, 1, C.byref(h))
+print("RC", rc, A.load_library().adypt_last_error().decode())
+""" % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "RC -4 out of host memory" in r.stdout, r.stdout + r.stderr[-500:]
