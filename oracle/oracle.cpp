@@ -12,13 +12,17 @@
 //   src/Util/Sobol.cpp:5-21         Gray-code Sobol                  -> oracle_sobol_*
 //   shaders/pathtracer.glsl:49-227 + OglPathTracer.cpp:34-61 path tracer -> oracle_pt.inc
 //
-// PARITY PINNING: the reference ships no golden vectors or tests for this path, and its
-// GPU arithmetic is whatever a GL driver's GLSL compiler emits, so bit-level truth for the traversal is
-// DEFINED here by the FP policy in DESIGN.md ("un-fused left-to-right IEEE fp32, except explicit fmaf in
-// the slab test and the Woop dot chains"). What CAN be pinned is pinned in tests/: Woop rows, mat4
-// inverse, camera matrices, Sobol vectors and CWBVH arrays against the reference's own C++ compiled in
-// place (oracle/_ref), and traversal results against an O(N) brute-force Woop test over all leaf
-// references plus hand-checked tiny scenes (tests/golden/).
+// PARITY PINNING: the reference ships no golden vectors or tests for this path and its GL
+// program cannot run here, so the oracle is pinned against the reference's SOURCES compiled in place:
+//  * host side (Woop rows, mat4 inverse, camera matrices, Sobol vectors, CWBVH arrays) against the reference's
+//    own C++ (oracle/_ref/libadypt_ref.so, tests/test_oracle_pins.py);
+//  * traversal and shading against the reference's own SHADER TEXT run on the CPU (oracle/_ref/libadypt_glsl.so,
+//    built by glsl_transpile.py from shaders/*.glsl; tests/test_glsl_reference.py): ids, uv, any-hit bits,
+//    viewer images and path-traced images agree bit for bit;
+//  * plus an O(N) brute-force Woop test over all leaf references and hand-checked tiny scenes (tests/golden/).
+// The GPU's arithmetic is whatever a GL driver's GLSL compiler emits, so the one thing DEFINED here rather than
+// taken from the reference is the FP policy in DESIGN.md §3 ("un-fused left-to-right IEEE fp32, except explicit
+// fmaf in the slab test and the Woop dot chains"); the shader build applies the same policy.
 //
 // Build: make -C oracle oracle   (-O3 -mavx2 -mfma -ffp-contract=off)
 #include <algorithm>
