@@ -5,7 +5,7 @@ Workload: ~1.0M-triangle procedural box city, 8M incoherent cosine-weighted boun
 of 1000x1000 primary rays. One "step" = one closest-hit pass over the whole 8M-ray batch.
 
   python bench.py [--gpus N] [--steps K] [--warmup W]            product arm (CUDA, sm_100a)
-  python bench.py --impl reference [...]                          reference arm: CPU port of traversal.glsl
+  python bench.py --impl reference [...]                          reference arm: the reference's traversal.glsl on the CPU
   torchrun --nproc-per-node N bench.py --gpus N ...               one rank per GPU, weak scaling (each rank
                                                                   traces its own 8M-ray batch, no collective)
 Prints ONE JSON line on rank 0. See DESIGN.md §6 for how every field is measured.
@@ -94,21 +94,35 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_leg(bvh, rays, budget_s=12.0):
-    """The CPU port of traversal.glsl (oracle/oracle.cpp) on all host threads over a bounded sample."""
+def cpu_tracer(bvh):
+    """The CPU implementation timed as the baseline: the reference's own shaders/traversal.glsl compiled for the CPU
+    (oracle/_ref/libadypt_glsl.so, kind "reference") when that build exists, else the oracle's C++ port (kind "port")."""
+    from oracle import cpu, glsl_ref
+    if glsl_ref.available():
+        return (lambda r: glsl_ref.trace_closest(bvh.nodes, bvh.tri_indices, bvh.woop, r)[0]), "reference", \
+            "the reference's shaders/traversal.glsl compiled for the CPU from its own text (oracle/glsl_transpile.py)"
+    return (lambda r: cpu.trace_closest(bvh.nodes, bvh.tri_indices, bvh.woop, r, want_t=False)["tri"]), "port", \
+        "multithreaded C++ port of shaders/traversal.glsl (oracle/oracle.cpp)"
+
+
+def cpu_leg(bvh, rays, budget_s=10.0):
+    """The CPU baseline on all host threads over a bounded sample (+ the oracle's counters on the same sample)."""
     from oracle import cpu
     cores = cpu.hardware_threads()
     probe = min(rays.shape[0], 262144)
     bvh.woop = cpu.build_woop(bvh.tris, bvh.tri_indices)
+    trace, kind, what = cpu_tracer(bvh)
     t0 = time.perf_counter()
-    cpu.trace_closest(bvh.nodes, bvh.tri_indices, bvh.woop, rays[:probe], want_t=False)
+    trace(rays[:probe])
     rate = probe / (time.perf_counter() - t0)
     n = int(min(rays.shape[0], max(probe, rate * budget_s)))
     t0 = time.perf_counter()
-    r = cpu.trace_closest(bvh.nodes, bvh.tri_indices, bvh.woop, rays[:n], want_t=False)
+    tri = trace(rays[:n])
     dt = time.perf_counter() - t0
-    return dict(value=n / dt / 1e6, unit=UNIT, cores=cores, kind="port",
-                sample=f"first {n} of the {rays.shape[0]} rays of the same batch, {cores} threads, dynamic 4096-ray chunks",
+    r = cpu.trace_closest(bvh.nodes, bvh.tri_indices, bvh.woop, rays[:n], want_t=False)
+    assert np.array_equal(tri, r["tri"]), "CPU baseline and oracle disagree"
+    return dict(value=n / dt / 1e6, unit=UNIT, cores=cores, kind=kind, what=what,
+                sample=f"first {n} of the {rays.shape[0]} rays of the same batch, {cores} threads",
                 per_core=n / dt / 1e6 / cores), r["counters"], n
 
 
@@ -130,17 +144,18 @@ def run_reference(args, rank, world):
     ph = cpu.trace_closest(bvh.nodes, bvh.tri_indices, bvh.woop, prim)
     rays = W.bounce_rays(mesh.positions(), prim, ph["tri"], ph["uv"], per_hit=8, seed=RAY_SEED)
     cores = cpu.hardware_threads()
+    trace, kind, what = cpu_tracer(bvh)
     # bounded sample per step so the whole run ends within minutes on any host
     t0 = time.perf_counter()
-    cpu.trace_closest(bvh.nodes, bvh.tri_indices, bvh.woop, rays[:262144], want_t=False)
+    trace(rays[:262144])
     rate = 262144 / (time.perf_counter() - t0)
     budget = 90.0 / max(1, args.steps + args.warmup)
     n = int(min(rays.shape[0], max(262144, rate * min(budget, 15.0))))
     for _ in range(args.warmup):
-        cpu.trace_closest(bvh.nodes, bvh.tri_indices, bvh.woop, rays[:n], want_t=False)
+        trace(rays[:n])
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu.trace_closest(bvh.nodes, bvh.tri_indices, bvh.woop, rays[:n], want_t=False)
+        trace(rays[:n])
     dt = (time.perf_counter() - t0) / args.steps
     v = n / dt / 1e6
     sample = f"first {n} of the {rays.shape[0]} rays per step, {cores} threads"
@@ -149,9 +164,9 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": cfg,
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "the reference's hot path is GLSL under OpenGL and cannot run headless; this is the multithreaded C++ port of shaders/traversal.glsl (oracle/oracle.cpp) on the host cores",
+        "note": "the reference's hot path is GLSL under OpenGL and cannot run headless; timed here on the host cores: " + what,
     }), flush=True)
 
 
