@@ -127,11 +127,11 @@ int launch_trace(adypt_scene *s, const float4 *d_rays, uint64_t n, int32_t *d_tr
 	}
 	ADYPT_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned long long), stream));
 	// code-generation variants of the same algorithm (identical results); 0 = tuned default: 4 conversion planes on
-	// the I2F pipe, 8 CTAs/SM, triangle batch 2 (closest-hit: with both fetches up front)
+	// the I2F pipe, 8 CTAs/SM, triangle batch 2 with both fetches up front
 	if (any) switch (s->variant) {
 	case 1: trace_kernel<true, false, 2, 8, 0><<<grid, kTraceBlock, 0, stream>>>(p); break;
 	case 2: trace_kernel<true, false, 2, 8, 2><<<grid, kTraceBlock, 0, stream>>>(p); break;
-	case 5: trace_kernel<true, false, 4, 8, 12><<<grid, kTraceBlock, 0, stream>>>(p); break;
+	case 5: trace_kernel<true, false, 4, 8, 2><<<grid, kTraceBlock, 0, stream>>>(p); break;
 	default: trace_kernel<true><<<grid, kTraceBlock, 0, stream>>>(p); break;
 	}
 	else switch (s->variant) {

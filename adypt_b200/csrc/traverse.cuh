@@ -118,7 +118,7 @@ __device__ __forceinline__ uint32_t test_children4(uint32_t meta4, uint32_t octi
 // the group is empty; 12 = K 2 with both triangles' rows fetched before the first test. Only the warp-level
 // interleaving differs: each ray's own sequence of node steps and triangle tests -- and therefore every result and
 // counter -- is the same. A warp no longer waits for its one lane with nine triangles: -12 % time on C2.
-template <bool ANY, bool STATS = false, int CVT_PLANES = 4, int MIN_CTAS = 8, int TRI_BATCH = (ANY ? 2 : 12)>
+template <bool ANY, bool STATS = false, int CVT_PLANES = 4, int MIN_CTAS = 8, int TRI_BATCH = 12>
 __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const TraceParams p)
 {
 	const uint32_t magic = p.magic;
@@ -134,25 +134,25 @@ __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const Trac
 	unsigned long long pool_next = 0, pool_end = 0;
 	bool exhausted = false;
 
-	// per-lane ray state
-	bool active = false;
-	bool unsaved = false; // the lane's finished ray still has its result in registers (stored at the next refill)
+	// per-lane ray state. sp doubles as the lane's status: >= 0 traversing (stack depth), kIdle = no ray,
+	// kUnsaved = ray finished, result still in registers (stored at the next refill)
+	constexpr int kIdle = -1, kUnsaved = -2;
 	unsigned long long ray_idx = 0;
 	float ox = 0, oy = 0, oz = 0, tmin = 0, dx = 0, dy = 0, dz = 0, idx = 0, idy = 0, idz = 0;
 	uint32_t octinv = 0;
 	float hit_t = 0, hit_u = 0, hit_v = 0;
 	int32_t hit_idx = -1;
 	uint2 ng = make_uint2(0, 0), tg = make_uint2(0, 0);
-	int sp = 0;
+	int sp = kIdle;
 	unsigned long long st_nodes = 0, st_tris = 0, st_hits = 0, st_depth = 0; // dead code unless STATS
 
 	for (;;) {
 		// ---------------------------------------------------------------- refill idle lanes
-		unsigned idle = __ballot_sync(kFullMask, !active);
+		unsigned idle = __ballot_sync(kFullMask, sp < 0);
 		// Results of rays that finished since the last refill are written here, by all such lanes together
 		// (about 6 per pass), instead of by 1-3 lanes at the moment each ray ends.
-		if (unsaved) {
-			unsaved = false;
+		if (sp == kUnsaved) {
+			sp = kIdle;
 			if (STATS && hit_t < 1e9f) ++st_hits;
 			if (ANY) {
 				p.out_occ[ray_idx] = (hit_t < 1e9f) ? 1 : 0;
@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const Trac
 				pool_end = (b + p.pool_chunk < n_rays) ? b + p.pool_chunk : n_rays;
 			}
 			const unsigned long long cand = pool_next + __popc(idle & lt_mask);
-			const bool take = !active && cand < pool_end;
+			const bool take = sp < 0 && cand < pool_end;
 			if (take) {
 				// ray setup, traversal.glsl:16-35
 				ray_idx = cand;
@@ -191,18 +191,17 @@ __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const Trac
 				ng = make_uint2(0u, 0x80000000u);
 				tg = make_uint2(0u, 0u);
 				sp = 0;
-				active = true;
 			}
 			const unsigned took = __ballot_sync(kFullMask, take);
 			pool_next += __popc(took);
 			idle &= ~took;
 		}
-		if (!__any_sync(kFullMask, active)) break;
+		if (!__any_sync(kFullMask, sp >= 0)) break;
 
 		// ---------------------------------------------------------------- traverse
 		unsigned busy;
 		do {
-			if (active) {
+			if (sp >= 0) {
 				if (TRI_BATCH > 0 && tg.y != 0u) {
 					// triangles left over from the previous round: no node step yet
 				} else if (ng.y > 0x00ffffffu) {
@@ -246,10 +245,10 @@ __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const Trac
 						aix, aiy, aiz, aox, aoy, aoz, tmin, hit_t, magic);
 					ng.y = (hitmask & 0xff000000u) | (n0.w >> 24);
 					tg.y = hitmask & 0x00ffffffu;
-				} else { // :207-211
-					tg = ng;
-					ng = make_uint2(0u, 0u);
 				}
+				// The GLSL's else branch (:207-211, "G is a triangle group": tg = ng, ng = 0) cannot be reached: ng.y is
+				// above 0x00ffffff at ray start and after every pop (only groups with inner hits are pushed), and a
+				// group that loses its last inner hit is replaced at the bottom of the same round.
 
 				bool finished = false;
 				// Woop test of leaf reference TR with rows M0..M2 (:221-241)
@@ -303,12 +302,9 @@ __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const Trac
 					}
 				}
 
-				if (finished) {
-					active = false;
-					unsaved = true;
-				}
+				if (finished) sp = kUnsaved;
 			}
-			busy = __ballot_sync(kFullMask, active);
+			busy = __ballot_sync(kFullMask, sp >= 0);
 		} while (busy != 0u && (exhausted || __popc(busy) >= p.refill_threshold));
 	}
 	if (STATS) {
