@@ -10,8 +10,9 @@ struct DecodedImage { // RGB8, top row first (what stbi_load(..., 3) returns)
 	int width = 0, height = 0;
 	std::vector<uint8_t> rgb;
 };
-// PNG / TGA file -> RGB8; false when the file is missing or in a format that is not decoded
+// PNG / JPEG / TGA file -> RGB8; false when the file is missing or in a format that is not decoded
 bool decode_image_file(const char *path, DecodedImage *out);
+bool decode_jpeg(const std::vector<uint8_t> &file, DecodedImage *out); // jpeg_decode.cpp
 } // namespace host
 } // namespace adypt
 

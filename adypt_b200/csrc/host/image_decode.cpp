@@ -1,9 +1,9 @@
 // Texture file decoding for diffuse maps (map_Kd): the stand-in for stbi_load(filename, &w, &h, &n, 3) as
 // OglScene::load_texture calls it (src/Tracer/OglScene.cpp:12-43). Output: tightly packed RGB8, top row first.
-// Formats: PNG (all colour types and bit depths, Adam7 interlace; zlib does the inflate) and TGA (true-colour
-// 24/32 bpp and 8-bit grey, raw or RLE, either origin). Conversions to 3 channels follow stb_image's rules
-// (grey replicated, alpha dropped, 16-bit samples truncated to their high byte, 1/2/4-bit grey scaled by
-// 255/85/17). JPEG/BMP/PSD/GIF/HDR are not decoded: such a texture fails to load, which the reference
+// Formats: PNG (all colour types and bit depths, Adam7 interlace; zlib does the inflate), JPEG (jpeg_decode.cpp)
+// and TGA (true-colour 24/32 bpp and 8-bit grey, raw or RLE, either origin). Conversions to 3 channels follow
+// stb_image's rules (grey replicated, alpha dropped, 16-bit samples truncated to their high byte, 1/2/4-bit grey
+// scaled by 255/85/17). BMP/PSD/GIF/HDR are not decoded: such a texture fails to load, which the reference
 // handles by giving the material texture index -1 (OglScene.cpp:27-32).
 #include <zlib.h>
 #include <cstdint>
@@ -209,6 +209,7 @@ bool decode_image_file(const char *path, DecodedImage *img)
 	std::vector<uint8_t> file;
 	if (!read_file(path, &file)) return false;
 	if (decode_png(file, img)) return true;
+	if (decode_jpeg(file, img)) return true;
 	const size_t n = strlen(path);
 	if (n > 4 && (!strcmp(path + n - 4, ".tga") || !strcmp(path + n - 4, ".TGA"))) return decode_tga(file, img); // TGA has no magic number
 	return false;

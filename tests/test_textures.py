@@ -37,6 +37,7 @@ def make_images(d):
     save("rgba.tga", PIL.fromarray(rgba))
     save("grey.tga", PIL.fromarray(grey))
     save("photo.jpg", PIL.fromarray(rgb))
+    save("unsupported.bmp", PIL.fromarray(rgb))
     return files
 
 
@@ -52,14 +53,105 @@ def test_decoders_match_stb_image(refmod, tmp_path):
     for name, path in files.items():
         exp = refmod.load_image_rgb8(path)  # stbi_load(path, ..., 3)
         assert exp is not None
-        if name.endswith(".jpg"):
-            continue  # JPEG is not decoded here: the material gets texture index -1 (checked below)
+        if name.endswith(".bmp"):
+            continue  # BMP is not decoded here: the material gets texture index -1 (checked below)
         got = next(decoded)
         assert got.shape == exp.shape, name
         assert np.array_equal(got, exp), name
     assert (ok, bad) == (len(files) - 1, 1)
     dtex = hs.mats[:, 0:4].copy().view(np.int32).ravel()
     assert dtex.tolist() == list(range(len(files) - 1)) + [-1]  # renumbered among the loaded ones; failure -> -1
+
+
+def jpeg_cases(d):
+    """JPEG files covering what stb_image's decoder distinguishes: baseline / progressive, 4:4:4 / 4:2:2 / 4:2:0 /
+    4:1:1 chroma, grey, CMYK and YCCK (Adobe), RGB-tagged components, restart intervals, 16x16-MCU images whose
+    size is not a multiple of anything, one-pixel-wide images, optimised Huffman tables, high and low quality."""
+    rng = np.random.default_rng(11)
+    yy, xx = np.mgrid[0:95, 0:131]
+    smooth = np.stack([(np.sin(xx / 9.0) * 0.5 + 0.5) * 255, (np.cos(yy / 7.0) * 0.5 + 0.5) * 255, ((xx + yy) % 64) * 4], axis=2)
+    photo = np.clip(smooth + rng.normal(0, 12, smooth.shape), 0, 255).astype(np.uint8)
+    noise = rng.integers(0, 256, size=(37, 53, 3), dtype=np.uint8)
+    out = {}
+
+    def save(name, arr, mode=None, **kw):
+        p = os.path.join(d, name)
+        img = PIL.fromarray(arr, mode) if mode else PIL.fromarray(arr)
+        img.save(p, "JPEG", **kw)
+        out[name] = p
+
+    for sub, tag in ((0, "444"), (1, "422"), (2, "420")):
+        save(f"base_{tag}.jpg", photo, quality=85, subsampling=sub)
+        save(f"prog_{tag}.jpg", photo, quality=85, subsampling=sub, progressive=True)
+    save("noise_420_q30.jpg", noise, quality=30, subsampling=2)
+    save("noise_444_q100.jpg", noise, quality=100, subsampling=0)
+    save("optimized.jpg", photo, quality=70, optimize=True)
+    save("prog_noise.jpg", noise, quality=50, progressive=True, subsampling=2)
+    save("grey.jpg", photo[..., 0], quality=80)
+    save("grey_prog.jpg", photo[..., 1], quality=80, progressive=True)
+    save("cmyk.jpg", np.concatenate([photo, 255 - photo[..., :1]], axis=2), "CMYK", quality=90)
+    save("rgb_tagged.jpg", photo, quality=90, subsampling=0, keep_rgb=True)
+    save("restart.jpg", photo, quality=75, subsampling=2, restart_marker_blocks=3)
+    save("restart_prog.jpg", photo, quality=75, subsampling=1, progressive=True, restart_marker_rows=1)
+    save("column.jpg", photo[:, :1], quality=90, subsampling=2)
+    save("row.jpg", photo[:1, :], quality=90, subsampling=2)
+    save("pixel.jpg", photo[:1, :1], quality=90, subsampling=2)
+    save("w17h9_411.jpg", photo[:9, :17], quality=90, subsampling="4:1:1")
+    save("qtables16.jpg", photo, qtables=[[255 + i * 3 for i in range(64)], [300 + i for i in range(64)]], subsampling=2)
+    # PIL writes 4-component files as plain CMYK (Adobe transform 0); patch the flag to get the other two readings
+    ycck = open(out["cmyk.jpg"], "rb").read()
+    at = ycck.index(b"Adobe") + 11
+    assert ycck[at] == 0
+    for t, name in ((2, "cmyk_read_as_ycck.jpg"), (1, "cmyk_transform1.jpg")):
+        out[name] = os.path.join(d, name)
+        open(out[name], "wb").write(ycck[:at] + bytes([t]) + ycck[at + 1:])
+    # and a 3-component Adobe file without JFIF whose transform says "already RGB"
+    tagged = open(out["base_444.jpg"], "rb").read()
+    j = tagged.index(b"JFIF")
+    out["adobe_rgb_no_jfif.jpg"] = os.path.join(d, "adobe_rgb_no_jfif.jpg")
+    seg_len = (tagged[j - 2] << 8) | tagged[j - 1]
+    adobe = b"\xff\xee\x00\x0eAdobe\x00\x64\x00\x00\x00\x00\x00"
+    open(out["adobe_rgb_no_jfif.jpg"], "wb").write(tagged[:j - 4] + adobe + tagged[j - 2 + seg_len:])
+    return out
+
+
+def test_jpeg_decoder_matches_stb_image(refmod, tmp_path):
+    files = jpeg_cases(str(tmp_path))
+    assert len(files) >= 20
+    from adypt_b200 import host as H
+    for name, path in files.items():
+        exp = refmod.load_image_rgb8(path)
+        assert exp is not None, name
+        (tmp_path / "j.mtl").write_text(f"newmtl m0\nKd 1 1 1\nillum 1\nmap_Kd {name}\n")
+        (tmp_path / "j.obj").write_text("mtllib j.mtl\nv 0 0 0\nv 1 0 0\nv 0 1 0\nv 3 0 0\nv 4 0 0\nv 3 1 0\nusemtl m0\nf 1 2 3\nf 4 5 6\n")
+        hs = H.HostScene.from_obj(str(tmp_path / "j.obj"))
+        assert hs.load_textures() == (1, 0), name
+        got = hs.textures[0]
+        assert got.shape == exp.shape, (name, got.shape, exp.shape)
+        assert np.array_equal(got, exp), (name, int(np.abs(got.astype(int) - exp.astype(int)).max()), float((got != exp).mean()))
+
+
+def test_corrupt_jpeg_is_rejected_or_harmless(tmp_path):
+    """Truncated and bit-flipped files must never crash the loader: they either fail to load (texture index -1,
+    like the reference when stbi_load returns NULL) or decode to some image of the right size."""
+    files = jpeg_cases(str(tmp_path))
+    from adypt_b200 import host as H
+    rng = np.random.default_rng(3)
+    (tmp_path / "c.obj").write_text("mtllib c.mtl\nv 0 0 0\nv 1 0 0\nv 0 1 0\nv 3 0 0\nv 4 0 0\nv 3 1 0\nusemtl m0\nf 1 2 3\nf 4 5 6\n")
+    (tmp_path / "c.mtl").write_text("newmtl m0\nKd 1 1 1\nillum 1\nmap_Kd broken.jpg\n")
+    for name in ("base_420.jpg", "prog_422.jpg", "restart.jpg", "cmyk.jpg"):
+        data = bytearray(open(files[name], "rb").read())
+        for trial in range(12):
+            bad = bytearray(data)
+            if trial % 3 == 0:
+                bad = bad[: int(len(bad) * rng.uniform(0.05, 0.95))]
+            else:
+                for _ in range(1 + trial):
+                    bad[int(rng.integers(2, len(bad)))] = int(rng.integers(0, 256))
+            (tmp_path / "broken.jpg").write_bytes(bytes(bad))
+            hs = H.HostScene.from_obj(str(tmp_path / "c.obj"))
+            ok, failed = hs.load_textures()
+            assert ok + failed == 1
 
 
 def write_adam7_png(path, img):
