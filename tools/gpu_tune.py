@@ -28,7 +28,7 @@ def main():
     st = torch.cuda.current_stream().cuda_stream
     base = None
     res = {}
-    for variant in (0, 5):
+    for variant in (0, 1, 5):
         for thr in (24, 28, 32):
             for ctas in (0,):
                 sc.configure(ctas, thr, variant)
