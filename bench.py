@@ -160,14 +160,14 @@ def run_reference(args, rank, world):
     v = n / dt / 1e6
     sample = f"first {n} of the {rays.shape[0]} rays per step, {cores} threads"
     cfg = workload_config(rays.shape[0], {"triangles": int(mesh.n_tris)})
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": cfg,
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "the reference's hot path is GLSL under OpenGL and cannot run headless; timed here on the host cores: " + what,
-    }), flush=True)
+    }))
 
 
 def run_native(args, rank, world, local_rank):
@@ -287,7 +287,7 @@ def run_native(args, rank, world, local_rank):
         out["roofline"]["oracle_nodes_per_ray"] = counters["nodes"] / ns
         out["roofline"]["oracle_tris_per_ray"] = counters["tris"] / ns
     if rank == 0:
-        print(json.dumps(out), flush=True)
+        emit(json.dumps(out))
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -323,7 +323,26 @@ def path_tracer_aux(A, torch, dist, rank, local_rank, world):
             "seconds": dt, "gpu_launches": s1["launches"] - s0["launches"], "scaling": "weak"}
 
 
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line. Native libraries write there too (under torchrun NCCL prints its version
+    banner on fd 1, scene loading prints [SCENE] lines), so fd 1 is pointed at stderr for the whole run and the result
+    line is written to the original stdout at the end."""
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line: str):
+    sys.stdout.flush()
+    os.write(_RESULT_FD if _RESULT_FD is not None else 1, (line + "\n").encode())
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
