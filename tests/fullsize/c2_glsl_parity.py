@@ -4,7 +4,7 @@
 Test infrastructure: uses oracle/ as the checker."""
 import json, os, sys, time
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import adypt_b200 as A
 from adypt_b200 import host, workloads as W
 from oracle import cpu, glsl_ref

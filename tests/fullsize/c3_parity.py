@@ -5,7 +5,7 @@ pathtracer.glsl run on the CPU (oracle/_ref/libadypt_glsl.so, when built): 1920x
 Test infrastructure: uses oracle/ as the checker. ~2-3 minutes of CPU time on the GPU box."""
 import json, os, sys, time
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import adypt_b200 as A
 from adypt_b200 import host, workloads as W
 from oracle import cpu

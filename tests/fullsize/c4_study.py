@@ -4,7 +4,7 @@ BVH memory / L2 pressure study: same ray generators as C2, scene scaled to cells
 rows, i.e. 4.4x the 126 MB L2). Prints JSON; run under ncu to get L2 hit rate and DRAM bytes."""
 import json, os, sys, time
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import adypt_b200 as A
 from adypt_b200 import host, workloads as W
@@ -22,7 +22,7 @@ def main():
     reps = int(args[1]) if len(args) > 1 else 5
     mesh = W.city(cells, 1)
     hs = host.HostScene.from_triangles(mesh.positions(), mesh.face_mat, host.materials_array(mesh.materials))
-    cache = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), ".cache", "scenes", mesh.name + ".bvh")
+    cache = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), ".cache", "scenes", mesh.name + ".bvh")
     os.makedirs(os.path.dirname(cache), exist_ok=True)
     t0 = time.time()
     if not hs.load_bvh(cache):

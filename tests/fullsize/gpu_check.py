@@ -2,7 +2,7 @@
 """First-light check on a GPU box: product (CUDA) vs oracle (CPU) on C1, a C2 slice and a small render."""
 import os, sys, time, json
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import adypt_b200 as A
 from adypt_b200 import workloads as W
 from oracle import ref, cpu
