@@ -66,7 +66,8 @@ def test_argument_validation():
 
 def test_product_never_imports_oracle():
     """The product path must not route through the oracle (or any CPU fallback)."""
-    for path in glob.glob(os.path.join(ROOT, "adypt_b200", "**", "*"), recursive=True):
+    paths = glob.glob(os.path.join(ROOT, "adypt_b200", "**", "*"), recursive=True) + glob.glob(os.path.join(ROOT, "tools", "*.py"))
+    for path in paths:
         if os.path.isfile(path) and path.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".inc")):
             txt = open(path, errors="replace").read()
             assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), path
