@@ -28,7 +28,7 @@ EXPORTS = [
     "adypt_host_scene_load_textures", "adypt_host_scene_texture",
     "adypt_scene_read_woop", "adypt_scene_device_bytes", "adypt_trace_closest", "adypt_trace_any", "adypt_trace_stats", "adypt_launch_count",
     "adypt_trace_configure", "adypt_tracer_create", "adypt_tracer_destroy", "adypt_tracer_set_config",
-    "adypt_tracer_set_bias", "adypt_tracer_get_bias", "adypt_tracer_set_sun_visibility", "adypt_tracer_set_camera", "adypt_camera_matrices",
+    "adypt_tracer_set_bias", "adypt_tracer_get_bias", "adypt_tracer_set_sun_visibility", "adypt_tracer_set_russian_roulette", "adypt_tracer_set_camera", "adypt_camera_matrices",
     "adypt_tracer_primary", "adypt_tracer_sample", "adypt_tracer_accumulate", "adypt_tracer_sum_buffer",
     "adypt_tracer_clear_sum", "adypt_tracer_resolve_sum", "adypt_tracer_spp", "adypt_tracer_read",
     "adypt_tracer_result_buffer", "adypt_tracer_save_exr", "adypt_tracer_sync", "adypt_tracer_primary_rays",
@@ -36,7 +36,7 @@ EXPORTS = [
     "adypt_host_scene_load_obj", "adypt_host_scene_from_triangles", "adypt_host_scene_destroy", "adypt_host_scene_build_bvh",
     "adypt_host_scene_load_bvh", "adypt_host_scene_save_bvh", "adypt_host_scene_get", "adypt_host_scene_upload",
     "adypt_config_set_default", "adypt_config_load", "adypt_config_to_json", "adypt_config_save",
-    "adypt_group_create", "adypt_group_destroy", "adypt_group_set_camera", "adypt_group_set_sun_visibility", "adypt_group_render",
+    "adypt_group_create", "adypt_group_destroy", "adypt_group_set_camera", "adypt_group_set_sun_visibility", "adypt_group_set_russian_roulette", "adypt_group_render",
     "adypt_group_read", "adypt_group_save_exr", "adypt_tracer_stream",
 ]
 
@@ -100,6 +100,7 @@ def load_library():
         "adypt_tracer_set_bias": [vp, vp],
         "adypt_tracer_get_bias": [vp, vp],
         "adypt_tracer_set_sun_visibility": [vp, i32, vp],
+        "adypt_tracer_set_russian_roulette": [vp, i32],
         "adypt_tracer_set_camera": [vp, vp, vp, vp],
         "adypt_camera_matrices": [C.c_float, C.c_float, C.c_float, i32, i32, vp, vp],
         "adypt_tracer_primary": [vp, i32],
@@ -328,6 +329,10 @@ class Tracer:
         out = np.zeros((self.height, self.width, 2), dtype=np.uint8)
         _check(load_library().adypt_tracer_get_bias(self._h, out.ctypes.data))
         return out
+
+    def set_russian_roulette(self, start_bounce):
+        """Opt-in extension (not in the reference): roulette from bounce `start_bounce` on; None / negative = off."""
+        _check(load_library().adypt_tracer_set_russian_roulette(self._h, -1 if start_bounce is None else int(start_bounce)))
 
     def set_sun_visibility(self, enabled: bool, direction=(0.6, 1.0, 0.2)):
         """Connect stage: the any-hit sun test the reference has commented out (pathtracer.glsl:132)."""

@@ -19,12 +19,14 @@ using namespace adypt_b200;
 static int usage()
 {
 	fprintf(stderr, "usage: adypt_headless <instance.config> [--spp N] [--out file.exr] [--fp16] [--seed S] [--device D]\n"
-	                "                      [--viewer diffuse|specular|emissive|normal|position] [--per-frame] [--no-bvh-cache] [--keep-config]\n");
+	                "                      [--viewer diffuse|specular|emissive|normal|position] [--per-frame] [--no-bvh-cache] [--keep-config]\n"
+	                "                      [--gpus N] [--preview-every K] [--sun-visibility] [--russian-roulette FIRST_BOUNCE]\n");
 	return 2;
 }
 
 // --gpus N: the same load path as Instance::Initialize (Instance.cpp:10-42), then a render group instead of one tracer
-static int render_on_group(const char *config, int spp, int gpus, const char *out, bool fp16, unsigned long long seed, bool cache, bool sun_visibility)
+static int render_on_group(const char *config, int spp, int gpus, const char *out, bool fp16, unsigned long long seed, bool cache, bool sun_visibility,
+                           int rr_start)
 {
 	InstanceConfig cfg;
 	if (!cfg.LoadFromFile(config)) {
@@ -59,6 +61,7 @@ static int render_on_group(const char *config, int spp, int gpus, const char *ou
 		const float dir[3] = {0.6f, 1.0f, 0.2f};
 		adypt_group_set_sun_visibility(group, 1, dir);
 	}
+	if (rr_start >= 0 && adypt_group_set_russian_roulette(group, rr_start) != ADYPT_OK) printf("[PT]Err: %s\n", adypt_last_error());
 	adypt_group_render(group, 16); // warm-up: allocations, NCCL channels
 	const auto t0 = std::chrono::steady_clock::now();
 	int rc = adypt_group_render(group, spp);
@@ -79,7 +82,7 @@ int main(int argc, char **argv)
 {
 	if (argc < 2) return usage();
 	const char *config = nullptr, *out = "result.exr", *viewer = nullptr;
-	int spp = 64, device = 0, preview_every = 0, gpus = 1;
+	int spp = 64, device = 0, preview_every = 0, gpus = 1, rr_start = -1;
 	bool fp16 = false, per_frame = false, cache = true, keep = false, sun_visibility = false;
 	unsigned long long seed = 0;
 	for (int i = 1; i < argc; ++i) {
@@ -94,6 +97,7 @@ int main(int argc, char **argv)
 		else if (!strcmp(a, "--viewer")) viewer = next();
 		else if (!strcmp(a, "--preview-every")) preview_every = atoi(next());
 		else if (!strcmp(a, "--sun-visibility")) sun_visibility = true; // the shader's commented-out any-hit sun test (pathtracer.glsl:132)
+		else if (!strcmp(a, "--russian-roulette")) rr_start = atoi(next()); // opt-in extension: roulette from bounce N on
 		else if (!strcmp(a, "--per-frame")) per_frame = true; // one Trace(true) per sample, like the viewer's main loop
 		else if (!strcmp(a, "--no-bvh-cache")) cache = false;
 		else if (!strcmp(a, "--keep-config")) keep = true;    // do not rewrite the .config on exit
@@ -102,7 +106,7 @@ int main(int argc, char **argv)
 	}
 	if (!config || spp < 0) return usage();
 
-	if (gpus > 1 && !viewer) return render_on_group(config, spp, gpus, out, fp16, seed, cache, sun_visibility);
+	if (gpus > 1 && !viewer) return render_on_group(config, spp, gpus, out, fp16, seed, cache, sun_visibility, rr_start);
 
 	Instance instance;
 	instance.m_device = device;
@@ -115,6 +119,8 @@ int main(int argc, char **argv)
 		const float dir[3] = {0.6f, 1.0f, 0.2f};
 		adypt_tracer_set_sun_visibility(instance.m_path_tracer.Handle(), 1, dir);
 	}
+	if (rr_start >= 0 && adypt_tracer_set_russian_roulette(instance.m_path_tracer.Handle(), rr_start) != ADYPT_OK)
+		printf("[PT]Err: %s\n", adypt_last_error());
 	instance.m_enable_pt_flag = false;
 	if (viewer) {
 		static const char *names[] = {"diffuse", "specular", "emissive", "radiance", "normal", "position"};

@@ -61,6 +61,9 @@ struct DeviceGuard {
 	{
 		if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
 		ok = cudaSetDevice(dev) == cudaSuccess;
+		// A failed call made earlier by anyone in this process (ours, torch's, ...) leaves its code in the runtime's
+		// "last error" slot; the cudaGetLastError() after our next kernel launch would report it as ours. Start clean.
+		(void)cudaGetLastError();
 	}
 	~DeviceGuard()
 	{

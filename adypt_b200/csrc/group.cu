@@ -122,6 +122,15 @@ int adypt_group_set_camera(adypt_group *g, const float projection[16], const flo
 	});
 }
 
+int adypt_group_set_russian_roulette(adypt_group *g, int32_t start_bounce)
+{
+	return guarded([&]() -> int {
+	if (!g) return fail(ADYPT_EINVAL, "group is NULL");
+	for (adypt_tracer *t : g->tracers) ADYPT_TRY(adypt_tracer_set_russian_roulette(t, start_bounce));
+	return ADYPT_OK;
+	});
+}
+
 int adypt_group_set_sun_visibility(adypt_group *g, int32_t enabled, const float direction[3])
 {
 	return guarded([&]() -> int {

@@ -39,6 +39,8 @@ struct PTArgs { // uuPT (pathtracer.glsl:34-38) + batch bookkeeping
 	int32_t width, height;
 	int32_t first_spp; // spp of the batch's first sample
 	int32_t n_samples; // S
+	int32_t dims;      // Sobol dimensions per sample: 2*max_bounce, +max_bounce roulette draws when rr_start >= 0
+	int32_t rr_start;  // >= 0: Russian roulette from this bounce on (opt-in extension, -1 = the reference's behaviour)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -208,7 +210,7 @@ enum SegmentResult { kEnded = 0, kContinues = 1, kConnects = 2 };
 // shadow ray from `origin` towards the sun is unoccluded -- the test the reference carries commented out at
 // pathtracer.glsl:132.
 __device__ __forceinline__ SegmentResult shade_segment(const ShadeBuffers &B, const PTArgs &A, int b, int32_t tri_idx, float u, float v, float rx,
-                                              float ry, V3 &origin, V3 &dir, V3 &color, V3 &ret)
+                                              float ry, float xi, V3 &origin, V3 &dir, V3 &color, V3 &ret)
 {
 	if (tri_idx == -1) { // :130-135
 		if (B.conn_rays != nullptr) {
@@ -277,6 +279,13 @@ __device__ __forceinline__ SegmentResult shade_segment(const ShadeBuffers &B, co
 		dir = align_direction(sample_hemisphere(rx, ry, 0.0f), normal);
 		color = color * diffuse;
 	}
+	// Russian roulette (BASELINE.json configs[2]; not in the reference, off unless adypt_tracer_set_russian_roulette
+	// asked for it): survive with probability p = min(1, max(color)), then weight by 1/p. xi = this bounce's draw.
+	if (A.rr_start >= 0 && b >= A.rr_start) {
+		const float p = glsl_min(1.0f, glsl_max(color.x, glsl_max(color.y, color.z)));
+		if (!(xi < p)) return kEnded;
+		color = v3(__fdiv_rn(color.x, p), __fdiv_rn(color.y, p), __fdiv_rn(color.z, p));
+	}
 	return kContinues;
 }
 
@@ -301,7 +310,7 @@ __global__ void __launch_bounds__(256) k_shade_primary(ShadeBuffers B, PTArgs A,
 	const unsigned long long rounds = (total + stride - 1) / stride;
 	float bx, by;
 	subpixel_bias(A.subpixel, A.tmp_lifetime, A.first_spp, &bx, &by);
-	const int dims = 2 * A.max_bounce;
+	const int dims = A.dims;
 	for (unsigned long long r = 0; r < rounds; ++r) {
 		const unsigned long long id = r * stride + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
 		bool keep = false, conn = false;
@@ -312,8 +321,9 @@ __global__ void __launch_bounds__(256) k_shade_primary(ShadeBuffers B, PTArgs A,
 			const uchar2 bb = B.bias[pix];
 			const float rx = fract(B.sobol[s * dims + 0] + (float)bb.x / 255.0f);
 			const float ry = fract(B.sobol[s * dims + 1] + (float)bb.y / 255.0f);
+			const float xi = A.rr_start >= 0 ? fract(B.sobol[s * dims + 2 * A.max_bounce] + (float)bb.x / 255.0f) : 0.0f;
 			const float2 uv = B.prim_uv[pix];
-			const SegmentResult res = shade_segment(B, A, 0, B.prim_tri[pix], uv.x, uv.y, rx, ry, origin, dir, color, ret);
+			const SegmentResult res = shade_segment(B, A, 0, B.prim_tri[pix], uv.x, uv.y, rx, ry, xi, origin, dir, color, ret);
 			keep = res == kContinues;
 			conn = res == kConnects; // origin is still the camera position
 			B.ret[id] = make_float4(ret.x, ret.y, ret.z, 0.0f);
@@ -341,7 +351,7 @@ __global__ void __launch_bounds__(256) k_shade_bounce(ShadeBuffers B, PTArgs A, 
 	const unsigned long long total = *B.in_count;
 	const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
 	const unsigned long long rounds = (total + stride - 1) / stride;
-	const int dims = 2 * A.max_bounce;
+	const int dims = A.dims;
 	if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(B.segments, total);
 	for (unsigned long long r = 0; r < rounds; ++r) {
 		const unsigned long long q = r * stride + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -356,11 +366,12 @@ __global__ void __launch_bounds__(256) k_shade_bounce(ShadeBuffers B, PTArgs A, 
 			const uchar2 bb = B.bias[pix];
 			const float rx = fract(B.sobol[s * dims + 2 * b] + (float)bb.x / 255.0f);
 			const float ry = fract(B.sobol[s * dims + 2 * b + 1] + (float)bb.y / 255.0f);
+			const float xi = A.rr_start >= 0 ? fract(B.sobol[s * dims + 2 * A.max_bounce + b] + (float)bb.x / 255.0f) : 0.0f;
 			const float4 c4 = B.color[id], r4 = B.ret[id];
 			color = v3(c4.x, c4.y, c4.z);
 			ret = v3(r4.x, r4.y, r4.z);
 			const float2 uv = B.in_uv[q];
-			const SegmentResult res = shade_segment(B, A, b, B.in_tri[q], uv.x, uv.y, rx, ry, origin, dir, color, ret);
+			const SegmentResult res = shade_segment(B, A, b, B.in_tri[q], uv.x, uv.y, rx, ry, xi, origin, dir, color, ret);
 			keep = res == kContinues;
 			conn = res == kConnects;
 			if (conn) { // the shadow ray starts where this segment started: the previous hit point
@@ -485,6 +496,7 @@ using namespace adypt;
 // ================================================================================================
 struct adypt_tracer {
 	adypt_scene *scene = nullptr;
+	int device = 0; // copy of scene->device: destruction must not depend on the scene still being alive
 	adypt_pt_config cfg{};
 	int width = 0, height = 0;
 	unsigned npix = 0;
@@ -513,6 +525,7 @@ struct adypt_tracer {
 	// connect stage (off by default: the reference's sun test is commented out, pathtracer.glsl:132)
 	bool sun_visibility = false;
 	float sun_dir[3] = {0.f, 0.f, 0.f};
+	int rr_start = -1; // Russian roulette (opt-in extension): first bounce it applies to, -1 = off
 	float4 *d_conn_rays = nullptr;
 	uint8_t *d_conn_occ = nullptr;
 	unsigned long long conn_capacity = 0;
@@ -528,7 +541,7 @@ constexpr unsigned long long kDefaultMaxPaths = 48ull << 20;
 
 void free_tracer(adypt_tracer *t)
 {
-	DeviceGuard g(t->scene->device);
+	DeviceGuard g(t->device);
 	if (t->stream) cudaStreamSynchronize(t->stream);
 	cudaFree(t->d_result); cudaFree(t->d_sum); cudaFree(t->d_prim_tri); cudaFree(t->d_prim_uv); cudaFree(t->d_bias);
 	cudaFree(t->d_dirs); cudaFree(t->d_sobol); cudaFree(t->d_rays[0]); cudaFree(t->d_rays[1]); cudaFree(t->d_hit_tri);
@@ -598,6 +611,8 @@ int run_batch(adypt_tracer *t, int first, int n, bool sum_mode)
 	A.max_bounce = c.max_bounce; A.subpixel = c.subpixel; A.tmp_lifetime = c.tmp_lifetime;
 	A.clamp = c.clamp; A.sun[0] = c.sun[0]; A.sun[1] = c.sun[1]; A.sun[2] = c.sun[2];
 	A.width = t->width; A.height = t->height; A.first_spp = first; A.n_samples = n;
+	A.rr_start = t->rr_start;
+	A.dims = (t->rr_start >= 0 ? 3 : 2) * c.max_bounce;
 	// uSpp % uTmpLife == 0 -> trace and store the primary hit; otherwise reuse it (pathtracer.glsl:113-127)
 	if (first % c.tmp_lifetime == 0 || !t->prim_valid || t->prim_block != block) {
 		float bx, by;
@@ -609,7 +624,7 @@ int run_batch(adypt_tracer *t, int first, int n, bool sum_mode)
 		t->prim_valid = true;
 		t->prim_block = block;
 	}
-	const int dims = 2 * c.max_bounce;
+	const int dims = A.dims;
 	k_sobol<<<(dims * n + 127) / 128, 128, 0, t->stream>>>(t->d_dirs, dims, first, n, t->d_sobol);
 	count_launch();
 	ADYPT_CUDA(cudaMemsetAsync(t->d_counts, 0, (size_t)(kCountSlots - 1) * sizeof(unsigned long long), t->stream));
@@ -701,6 +716,7 @@ int adypt_tracer_create(adypt_scene *scene, const adypt_pt_config *config, int32
 	DeviceGuard g(scene->device);
 	adypt_tracer *t = new adypt_tracer;
 	t->scene = scene;
+	t->device = scene->device;
 	t->cfg = *config;
 	t->width = width;
 	t->height = height;
@@ -756,9 +772,22 @@ int adypt_tracer_set_config(adypt_tracer *t, const adypt_pt_config *config)
 	return guarded([&]() -> int {
 	if (!t || !config) return fail(ADYPT_EINVAL, "tracer/config is NULL");
 	ADYPT_TRY(check_config(config));
+	if (t->rr_start >= 0 && 3 * config->max_bounce > sobol_max_dim())
+		return fail(ADYPT_ERANGE, "Russian roulette needs 3*maxBounce Sobol dimensions (<= 64)");
 	t->cfg = *config;
 	t->cam.tmin = config->ray_tmin; // update_config_args, OglPathTracer.cpp:216
 	t->prim_valid = false;
+	return ADYPT_OK;
+	});
+}
+
+int adypt_tracer_set_russian_roulette(adypt_tracer *t, int32_t start_bounce)
+{
+	return guarded([&]() -> int {
+	if (!t) return fail(ADYPT_EINVAL, "tracer is NULL");
+	if (start_bounce >= 0 && 3 * t->cfg.max_bounce > sobol_max_dim())
+		return fail(ADYPT_ERANGE, "Russian roulette needs 3*maxBounce Sobol dimensions (<= 64)");
+	t->rr_start = start_bounce < 0 ? -1 : start_bounce;
 	return ADYPT_OK;
 	});
 }

@@ -207,6 +207,7 @@ class RenderGroup:
         l.adypt_group_destroy.argtypes = [vp]
         l.adypt_group_set_camera.argtypes = [vp, vp, vp, vp]
         l.adypt_group_set_sun_visibility.argtypes = [vp, C.c_int32, vp]
+        l.adypt_group_set_russian_roulette.argtypes = [vp, C.c_int32]
         l.adypt_group_render.argtypes = [vp, C.c_int32]
         l.adypt_group_read.argtypes = [vp, vp, C.c_int32]
         l.adypt_group_save_exr.argtypes = [vp, C.c_char_p, C.c_int32]

@@ -318,9 +318,29 @@ def path_tracer_aux(A, torch, dist, rank, local_rank, world):
     dt = float(dt.item())
     s1 = tr.stats()
     seg = s1["segments"] - s0["segments"]
-    return {"workload": "C3: 1920x1080, 64 spp, maxBounce 5, mixed-material 1M-tri city, wavefront path tracer",
-            "path_samples_per_s": world * w * h * spp / dt, "path_segments_per_s": world * seg / dt, "segments_per_sample": seg / (w * h * spp),
-            "seconds": dt, "gpu_launches": s1["launches"] - s0["launches"], "scaling": "weak"}
+    out = {"workload": "C3: 1920x1080, 64 spp, maxBounce 5, mixed-material 1M-tri city, wavefront path tracer; no Russian roulette (the reference's pathtracer.glsl has none)",
+           "path_samples_per_s": world * w * h * spp / dt, "path_segments_per_s": world * seg / dt, "segments_per_sample": seg / (w * h * spp),
+           "seconds": dt, "gpu_launches": s1["launches"] - s0["launches"], "scaling": "weak"}
+    # BASELINE.json words configs[2] "4 bounces + Russian roulette": the same render with the opt-in roulette from bounce 1
+    tr.set_russian_roulette(1)
+    tr.primary(0)
+    tr.sample(16)
+    tr.sync()
+    tr.primary(0)
+    s0 = tr.stats()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    tr.sample(spp)
+    tr.sync()
+    dt2 = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=torch.device("cuda", local_rank))
+    if dist is not None:
+        dist.all_reduce(dt2, op=dist.ReduceOp.MAX)
+    dt2 = float(dt2.item())
+    seg2 = tr.stats()["segments"] - s0["segments"]
+    out["with_russian_roulette"] = {"start_bounce": 1, "path_samples_per_s": world * w * h * spp / dt2, "segments_per_sample": seg2 / (w * h * spp),
+                                    "seconds": dt2, "note": "opt-in extension (adypt_tracer_set_russian_roulette); unbiased, not the reference's image"}
+    return out
 
 
 _RESULT_FD = None

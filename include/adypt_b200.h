@@ -151,6 +151,13 @@ int adypt_tracer_get_bias(adypt_tracer *tracer, uint8_t *rg8);
  * (direction is normalised inside); the default, 0, is the reference's shipped behaviour. */
 int adypt_tracer_set_sun_visibility(adypt_tracer *tracer, int32_t enabled, const float direction[3]);
 
+/* Russian roulette, an OPT-IN extension (BASELINE.json's configs[2] asks for it; shaders/pathtracer.glsl has none, so
+ * the default -- start_bounce < 0 -- is the reference's behaviour). With start_bounce >= 0, after shading bounce
+ * b >= start_bounce a path survives with probability p = min(1, max(throughput.rgb)) and its throughput is divided
+ * by p; the draw is Sobol dimension 2*maxBounce + b shifted by the pixel's bias like the other draws (needs
+ * 3*maxBounce <= 64, else ADYPT_ERANGE). Unbiased: the expected image is unchanged. */
+int adypt_tracer_set_russian_roulette(adypt_tracer *tracer, int32_t start_bounce);
+
 /* OglPathTracer::SetCamera(const mat4& projection, const mat4& view, const vec3& position)
  * (OglPathTracer.cpp:27-32): column-major float[16]; the inverses are computed inside with glm::inverse's
  * arithmetic order. */
@@ -258,6 +265,7 @@ int adypt_group_create(adypt_host_scene *scene, const adypt_pt_config *config, i
 int adypt_group_destroy(adypt_group *group);
 int adypt_group_set_camera(adypt_group *group, const float projection[16], const float view[16], const float position[3]);
 int adypt_group_set_sun_visibility(adypt_group *group, int32_t enabled, const float direction[3]);
+int adypt_group_set_russian_roulette(adypt_group *group, int32_t start_bounce);
 int adypt_group_render(adypt_group *group, int32_t total_spp); /* samples [0, total_spp); blocks until the image is resolved */
 int adypt_group_read(adypt_group *group, float *out, int32_t channels);
 int adypt_group_save_exr(adypt_group *group, const char *filename, int32_t save_as_fp16);

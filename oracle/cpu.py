@@ -41,7 +41,7 @@ def lib():
         l.oracle_sobol_directions.argtypes = [C.c_uint32, vp]
         l.oracle_sobol_sequence.argtypes = [C.c_uint32, C.c_uint32, vp]
         l.oracle_sobol_at.argtypes = [C.c_uint32, C.c_uint32, vp]
-        l.oracle_pt_render.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, C.POINTER(PTConfig), vp, i32, i32, vp, vp, vp, i32, i32, i32, vp, vp, vp]
+        l.oracle_pt_render.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, C.POINTER(PTConfig), vp, i32, i32, vp, vp, vp, i32, i32, i32, vp, vp, vp, i32]
         l.oracle_primary_view.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, i32, i32, vp, vp]
         l.oracle_det_sincos.argtypes = [vp, u64, vp, vp]
         l.oracle_det_pow.argtypes = [vp, vp, u64, vp]
@@ -152,7 +152,7 @@ def _textures(textures):
 
 
 def pt_render(bvh, origin, inv_proj, inv_view, width, height, cfg: dict, bias_rg8, first_spp, n_spp,
-              out_rgba=None, primary_tmp=None, nthreads=0, sum_mode=False, textures=None, sun_visibility=None):
+              out_rgba=None, primary_tmp=None, nthreads=0, sum_mode=False, textures=None, sun_visibility=None, russian_roulette=None):
     """bvh: object with nodes/tri_indices/woop/tris/mats arrays. Returns (out_rgba, primary_tmp, counters)."""
     c = PTConfig(cfg["max_bounce"], cfg["subpixel"], cfg["tmp_lifetime"], cfg["ray_tmin"], cfg["clamp"],
                  (C.c_float * 3)(*cfg["sun"]))
@@ -170,7 +170,8 @@ def pt_render(bvh, origin, inv_proj, inv_view, width, height, cfg: dict, bias_rg
     nodes, ti, woop = _c(bvh.nodes, np.uint8), _c(bvh.tri_indices, np.int32), _c(bvh.woop, np.float32)
     tris, mats = _c(bvh.tris, np.uint8), _c(bvh.mats, np.uint8)
     rc = lib().oracle_pt_render(_p(nodes), _p(ti), _p(woop), _p(tris), _p(mats), _p(o), _p(ip), _p(iv), width, height,
-                                C.byref(c), _p(bias), first_spp, n_spp, _p(out_rgba), _p(primary_tmp), _p(cnt), nthreads, int(sum_mode), nt, tp, _p(twh), _p(sv))
+                                C.byref(c), _p(bias), first_spp, n_spp, _p(out_rgba), _p(primary_tmp), _p(cnt), nthreads, int(sum_mode), nt, tp, _p(twh), _p(sv),
+                                -1 if russian_roulette is None else int(russian_roulette))
     if rc != 0:
         raise RuntimeError("oracle_pt_render failed")
     return out_rgba, primary_tmp, dict(nodes=int(cnt[0]), tris=int(cnt[1]), max_stack=int(cnt[2]), hits=int(cnt[3]), segments=int(cnt[4]))

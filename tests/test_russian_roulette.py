@@ -1,0 +1,70 @@
+"""Russian roulette: an OPT-IN extension (BASELINE.json configs[2] names it; shaders/pathtracer.glsl has none, so it is
+off by default and every reference-parity test runs without it). Checked here: the estimator stays unbiased, it cuts
+traced segments, and the CUDA wavefront equals the oracle bit for bit with it on."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+W_, H_ = 64, 48
+CFG = dict(max_bounce=6, subpixel=4, tmp_lifetime=8, ray_tmin=1e-4, clamp=1e9, sun=(1.0, 0.9, 0.8))
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def cam_of(cpu, g):
+    cam = g.extra["cam"]
+    return cam, cpu.camera_matrices(float(cam[5]), float(cam[3]), float(cam[4]), W_, H_)
+
+
+def test_oracle_roulette_is_unbiased_and_cheaper(cpu):
+    g = load_golden("city12")
+    cam, m = cam_of(cpu, g)
+    bias = np.random.default_rng(1).integers(0, 256, size=(H_ * W_, 2), dtype=np.uint8)
+    spp = 128
+    ref_img, _, c0 = cpu.pt_render(g, cam[:3], m["inv_proj"], m["inv_view"], W_, H_, CFG, bias, 0, spp)
+    means = [ref_img[:, :3].mean()]
+    for start in (0, 2):
+        img, _, c = cpu.pt_render(g, cam[:3], m["inv_proj"], m["inv_view"], W_, H_, CFG, bias, 0, spp, russian_roulette=start)
+        assert c["segments"] < c0["segments"]
+        assert not np.array_equal(bits(img), bits(ref_img))
+        means.append(img[:, :3].mean())
+        # per-channel image means agree to ~1 % (unbiased estimator, 0.4 M samples; measured 0.2-0.3 %)
+        assert np.allclose(img[:, :3].mean(axis=0), ref_img[:, :3].mean(axis=0), rtol=0.01), (start, img[:, :3].mean(axis=0), ref_img[:, :3].mean(axis=0))
+    off, _, _ = cpu.pt_render(g, cam[:3], m["inv_proj"], m["inv_view"], W_, H_, CFG, bias, 0, 8, russian_roulette=None)
+    assert np.array_equal(bits(off), bits(cpu.pt_render(g, cam[:3], m["inv_proj"], m["inv_view"], W_, H_, CFG, bias, 0, 8)[0]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("start", [0, 1, 3])
+def test_gpu_roulette_equals_oracle(A, cpu, start):
+    g = load_golden("city12")
+    cam, m = cam_of(cpu, g)
+    sc = A.Scene(g.nodes, g.tri_indices, g.woop, g.tris, g.mats)
+    pc = A.PTConfig.make(max_bounce=CFG["max_bounce"], subpixel=CFG["subpixel"], tmp_lifetime=CFG["tmp_lifetime"], ray_tmin=CFG["ray_tmin"],
+                         clamp=CFG["clamp"], sun=CFG["sun"])
+    tr = A.Tracer(sc, pc, W_, H_, bias_seed=3)
+    tr.look(cam[:3], float(cam[3]), float(cam[4]), float(cam[5]))
+    tr.set_russian_roulette(start)
+    tr.sample(40)
+    exp, _, cnt = cpu.pt_render(g, cam[:3], m["inv_proj"], m["inv_view"], W_, H_, CFG, tr.get_bias(), 0, 40, russian_roulette=start)
+    assert np.array_equal(bits(tr.read(4).reshape(-1, 4)), bits(exp))
+    assert tr.stats()["segments"] == cnt["segments"]
+    # switching it off again restores the reference's image
+    tr.set_russian_roulette(None)
+    tr.trace(False, 0)
+    tr.sample(16)
+    off, _, _ = cpu.pt_render(g, cam[:3], m["inv_proj"], m["inv_view"], W_, H_, CFG, tr.get_bias(), 0, 16)
+    assert np.array_equal(bits(tr.read(4).reshape(-1, 4)), bits(off))
+
+
+@pytest.mark.gpu
+def test_gpu_roulette_needs_enough_sobol_dimensions(A):
+    g = load_golden("city12")
+    sc = A.Scene(g.nodes, g.tri_indices, g.woop, g.tris, g.mats)
+    tr = A.Tracer(sc, A.PTConfig.make(max_bounce=30), 8, 8, bias_seed=3)  # 2*30 <= 64 but 3*30 > 64
+    with pytest.raises(A.AdyptError) as e:
+        tr.set_russian_roulette(1)
+    assert e.value.code == -6
