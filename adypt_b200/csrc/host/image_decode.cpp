@@ -1,9 +1,10 @@
 // Texture file decoding for diffuse maps (map_Kd): the stand-in for stbi_load(filename, &w, &h, &n, 3) as
 // OglScene::load_texture calls it (src/Tracer/OglScene.cpp:12-43). Output: tightly packed RGB8, top row first.
-// Formats: PNG (all colour types and bit depths, Adam7 interlace; zlib does the inflate), JPEG (jpeg_decode.cpp)
-// and TGA (true-colour 24/32 bpp and 8-bit grey, raw or RLE, either origin). Conversions to 3 channels follow
+// Formats: PNG (all colour types and bit depths, Adam7 interlace; zlib does the inflate), JPEG (jpeg_decode.cpp),
+// BMP (uncompressed, 4/8-bit palette, 16/24/32-bit) and TGA (true-colour 24/32 bpp and 8-bit grey, raw or RLE,
+// either origin). Conversions to 3 channels follow
 // stb_image's rules (grey replicated, alpha dropped, 16-bit samples truncated to their high byte, 1/2/4-bit grey
-// scaled by 255/85/17). BMP/PSD/GIF/HDR are not decoded: such a texture fails to load, which the reference
+// scaled by 255/85/17). PSD/GIF/HDR/PNM are not decoded: such a texture fails to load, which the reference
 // handles by giving the material texture index -1 (OglScene.cpp:27-32).
 #include <zlib.h>
 #include <cstdint>
@@ -202,6 +203,138 @@ bool decode_tga(const std::vector<uint8_t> &f, DecodedImage *img)
 	return true;
 }
 
+
+// ---- BMP (stb_image.h:4920-5230 is the behaviour to match: BITMAPCOREHEADER / INFOHEADER / V3 (56) / V4 / V5 headers;
+// 4- and 8-bit palettes, 16-bit 5-5-5 or bit-field masks, 24-bit, 32-bit; bottom-up or top-down; 1-bit and RLE files
+// are rejected there, so they are here)
+struct ByteReader {
+	const uint8_t *p, *end;
+	int u8() { return p < end ? *p++ : 0; }
+	uint32_t u16() { const uint32_t a = (uint32_t)u8(); return a | ((uint32_t)u8() << 8); }
+	uint32_t u32() { const uint32_t a = u16(); return a | (u16() << 16); }
+	void skip(long n) { p = (n < 0 || n > end - p) ? (n < 0 ? p : end) : p + n; }
+};
+
+inline int top_bit(uint32_t z)
+{
+	int n = -1;
+	while (z) { ++n; z >>= 1; }
+	return n;
+}
+// a masked field moved so that its top bit lands on bit 7, then widened to 8 bits by repeating it
+inline int expand_field(int v, int shift, int bits)
+{
+	v = shift < 0 ? v << -shift : v >> shift;
+	int result = v;
+	for (int z = bits; z < 8; z += bits) result += v >> z;
+	return result;
+}
+
+bool decode_bmp(const std::vector<uint8_t> &f, DecodedImage *img)
+{
+	ByteReader r{f.data(), f.data() + f.size()};
+	if (r.u8() != 'B' || r.u8() != 'M') return false;
+	r.u32(); r.u16(); r.u16();
+	const long offset = (long)r.u32();
+	const long hsz = (long)r.u32();
+	if (hsz != 12 && hsz != 40 && hsz != 56 && hsz != 108 && hsz != 124) return false;
+	int32_t w, h;
+	if (hsz == 12) { w = (int32_t)r.u16(); h = (int32_t)r.u16(); }
+	else { w = (int32_t)r.u32(); h = (int32_t)r.u32(); }
+	if (r.u16() != 1) return false;
+	const int bpp = (int)r.u16();
+	if (bpp == 1) return false;
+	uint32_t mr = 0, mg = 0, mb = 0, ma = 0;
+	if (hsz != 12) {
+		const uint32_t compress = r.u32();
+		if (compress == 1 || compress == 2) return false; // RLE
+		for (int i = 0; i < 5; ++i) r.u32();
+		if (hsz == 40 || hsz == 56) {
+			if (hsz == 56) for (int i = 0; i < 4; ++i) r.u32();
+			if (bpp == 16 || bpp == 32) {
+				if (compress == 0) {
+					if (bpp == 32) { mr = 0xffu << 16; mg = 0xffu << 8; mb = 0xffu; ma = 0xffu << 24; }
+					else { mr = 31u << 10; mg = 31u << 5; mb = 31u; }
+				} else if (compress == 3) {
+					mr = r.u32(); mg = r.u32(); mb = r.u32();
+					if (mr == mg && mg == mb) return false;
+				} else
+					return false;
+			}
+		} else {
+			mr = r.u32(); mg = r.u32(); mb = r.u32(); ma = r.u32();
+			for (int i = 0; i < 13; ++i) r.u32();
+			if (hsz == 124) for (int i = 0; i < 4; ++i) r.u32();
+		}
+	}
+	const bool bottom_up = h > 0;
+	if (h < 0) h = -h;
+	if (w <= 0 || h <= 0 || (uint64_t)w * (uint64_t)h * 3u > 0x7fffffffu) return false;
+	long psize = 0;
+	if (hsz == 12) { if (bpp < 24) psize = (offset - 14 - 24) / 3; }
+	else if (bpp < 16) psize = (offset - 14 - hsz) >> 2;
+	img->width = w;
+	img->height = h;
+	img->rgb.assign((size_t)w * h * 3, 0);
+	uint8_t *out = img->rgb.data();
+	size_t z = 0;
+	if (bpp < 16) {
+		if (psize == 0 || psize > 256 || (bpp != 4 && bpp != 8)) return false;
+		uint8_t pal[256][3];
+		memset(pal, 0, sizeof(pal));
+		for (long i = 0; i < psize; ++i) {
+			pal[i][2] = (uint8_t)r.u8(); pal[i][1] = (uint8_t)r.u8(); pal[i][0] = (uint8_t)r.u8();
+			if (hsz != 12) r.u8();
+		}
+		r.skip(offset - 14 - hsz - psize * (hsz == 12 ? 3 : 4));
+		const int row_bytes = bpp == 4 ? (w + 1) >> 1 : w, pad = (-row_bytes) & 3;
+		for (int j = 0; j < h; ++j) {
+			for (int i = 0; i < w; i += 2) {
+				int v = r.u8(), v2 = 0;
+				if (bpp == 4) { v2 = v & 15; v >>= 4; }
+				out[z++] = pal[v][0]; out[z++] = pal[v][1]; out[z++] = pal[v][2];
+				if (i + 1 == w) break;
+				v = bpp == 8 ? r.u8() : v2;
+				out[z++] = pal[v][0]; out[z++] = pal[v][1]; out[z++] = pal[v][2];
+			}
+			r.skip(pad);
+		}
+	} else {
+		if (bpp != 16 && bpp != 24 && bpp != 32) return false;
+		r.skip(offset - 14 - hsz);
+		const int row_bytes = bpp == 24 ? 3 * w : bpp == 16 ? 2 * w : 0, pad = (-row_bytes) & 3;
+		const bool plain = bpp == 24 || (bpp == 32 && mb == 0xffu && mg == 0xff00u && mr == 0x00ff0000u && ma == 0xff000000u);
+		int rs = 0, gs = 0, bs = 0, rc = 0, gc = 0, bc = 0;
+		if (!plain) {
+			if (!mr || !mg || !mb) return false;
+			rs = top_bit(mr) - 7; rc = __builtin_popcount(mr);
+			gs = top_bit(mg) - 7; gc = __builtin_popcount(mg);
+			bs = top_bit(mb) - 7; bc = __builtin_popcount(mb);
+		}
+		for (int j = 0; j < h; ++j) {
+			for (int i = 0; i < w; ++i) {
+				if (plain) {
+					out[z + 2] = (uint8_t)r.u8(); out[z + 1] = (uint8_t)r.u8(); out[z] = (uint8_t)r.u8();
+					if (bpp == 32) r.u8();
+				} else {
+					const uint32_t v = bpp == 16 ? r.u16() : r.u32();
+					out[z] = (uint8_t)(expand_field((int)(v & mr), rs, rc) & 255);
+					out[z + 1] = (uint8_t)(expand_field((int)(v & mg), gs, gc) & 255);
+					out[z + 2] = (uint8_t)(expand_field((int)(v & mb), bs, bc) & 255);
+				}
+				z += 3;
+			}
+			r.skip(pad);
+		}
+	}
+	if (bottom_up)
+		for (int j = 0; j < h / 2; ++j) {
+			uint8_t *a = out + (size_t)j * w * 3, *b = out + (size_t)(h - 1 - j) * w * 3;
+			for (int i = 0; i < w * 3; ++i) { const uint8_t t = a[i]; a[i] = b[i]; b[i] = t; }
+		}
+	return true;
+}
+
 } // namespace
 
 bool decode_image_file(const char *path, DecodedImage *img)
@@ -209,6 +342,7 @@ bool decode_image_file(const char *path, DecodedImage *img)
 	std::vector<uint8_t> file;
 	if (!read_file(path, &file)) return false;
 	if (decode_png(file, img)) return true;
+	if (file.size() > 2 && file[0] == 'B' && file[1] == 'M') return decode_bmp(file, img);
 	if (decode_jpeg(file, img)) return true;
 	const size_t n = strlen(path);
 	if (n > 4 && (!strcmp(path + n - 4, ".tga") || !strcmp(path + n - 4, ".TGA"))) return decode_tga(file, img); // TGA has no magic number

@@ -37,7 +37,7 @@ def make_images(d):
     save("rgba.tga", PIL.fromarray(rgba))
     save("grey.tga", PIL.fromarray(grey))
     save("photo.jpg", PIL.fromarray(rgb))
-    save("unsupported.bmp", PIL.fromarray(rgb))
+    save("unsupported.gif", PIL.fromarray(rgb))
     return files
 
 
@@ -53,14 +53,90 @@ def test_decoders_match_stb_image(refmod, tmp_path):
     for name, path in files.items():
         exp = refmod.load_image_rgb8(path)  # stbi_load(path, ..., 3)
         assert exp is not None
-        if name.endswith(".bmp"):
-            continue  # BMP is not decoded here: the material gets texture index -1 (checked below)
+        if name.endswith(".gif"):
+            continue  # GIF is not decoded here: the material gets texture index -1 (checked below)
         got = next(decoded)
         assert got.shape == exp.shape, name
         assert np.array_equal(got, exp), name
     assert (ok, bad) == (len(files) - 1, 1)
     dtex = hs.mats[:, 0:4].copy().view(np.int32).ravel()
     assert dtex.tolist() == list(range(len(files) - 1)) + [-1]  # renumbered among the loaded ones; failure -> -1
+
+
+def bmp_cases(d):
+    """BMP files covering stb_image's branches: 24-bit, 8-bit palette / grey, 32-bit, 4-bit palette, 16-bit 5-5-5 and
+    5-6-5 bit fields, 32-bit bit fields, top-down rows, the 12-byte OS/2 header, the 56-byte V3 header; 1-bit and RLE
+    files, which stb_image refuses."""
+    import struct
+    rng = np.random.default_rng(21)
+    rgb = rng.integers(0, 256, size=(13, 19, 3), dtype=np.uint8)
+    out = {}
+
+    def pil(name, img, **kw):
+        out[name] = os.path.join(d, name)
+        img.save(out[name], "BMP", **kw)
+
+    pil("rgb24.bmp", PIL.fromarray(rgb))
+    pil("pal8.bmp", PIL.fromarray(rgb).convert("P", palette=PIL.ADAPTIVE, colors=200))
+    pil("grey8.bmp", PIL.fromarray(rgb[..., 0]))
+    pil("rgba32.bmp", PIL.fromarray(np.concatenate([rgb, rgb[..., :1]], axis=2), "RGBA"))
+    pil("mono1.bmp", PIL.fromarray(rgb[..., 0] > 128))
+
+    def raw(name, w, h, bpp, rows, palette=b"", compress=0, masks=b"", hsz=40, top_down=False):
+        """rows: list of bytes objects, bottom row first unless top_down; each already padded to 4 bytes."""
+        body = b"".join(rows)
+        if hsz == 12:
+            hdr = struct.pack("<IHHHH", 12, w, h, 1, bpp)
+        else:
+            hdr = struct.pack("<IiiHHIIiiII", hsz, w, -h if top_down else h, 1, bpp, compress, len(body), 2835, 2835, 0, 0) + masks
+            hdr += b"\0" * (hsz - len(hdr)) if hsz > len(hdr) else b""
+        off = 14 + len(hdr) + len(palette)
+        out[name] = os.path.join(d, name)
+        open(out[name], "wb").write(b"BM" + struct.pack("<IHHI", off + len(body), 0, 0, off) + hdr + palette + body)
+
+    def pad4(b):
+        return b + b"\0" * ((-len(b)) & 3)
+
+    w, h = 19, 13
+    idx = rng.integers(0, 16, size=(h, w), dtype=np.uint8)
+    pal16 = rng.integers(0, 256, size=(16, 4), dtype=np.uint8).tobytes()
+    rows4 = [pad4(bytes((int(r[i]) << 4) | (int(r[i + 1]) if i + 1 < w else 0) for i in range(0, w, 2))) for r in idx[::-1]]
+    raw("pal4.bmp", w, h, 4, rows4, palette=pal16)
+    v555 = rng.integers(0, 1 << 15, size=(h, w), dtype=np.uint16)
+    raw("rgb555.bmp", w, h, 16, [pad4(r.astype("<u2").tobytes()) for r in v555[::-1]])
+    v565 = rng.integers(0, 1 << 16, size=(h, w), dtype=np.uint16)
+    raw("rgb565.bmp", w, h, 16, [pad4(r.astype("<u2").tobytes()) for r in v565[::-1]], compress=3, masks=struct.pack("<III", 0xF800, 0x07E0, 0x001F), hsz=52 + 4)
+    v32 = rng.integers(0, 1 << 32, size=(h, w), dtype=np.uint32)
+    raw("bitfields32.bmp", w, h, 32, [r.astype("<u4").tobytes() for r in v32[::-1]], compress=3, masks=struct.pack("<IIII", 0x3FF00000, 0x000FFC00, 0x000003FF, 0xC0000000), hsz=108)
+    raw("topdown24.bmp", w, h, 24, [pad4(r[:, ::-1].tobytes()) for r in rgb], top_down=True)
+    raw("os2_24.bmp", w, h, 24, [pad4(r[:, ::-1].tobytes()) for r in rgb[::-1]], hsz=12)
+    pal3 = rng.integers(0, 256, size=(256, 3), dtype=np.uint8).tobytes()
+    # stb_image sizes an OS/2 palette as (offset - 14 - 24) / 3 = 252 entries here, not 256 (it subtracts 24 for the
+    # 12-byte header); entries 252..255 stay uninitialised there, so the fixture keeps to the defined ones
+    idx8 = rng.integers(0, 252, size=(h, w), dtype=np.uint8)
+    raw("os2_pal8.bmp", w, h, 8, [pad4(r.tobytes()) for r in idx8[::-1]], palette=pal3, hsz=12)
+    raw("rle8.bmp", w, h, 8, [pad4(r.tobytes()) for r in idx8[::-1]], palette=rng.integers(0, 256, size=(256, 4), dtype=np.uint8).tobytes(), compress=1)
+    return out
+
+
+def test_bmp_decoder_matches_stb_image(refmod, tmp_path):
+    files = bmp_cases(str(tmp_path))
+    from adypt_b200 import host as H
+    refused = 0
+    for name, path in files.items():
+        exp = refmod.load_image_rgb8(path)
+        (tmp_path / "b.mtl").write_text(f"newmtl m0\nKd 1 1 1\nillum 1\nmap_Kd {name}\n")
+        (tmp_path / "b.obj").write_text("mtllib b.mtl\nv 0 0 0\nv 1 0 0\nv 0 1 0\nv 3 0 0\nv 4 0 0\nv 3 1 0\nusemtl m0\nf 1 2 3\nf 4 5 6\n")
+        hs = H.HostScene.from_obj(str(tmp_path / "b.obj"))
+        ok, bad = hs.load_textures()
+        if exp is None:  # stb_image refuses it (1-bit, RLE): so must we
+            assert (ok, bad) == (0, 1), name
+            refused += 1
+            continue
+        assert (ok, bad) == (1, 0), name
+        assert hs.textures[0].shape == exp.shape, (name, hs.textures[0].shape, exp.shape)
+        assert np.array_equal(hs.textures[0], exp), name
+    assert refused == 2 and len(files) - refused >= 11
 
 
 def jpeg_cases(d):
