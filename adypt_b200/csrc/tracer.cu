@@ -302,7 +302,7 @@ __device__ __forceinline__ unsigned long long queue_append(bool keep, unsigned l
 }
 
 // bounce 0 for every (sample, pixel) of the batch: reads the cached primary hit
-__global__ void __launch_bounds__(256) k_shade_primary(ShadeBuffers B, PTArgs A, CameraArgs cam)
+__global__ void __launch_bounds__(256, 4) k_shade_primary(ShadeBuffers B, PTArgs A, CameraArgs cam)
 {
 	const unsigned long long npix = (unsigned long long)A.width * (unsigned long long)A.height;
 	const unsigned long long total = npix * (unsigned long long)A.n_samples;
@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(256) k_shade_primary(ShadeBuffers B, PTArgs A,
 }
 
 // bounce b >= 1 over the current queue
-__global__ void __launch_bounds__(256) k_shade_bounce(ShadeBuffers B, PTArgs A, int b, float tmin)
+__global__ void __launch_bounds__(256, 4) k_shade_bounce(ShadeBuffers B, PTArgs A, int b, float tmin)
 {
 	const unsigned long long npix = (unsigned long long)A.width * (unsigned long long)A.height;
 	const unsigned long long total = *B.in_count;
@@ -353,8 +353,34 @@ __global__ void __launch_bounds__(256) k_shade_bounce(ShadeBuffers B, PTArgs A, 
 	const unsigned long long rounds = (total + stride - 1) / stride;
 	const int dims = A.dims;
 	if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(B.segments, total);
+	// Each block regroups its 256 queue entries by shading branch before shading them, so that a warp mostly runs ONE
+	// of miss / diffuse / glossy / mirror / glass instead of all of them one after the other (measured 13.4 of 32
+	// lanes active without this). Which lane shades which entry never reaches the image: every path writes its own
+	// slots, and the next queue's order is free.
+	__shared__ unsigned s_class_count[8];
+	__shared__ unsigned short s_order[256];
 	for (unsigned long long r = 0; r < rounds; ++r) {
-		const unsigned long long q = r * stride + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+		const unsigned long long q0 = r * stride + (unsigned long long)blockIdx.x * blockDim.x;
+		if (threadIdx.x < 8) s_class_count[threadIdx.x] = 0u;
+		__syncthreads();
+		unsigned cls = 7u, rank = 0u; // 7 = past the end of the queue
+		if (q0 + threadIdx.x < total) {
+			const int32_t tri_idx = B.in_tri[q0 + threadIdx.x];
+			if (tri_idx == -1) cls = 0u;
+			else {
+				const int32_t matid = *(const int32_t *)(B.tris + (size_t)tri_idx * 100u + 96u);
+				const int32_t illum = B.mats[matid].illum;
+				cls = illum == 1 ? 1u : illum == 2 ? (B.mats[matid].shininess * 0.01f > 0.3f ? 2u : 1u) : (illum >= 3 && illum <= 5) ? 3u
+				      : (illum == 6 || illum == 7) ? 4u : 5u;
+			}
+		}
+		rank = atomicAdd(&s_class_count[cls], 1u);
+		__syncthreads();
+		unsigned before = 0u;
+		for (unsigned c = 0; c < cls; ++c) before += s_class_count[c];
+		s_order[before + rank] = (unsigned short)threadIdx.x;
+		__syncthreads();
+		const unsigned long long q = q0 + s_order[threadIdx.x];
 		bool keep = false, conn = false;
 		V3 origin = v3(0, 0, 0), dir = v3(0, 0, 0), color = v3(0, 0, 0), ret = v3(0, 0, 0);
 		unsigned id = 0;

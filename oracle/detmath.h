@@ -116,6 +116,7 @@ ORACLE_INL float pow(float x, float y)
 	if (x != x || y != y || x < 0.0f) return (float)u64_as_double(0x7ff8000000000000ull);
 	if (x == 0.0f) return y > 0.0f ? 0.0f : (y == 0.0f ? 1.0f : (float)u64_as_double(0x7ff0000000000000ull));
 	if (x > 3.40282346638528859812e+38f) return y > 0.0f ? x : (y == 0.0f ? 1.0f : 0.0f);
+	if (y == 1.0f) return x; // what the general path returns too (|error| < 2^-45 relative, x is a float): skips ~150 FP64 operations
 	return (float)exp2_any((double)y * log2_pos((double)x));
 }
 
