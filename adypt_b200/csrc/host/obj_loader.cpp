@@ -217,38 +217,78 @@ struct MtlEntry {
 	float dissolve = 1.0f, shininess = 1.0f, ior = 1.0f;
 };
 
-std::string rstrip(std::string s)
+// Lines as tinyobj's safeGetline cuts them (tiny_obj_loader.h:419-451): '\n', "\r\n" and a lone '\r' all end a line
+struct LineReader {
+	std::string data;
+	size_t pos = 0;
+	bool open(const std::string &path)
+	{
+		std::ifstream in(path.c_str(), std::ios::binary);
+		if (!in) return false;
+		std::ostringstream ss;
+		ss << in.rdbuf();
+		data = ss.str();
+		return true;
+	}
+	bool next(std::string *line)
+	{
+		if (pos >= data.size()) return false;
+		size_t e = pos;
+		while (e < data.size() && data[e] != '\n' && data[e] != '\r') ++e;
+		line->assign(data, pos, e - pos);
+		if (e < data.size()) e += (data[e] == '\r' && e + 1 < data.size() && data[e + 1] == '\n') ? 2 : 1;
+		pos = e;
+		return true;
+	}
+};
+
+// what follows a texture keyword (tiny_obj_loader.h:861-962): options are consumed token by token -- a numeric option
+// swallows as many tokens as it has parameters, whatever they are -- and the first thing that is not an option is
+// the file name, taken to the end of the line
+bool texture_name(const char *tok, std::string *name)
 {
-	const size_t e = s.find_last_not_of(" \t\r\n");
-	return e == std::string::npos ? std::string() : s.substr(0, e + 1);
+	auto word = [&](const char *w, size_t n) { return strncmp(tok, w, n) == 0 && is_space(tok[n]); };
+	auto skip_token = [&]() { tok += strspn(tok, " \t"); tok += strcspn(tok, " \t\r"); };
+	while (*tok != '\0' && *tok != '\r' && *tok != '\n') {
+		tok += strspn(tok, " \t");
+		if (word("-blendu", 7) || word("-blendv", 7)) { tok += 8; skip_token(); }
+		else if (word("-clamp", 6) || word("-boost", 6)) { tok += 7; skip_token(); }
+		else if (word("-bm", 3)) { tok += 4; skip_token(); }
+		else if (word("-o", 2) || word("-s", 2) || word("-t", 2)) { tok += 3; skip_token(); skip_token(); skip_token(); }
+		else if (word("-type", 5)) { tok += 5; skip_token(); }
+		else if (word("-imfchan", 8)) { tok += 9; skip_token(); }
+		else if (word("-mm", 3)) { tok += 4; skip_token(); skip_token(); }
+		else {
+			*name = tok;
+			return true;
+		}
+	}
+	return false;
 }
 
-void load_mtl(const std::string &path, std::map<std::string, int> *index, std::vector<MtlEntry> *mats)
+// LoadMtl + MaterialFileReader (tiny_obj_loader.h:1273-1656, 1659-1692). false = the file cannot be opened.
+bool load_mtl(const std::string &path, std::map<std::string, int> *index, std::vector<MtlEntry> *mats)
 {
-	std::ifstream in(path);
-	if (!in.is_open()) return; // tinyobj warns and carries on; faces then get material id -1
-	MtlEntry cur;
-	bool open = false, has_d = false;
-	std::string line;
+	LineReader in;
+	if (!in.open(path)) return false; // tinyobj warns and tries the next name; with none left faces get material id -1
+	MtlEntry cur; // "create a default material anyway": what precedes the first newmtl lands in a nameless one
+	bool has_d = false;
 	auto flush = [&]() {
-		if (open) {
-			index->insert(std::make_pair(cur.name, (int)mats->size()));
-			mats->push_back(cur);
-		}
+		index->insert(std::make_pair(cur.name, (int)mats->size())); // the first definition of a name keeps it
+		mats->push_back(cur);
 	};
-	while (std::getline(in, line)) {
-		line = rstrip(line);
+	std::string line;
+	while (in.next(&line)) {
+		const size_t e = line.find_last_not_of(" \t"); // the MTL reader trims trailing blanks (the OBJ reader does not)
+		line = e == std::string::npos ? std::string() : line.substr(0, e + 1);
 		const char *tok = line.c_str();
 		tok += strspn(tok, " \t");
 		if (*tok == '\0' || *tok == '#') continue;
 		if (strncmp(tok, "newmtl", 6) == 0 && is_space(tok[6])) {
-			flush();
+			if (!cur.name.empty()) flush();
 			cur = MtlEntry();
 			has_d = false;
-			open = true;
-			tok += 7;
-			tok += strspn(tok, " \t");
-			cur.name = tok;
+			cur.name = tok + 7; // verbatim, inner blanks included
 			continue;
 		}
 		if (tok[0] == 'K' && tok[1] == 'd' && is_space(tok[2])) { tok += 2; for (int i = 0; i < 3; ++i) cur.kd[i] = next_real(&tok); continue; }
@@ -260,15 +300,12 @@ void load_mtl(const std::string &path, std::map<std::string, int> *index, std::v
 		if (tok[0] == 'd' && is_space(tok[1])) { tok += 1; cur.dissolve = next_real(&tok); has_d = true; continue; }
 		if (tok[0] == 'T' && tok[1] == 'r' && is_space(tok[2])) { tok += 2; if (!has_d) cur.dissolve = 1.0f - next_real(&tok); continue; }
 		if (strncmp(tok, "map_Kd", 6) == 0 && is_space(tok[6])) {
-			tok += 7;
-			// texture options (-o, -s, -bm ...) are skipped; the file name is the last token
-			std::string rest = rstrip(tok);
-			const size_t sp = rest.find_last_of(" \t");
-			cur.diffuse_tex = (rest.find('-') == 0 && sp != std::string::npos) ? rest.substr(sp + 1) : rest.substr(rest.find_first_not_of(" \t") == std::string::npos ? 0 : rest.find_first_not_of(" \t"));
+			texture_name(tok + 7, &cur.diffuse_tex);
 			continue;
 		}
 	}
-	flush();
+	flush(); // "flush last material": always, even for an empty file
+	return true;
 }
 
 } // namespace
@@ -282,8 +319,8 @@ std::string load_obj(const char *path, adypt_host_scene *out)
 		const size_t cut = base.find_last_of("/\\");
 		base = cut == std::string::npos ? std::string() : base.substr(0, cut + 1);
 	}
-	std::ifstream in(path);
-	if (!in.is_open()) return std::string("[SCENE]Failed to load ") + path;
+	LineReader in;
+	if (!in.open(path)) return std::string("[SCENE]Failed to load ") + path;
 
 	std::vector<float> v, vn, vt;
 	std::vector<MtlEntry> mtls;
@@ -293,8 +330,7 @@ std::string load_obj(const char *path, adypt_host_scene *out)
 	out->tris.clear();
 
 	std::string line;
-	while (std::getline(in, line)) {
-		if (!line.empty() && line.back() == '\r') line.pop_back();
+	while (in.next(&line)) {
 		const char *tok = line.c_str();
 		tok += strspn(tok, " \t");
 		if (*tok == '\0' || *tok == '#') continue;
@@ -350,18 +386,17 @@ std::string load_obj(const char *path, adypt_host_scene *out)
 			continue;
 		}
 		if (strncmp(tok, "usemtl", 6) == 0 && is_space(tok[6])) {
-			tok += 7;
-			tok += strspn(tok, " \t");
-			const std::string name = rstrip(tok);
-			const auto it = mtl_index.find(name);
+			// the name is everything after "usemtl " (tiny_obj_loader.h:1877-1901): extra or trailing blanks are part of it
+			const auto it = mtl_index.find(std::string(tok + 7));
 			material = it == mtl_index.end() ? -1 : it->second;
 			continue;
 		}
 		if (strncmp(tok, "mtllib", 6) == 0 && is_space(tok[6])) {
-			tok += 7;
-			std::istringstream names(rstrip(tok));
+			// names are separated by single spaces; they are tried in turn until ONE file opens (tiny_obj_loader.h:1904-1943)
+			std::istringstream names(std::string(tok + 7));
 			std::string n;
-			while (names >> n) load_mtl(base + n, &mtl_index, &mtls);
+			while (std::getline(names, n, ' '))
+				if (load_mtl(base + n, &mtl_index, &mtls)) break;
 			continue;
 		}
 		// g / o / s and everything else do not change triangle order or content
