@@ -85,8 +85,11 @@ struct Parser {
 				if (!use_double) {
 					if (i > 1844674407370955161ull || (i == 1844674407370955161ull && *p > '5')) { use_double = true; d = (double)i; }
 				}
-				if (use_double) d = d * 10.0 + (*p - '0');
-				else i = i * 10 + (uint64_t)(*p - '0');
+				if (use_double) {
+					if (d >= 1.7976931348623157e307) { ok = false; return; } // rapidjson: kParseErrorNumberTooBig (reader.h:1232-1236)
+					d = d * 10.0 + (*p - '0');
+				} else
+					i = i * 10 + (uint64_t)(*p - '0');
 				++digits;
 				++p;
 			}
@@ -123,9 +126,19 @@ struct Parser {
 			bool eneg = false;
 			if (p < end && (*p == '+' || *p == '-')) eneg = *p++ == '-';
 			if (p >= end || *p < '0' || *p > '9') { ok = false; return; }
-			while (p < end && *p >= '0' && *p <= '9') {
-				if (exp < 100000) exp = exp * 10 + (*p - '0');
-				++p;
+			exp = *p++ - '0';
+			if (eneg) {
+				while (p < end && *p >= '0' && *p <= '9') {
+					exp = exp * 10 + (*p++ - '0');
+					if (exp >= 214748364)
+						while (p < end && *p >= '0' && *p <= '9') ++p;
+				}
+			} else {
+				const int max_exp = 308 - exp_adj; // reader.h:1313-1319: a larger exponent is kParseErrorNumberTooBig
+				while (p < end && *p >= '0' && *p <= '9') {
+					exp = exp * 10 + (*p++ - '0');
+					if (exp > max_exp) { ok = false; return; }
+				}
 			}
 			if (eneg) exp = -exp;
 		}

@@ -123,3 +123,76 @@ def test_defaults_match_instanceconfig_hpp():
     assert c.cam.fov == 45.0 and c.cam.speed == 1.0
     with pytest.raises(AdyptError):
         host.InstanceConfig.load("/nonexistent/x.config")
+
+
+@pytest.mark.parametrize("number", ["1e400", "1e309", "12345678901234567890123456789e290", "1" + "0" * 309, "0.1e310", "1e308", "0.001e311", "1e-400", "1e-99999999999"])
+def test_numbers_too_big_for_a_double_reject_the_whole_file(refmod, tmp_path, number):
+    """rapidjson's parser gives up on a number whose exponent or digit string overflows a double (reader.h:1232-1236,
+    1313-1319) -- wherever it stands, even under a key nobody reads -- while huge NEGATIVE exponents quietly become 0."""
+    txt = json.dumps(GOOD)[:-1] + ', "ignored": ' + number + "}"
+    p = write(tmp_path, txt)
+    r = refmod.config_load(p)
+    if r is None:
+        with pytest.raises(AdyptError):
+            host.InstanceConfig.load(p)
+    else:
+        assert fields(host.InstanceConfig.load(p)) == ref_fields(r)
+
+
+def test_config_text_fuzz_matches_reference(refmod, tmp_path):
+    """300 random re-spellings of a valid instance file -- whitespace, key order, number formats (some making an int
+    a float, which InstanceConfig refuses, or overflowing), escapes, duplicate and foreign keys, trailing junk, BOM,
+    comments: both readers must agree on accept / reject and on every value."""
+    import random
+    rnd = random.Random(17)
+
+    def fnum(v):
+        if isinstance(v, int):
+            return rnd.choice([str(v)] * 20 + [f"{v}.0", f"{v}e0", "-0" if v == 0 else str(v)])
+        alts = [repr(float(v)), f"{v:.3f}", f"{v:e}", f"{v:E}", f"{v:.1f}", f"{int(v)}.5e-1", "-0.0", repr(float(v)), repr(float(v))]
+        if rnd.random() < 0.03:
+            alts.append(rnd.choice(["1e400", str(int(v)), "1e-400"]))
+        return rnd.choice(alts)
+
+    ws = lambda: rnd.choice(["", " ", "  ", "\n", "\t", "\r\n", " \n "])
+
+    def emit(o):
+        if isinstance(o, dict):
+            items = list(o.items())
+            if rnd.random() < 0.5:
+                rnd.shuffle(items)
+            parts = []
+            for k, v in items:
+                parts.append(ws() + json.dumps(k) + ws() + ":" + ws() + emit(v))
+                if rnd.random() < 0.03:
+                    parts.append(ws() + json.dumps(k) + ":" + emit(v))
+                if rnd.random() < 0.08:
+                    parts.append(ws() + '"extra%d":' % rnd.randrange(9) + rnd.choice(["1", "null", "[1,2]", '{"a":1}', '"x"', "true"]))
+            return "{" + ",".join(parts) + ws() + "}"
+        if isinstance(o, list):
+            return "[" + ",".join(ws() + emit(v) + ws() for v in o) + "]"
+        if isinstance(o, str):
+            return rnd.choice([json.dumps(o), json.dumps(o).replace("/", "\\/"), json.dumps(o + "é"), json.dumps(o + "é", ensure_ascii=False), '"a\\u0041\\n"'])
+        return fnum(o)
+
+    accepted = 0
+    for t in range(300):
+        txt = emit(json.loads(json.dumps(GOOD)))
+        if rnd.random() < 0.1:
+            txt += rnd.choice([" ", "\n", "x", ",", "}"])
+        if rnd.random() < 0.05:
+            txt = "﻿" + txt
+        if rnd.random() < 0.05:
+            txt = "// c\n" + txt
+        p = tmp_path / "f.config"
+        p.write_text(txt, encoding="utf-8", newline="")
+        r = refmod.config_load(str(p))
+        try:
+            o = host.InstanceConfig.load(str(p))
+        except AdyptError:
+            o = None
+        assert (r is None) == (o is None), (t, txt)
+        if r is not None:
+            accepted += 1
+            assert fields(o) == ref_fields(r), (t, txt)
+    assert accepted >= 60
