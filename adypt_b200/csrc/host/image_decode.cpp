@@ -1,8 +1,8 @@
 // Texture file decoding for diffuse maps (map_Kd): the stand-in for stbi_load(filename, &w, &h, &n, 3) as
 // OglScene::load_texture calls it (src/Tracer/OglScene.cpp:12-43). Output: tightly packed RGB8, top row first.
 // Formats: PNG (all colour types and bit depths, Adam7 interlace; zlib does the inflate), JPEG (jpeg_decode.cpp),
-// BMP (uncompressed, 4/8-bit palette, 16/24/32-bit) and TGA (true-colour 24/32 bpp and 8-bit grey, raw or RLE,
-// either origin). Conversions to 3 channels follow
+// BMP (uncompressed, 4/8-bit palette, 16/24/32-bit) and TGA (true-colour, 15/16-bit, grey, grey+alpha,
+// colour-mapped; raw or RLE, either origin). Conversions to 3 channels follow
 // stb_image's rules (grey replicated, alpha dropped, 16-bit samples truncated to their high byte, 1/2/4-bit grey
 // scaled by 255/85/17). PSD/GIF/HDR/PNM are not decoded: such a texture fails to load, which the reference
 // handles by giving the material texture index -1 (OglScene.cpp:27-32).
@@ -157,52 +157,100 @@ bool decode_png(const std::vector<uint8_t> &file, DecodedImage *img)
 	return true;
 }
 
+// ---- TGA (stb_image.h:5230-5560 is the behaviour to match): true-colour 24/32 bpp, 15/16-bit 5-5-5, 8-bit grey,
+// 16-bit grey+alpha, colour-mapped with 8- or 16-bit indices and any of those entry formats; raw or RLE; bottom-up
+// unless descriptor bit 5 is set (bit 4, right-to-left, is ignored there, so it is here). Reads past the end of the
+// file yield zeros, as stb_image's byte reader does.
 bool decode_tga(const std::vector<uint8_t> &f, DecodedImage *img)
 {
-	if (f.size() < 18) return false;
-	const int id_len = f[0], cmap_type = f[1], type = f[2];
-	const int w = f[12] | (f[13] << 8), h = f[14] | (f[15] << 8), bpp = f[16], desc = f[17];
-	const bool rle = type == 10 || type == 11, grey = type == 3 || type == 11;
-	if (cmap_type != 0 || !(type == 2 || type == 3 || type == 10 || type == 11)) return false; // colour-mapped TGAs not handled
-	if (w <= 0 || h <= 0 || !((grey && bpp == 8) || (!grey && (bpp == 24 || bpp == 32)))) return false;
-	const int nb = bpp / 8;
-	size_t pos = 18 + (size_t)id_len;
-	img->width = w;
-	img->height = h;
-	img->rgb.assign((size_t)w * h * 3, 0);
+	size_t pos = 0;
+	auto u8 = [&]() -> int { return pos < f.size() ? f[pos++] : 0; };
+	auto u16 = [&]() -> int { const int a = u8(); return a | (u8() << 8); };
+	const int id_len = u8(), indexed = u8();
+	int type = u8();
+	const int pal_start = u16(), pal_len = u16(), pal_bits = u8();
+	u16(); u16(); // x / y origin
+	const int w = u16(), h = u16(), bpp = u8(), desc = u8();
+	// the acceptance test (stbi__tga_test)
+	if (indexed > 1) return false;
+	if (indexed) {
+		if (type != 1 && type != 9) return false;
+		if (pal_bits != 8 && pal_bits != 15 && pal_bits != 16 && pal_bits != 24 && pal_bits != 32) return false;
+		if (bpp != 8 && bpp != 16) return false;
+	} else if (type != 2 && type != 3 && type != 10 && type != 11)
+		return false;
+	if (w < 1 || h < 1) return false;
+	if (bpp != 8 && bpp != 15 && bpp != 16 && bpp != 24 && bpp != 32) return false;
+	const bool rle = type >= 8;
+	if (rle) type -= 8;
+	// bytes per decoded pixel: 1 grey, 2 grey+alpha, 3 rgb (15/16-bit sources are expanded to 3), 4 rgba
+	const int bits = indexed ? pal_bits : bpp;
+	bool rgb16 = false;
+	int comp;
+	if (bits == 8) comp = 1;
+	else if (bits == 16 && !indexed && type == 3) comp = 2;
+	else if (bits == 15 || bits == 16) { comp = 3; rgb16 = true; }
+	else comp = bits / 8;
+	if ((uint64_t)w * (uint64_t)h * 4u > 0x7fffffffu) return false;
+	auto read_rgb16 = [&](uint8_t *out) {
+		const int px = u16();
+		out[0] = (uint8_t)((((px >> 10) & 31) * 255) / 31);
+		out[1] = (uint8_t)((((px >> 5) & 31) * 255) / 31);
+		out[2] = (uint8_t)(((px & 31) * 255) / 31);
+	};
+	pos += (size_t)id_len;
+	std::vector<uint8_t> palette;
+	if (indexed) {
+		pos += (size_t)pal_start; // sic: the first-entry index is skipped as a byte count
+		palette.assign((size_t)pal_len * comp + 4, 0);
+		for (int i = 0; i < pal_len; ++i) {
+			if (rgb16) read_rgb16(&palette[(size_t)i * 3]);
+			else for (int j = 0; j < comp; ++j) palette[(size_t)i * comp + j] = (uint8_t)u8();
+		}
+	}
 	const size_t npix = (size_t)w * h;
+	std::vector<uint8_t> data(npix * comp);
 	uint8_t px[4] = {0, 0, 0, 0};
-	size_t i = 0;
 	int run = 0;
-	bool run_is_rle = false;
-	while (i < npix) {
+	bool repeating = false;
+	for (size_t i = 0; i < npix; ++i) {
 		bool read_pixel = true;
 		if (rle) {
 			if (run == 0) {
-				if (pos >= f.size()) return false;
-				const int c = f[pos++];
+				const int c = u8();
 				run = 1 + (c & 127);
-				run_is_rle = (c & 128) != 0;
-			} else if (run_is_rle)
+				repeating = (c >> 7) != 0;
+			} else if (repeating)
 				read_pixel = false;
 		}
 		if (read_pixel) {
-			if (pos + (size_t)nb > f.size()) return false;
-			memcpy(px, &f[pos], (size_t)nb);
-			pos += (size_t)nb;
+			if (indexed) {
+				int idx = bpp == 8 ? u8() : u16();
+				if (idx >= pal_len) idx = 0;
+				for (int j = 0; j < comp; ++j) px[j] = palette[(size_t)idx * comp + j];
+			} else if (rgb16)
+				read_rgb16(px);
+			else
+				for (int j = 0; j < comp; ++j) px[j] = (uint8_t)u8();
 		}
-		const size_t y = i / (size_t)w, x = i % (size_t)w;
-		const size_t yy = (desc & 0x20) ? y : (size_t)h - 1 - y; // bit 5 set = top-left origin
-		const size_t xx = (desc & 0x10) ? (size_t)w - 1 - x : x;
-		uint8_t *o = &img->rgb[(yy * (size_t)w + xx) * 3];
-		if (grey) o[0] = o[1] = o[2] = px[0];
-		else { o[0] = px[2]; o[1] = px[1]; o[2] = px[0]; } // BGR(A) on disk
-		++i;
-		if (rle) --run;
+		memcpy(&data[i * comp], px, (size_t)comp);
+		--run;
+	}
+	img->width = w;
+	img->height = h;
+	img->rgb.assign(npix * 3, 0);
+	const bool bottom_up = ((desc >> 5) & 1) == 0;
+	for (int y = 0; y < h; ++y) {
+		const uint8_t *src = &data[(size_t)(bottom_up ? h - 1 - y : y) * w * comp];
+		uint8_t *dst = &img->rgb[(size_t)y * w * 3];
+		for (int x = 0; x < w; ++x, src += comp, dst += 3) {
+			if (comp <= 2) dst[0] = dst[1] = dst[2] = src[0];                    // grey (+alpha): replicated
+			else if (rgb16) { dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; } // already R,G,B
+			else { dst[0] = src[2]; dst[1] = src[1]; dst[2] = src[0]; }            // B,G,R(,A) on disk
+		}
 	}
 	return true;
 }
-
 
 // ---- BMP (stb_image.h:4920-5230 is the behaviour to match: BITMAPCOREHEADER / INFOHEADER / V3 (56) / V4 / V5 headers;
 // 4- and 8-bit palettes, 16-bit 5-5-5 or bit-field masks, 24-bit, 32-bit; bottom-up or top-down; 1-bit and RLE files
@@ -344,9 +392,7 @@ bool decode_image_file(const char *path, DecodedImage *img)
 	if (decode_png(file, img)) return true;
 	if (file.size() > 2 && file[0] == 'B' && file[1] == 'M') return decode_bmp(file, img);
 	if (decode_jpeg(file, img)) return true;
-	const size_t n = strlen(path);
-	if (n > 4 && (!strcmp(path + n - 4, ".tga") || !strcmp(path + n - 4, ".TGA"))) return decode_tga(file, img); // TGA has no magic number
-	return false;
+	return decode_tga(file, img); // TGA has no magic number: like stb_image, try it last, on the header's plausibility
 }
 
 } // namespace host

@@ -63,6 +63,69 @@ def test_decoders_match_stb_image(refmod, tmp_path):
     assert dtex.tolist() == list(range(len(files) - 1)) + [-1]  # renumbered among the loaded ones; failure -> -1
 
 
+def tga_cases(d):
+    """TGA files covering stb_image's branches: true colour 24/32, grey, grey+alpha, colour-mapped (PIL writes those for
+    mode P), RLE or raw, either origin; hand-made 15/16-bit 5-5-5, palettes with 16- and 32-bit entries, 16-bit
+    indices, out-of-range indices, the palette-start quirk, an 8-bit (grey) palette, the ignored right-to-left bit, an
+    RLE stream that ends early (zeros follow), and headers stb_image refuses."""
+    import struct
+    rng = np.random.default_rng(31)
+    out = {}
+    for k, (mode, kw) in enumerate([("RGB", {}), ("RGB", dict(compression="tga_rle")), ("RGBA", dict(orientation=1)), ("L", dict(compression="tga_rle", orientation=1)),
+                                    ("LA", {}), ("LA", dict(compression="tga_rle")), ("P", {}), ("P", dict(compression="tga_rle", orientation=1)), ("1", {})]):
+        arr = np.repeat(rng.integers(0, 256, size=(11, 5, 4), dtype=np.uint8), 4, axis=1)[:, :17]
+        img = {"RGB": lambda: PIL.fromarray(arr[..., :3]), "RGBA": lambda: PIL.fromarray(arr, "RGBA"), "L": lambda: PIL.fromarray(arr[..., 0]),
+               "LA": lambda: PIL.fromarray(arr[..., :2], "LA"), "P": lambda: PIL.fromarray(arr[..., :3]).convert("P", palette=PIL.ADAPTIVE, colors=40),
+               "1": lambda: PIL.fromarray(arr[..., 0] > 128)}[mode]()
+        name = f"pil{k}_{mode}.tga"
+        out[name] = os.path.join(d, name)
+        img.save(out[name], **kw)
+
+    def raw(name, idlen, indexed, typ, pal_start, pal_len, pal_bits, w, h, bpp, desc, pal=b"", body=b"", ident=b""):
+        out[name] = os.path.join(d, name)
+        open(out[name], "wb").write(struct.pack("<BBBHHBHHHHBB", idlen, indexed, typ, pal_start, pal_len, pal_bits, 0, 0, w, h, bpp, desc) + ident + pal + body)
+
+    w, h = 7, 5
+    v16 = rng.integers(0, 65536, size=(h, w), dtype=np.uint16).astype("<u2").tobytes()
+    idx8 = rng.integers(0, 16, size=(h, w), dtype=np.uint8).tobytes()
+    rnd = lambda n: rng.integers(0, 256, size=n, dtype=np.uint8).tobytes()
+    raw("rgb16.tga", 0, 0, 2, 0, 0, 0, w, h, 16, 0, body=v16)
+    raw("rgb15_top_id.tga", 3, 0, 2, 0, 0, 0, w, h, 15, 0x20, body=v16, ident=b"abc")
+    raw("idx_pal16.tga", 0, 1, 1, 0, 16, 16, w, h, 8, 0, pal=rnd(32), body=idx8)
+    raw("idx_pal32.tga", 0, 1, 1, 0, 16, 32, w, h, 8, 0x20, pal=rnd(64), body=idx8)
+    raw("idx16_pal24.tga", 0, 1, 1, 0, 300, 24, w, h, 16, 0, pal=rnd(900), body=rng.integers(0, 300, size=(h, w), dtype=np.uint16).astype("<u2").tobytes())
+    raw("idx_out_of_range.tga", 0, 1, 1, 0, 8, 24, w, h, 8, 0, pal=rnd(24), body=idx8)
+    raw("idx_pal_start.tga", 0, 1, 1, 2, 16, 24, w, h, 8, 0, pal=b"zz" + rnd(48), body=idx8)
+    raw("idx_pal8.tga", 0, 1, 1, 0, 16, 8, w, h, 8, 0, pal=rnd(16), body=idx8)
+    raw("right_to_left.tga", 0, 0, 2, 0, 0, 0, w, h, 24, 0x10, body=rnd(w * h * 3))
+    raw("rle_ends_early.tga", 0, 0, 10, 0, 0, 0, w, h, 24, 0, body=bytes([0x80 | 6, 1, 2, 3, 2, 9, 9, 9, 8, 8, 8, 7, 7, 7, 0x80 | 127, 5, 5, 5]))
+    raw("grey_alpha_rle.tga", 0, 0, 11, 0, 0, 0, w, h, 16, 0, body=bytes([0x80 | 34, 200, 17]))
+    raw("refused_type4.tga", 0, 0, 4, 0, 0, 0, w, h, 24, 0, body=b"\0" * 200)
+    raw("refused_bpp12.tga", 0, 0, 2, 0, 0, 0, w, h, 12, 0, body=b"\0" * 200)
+    return out
+
+
+def test_tga_decoder_matches_stb_image(refmod, tmp_path):
+    files = tga_cases(str(tmp_path))
+    from adypt_b200 import host as H
+    refused = 0
+    for name, path in files.items():
+        exp = refmod.load_image_rgb8(path)
+        # the texture is referenced under a neutral name: like stb_image, the decoder goes by content, not extension
+        os.replace(path, str(tmp_path / "texture.bin"))
+        (tmp_path / "g.mtl").write_text("newmtl m0\nKd 1 1 1\nillum 1\nmap_Kd texture.bin\n")
+        (tmp_path / "g.obj").write_text("mtllib g.mtl\nv 0 0 0\nv 1 0 0\nv 0 1 0\nv 3 0 0\nusemtl m0\nf 1 2 3\nf 2 3 4\n")
+        hs = H.HostScene.from_obj(str(tmp_path / "g.obj"))
+        ok, bad = hs.load_textures()
+        if exp is None:
+            assert (ok, bad) == (0, 1), name
+            refused += 1
+            continue
+        assert (ok, bad) == (1, 0), name
+        assert hs.textures[0].shape == exp.shape and np.array_equal(hs.textures[0], exp), name
+    assert refused == 3 and len(files) - refused >= 19  # refused: 1-bit (PIL writes it as an unsupported type), type 4, 12 bpp
+
+
 def bmp_cases(d):
     """BMP files covering stb_image's branches: 24-bit, 8-bit palette / grey, 32-bit, 4-bit palette, 16-bit 5-5-5 and
     5-6-5 bit fields, 32-bit bit fields, top-down rows, the 12-byte OS/2 header, the 56-byte V3 header; 1-bit and RLE
