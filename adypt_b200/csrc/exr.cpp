@@ -32,32 +32,33 @@ void put_attr(std::vector<uint8_t> &b, const char *name, const char *type, const
 	b.insert(b.end(), p, p + size);
 }
 
-// IEEE binary32 -> binary16, round to nearest even, with subnormals, overflow to inf and NaN kept quiet
+// binary32 -> binary16 with the rules of the reference's writer (tinyexr's float_to_half_full, dep/tinyexr.h:7160-7195,
+// "based on ISPC reference code"), so that an fp16 file holds the same bits: the first dropped bit decides the
+// rounding (halves go UP, not to even), float subnormals become zero, any NaN becomes the quiet NaN 0x7e00 (sign
+// kept), results of 2^16 and above become infinity, and a rounding carry may walk into the exponent.
 uint16_t float_to_half(float f)
 {
 	uint32_t x;
 	memcpy(&x, &f, 4);
-	const uint32_t sign = (x >> 16) & 0x8000u;
-	const uint32_t mag = x & 0x7fffffffu;
-	if (mag >= 0x7f800000u) return (uint16_t)(sign | 0x7c00u | (mag > 0x7f800000u ? 0x200u | ((mag >> 13) & 0x3ffu) : 0u));
-	if (mag >= 0x477ff000u) return (uint16_t)(sign | 0x7c00u); // rounds to >= 65520 -> inf
-	if (mag < 0x33000001u) return (uint16_t)sign;               // rounds to zero (< 2^-25, or exactly 2^-25 ties to even 0)
-	const int exp = (int)(mag >> 23) - 127;
-	uint32_t man = (mag & 0x7fffffu) | 0x800000u;
-	int shift;
-	uint32_t base;
-	if (exp < -14) { // subnormal half
-		shift = 13 + (-14 - exp);
-		base = 0;
-	} else {
-		shift = 13;
-		base = (uint32_t)(exp + 15) << 10;
-		man &= 0x7fffffu;
+	const uint32_t sign = (x >> 16) & 0x8000u, exp8 = (x >> 23) & 0xffu, man = x & 0x7fffffu;
+	uint32_t h = 0;
+	if (exp8 == 0) h = 0;
+	else if (exp8 == 255) h = 0x7c00u | (man ? 0x200u : 0u);
+	else {
+		const int e = (int)exp8 - 127 + 15;
+		if (e >= 31) h = 0x7c00u;
+		else if (e <= 0) {
+			if (14 - e <= 24) {
+				const uint32_t m = man | 0x800000u;
+				h = m >> (14 - e);
+				if ((m >> (13 - e)) & 1u) ++h;
+			}
+		} else {
+			h = ((uint32_t)e << 10) | (man >> 13);
+			if (man & 0x1000u) ++h;
+		}
 	}
-	uint32_t q = man >> shift;
-	const uint32_t rem = man & ((1u << shift) - 1u), half = 1u << (shift - 1);
-	if (rem > half || (rem == half && (q & 1u))) ++q; // carries propagate into the exponent correctly
-	return (uint16_t)(sign | (base + q));
+	return (uint16_t)(sign | h);
 }
 
 } // namespace
@@ -94,7 +95,8 @@ extern "C" int adypt_write_exr(const char *filename, const float *rgb, int32_t w
 	const float one = 1.0f, zero2[2] = {0.0f, 0.0f};
 	put_attr(hdr, "pixelAspectRatio", "float", &one, 4);
 	put_attr(hdr, "screenWindowCenter", "v2f", zero2, 8);
-	put_attr(hdr, "screenWindowWidth", "float", &one, 4);
+	const float screen_width = (float)width; // tinyexr writes the image width here (dep/tinyexr.h:11767-11773)
+	put_attr(hdr, "screenWindowWidth", "float", &screen_width, 4);
 	hdr.push_back(0);
 
 	const int lines_per_chunk = 16;

@@ -48,6 +48,8 @@ def lib():
         l.ref_config_load.argtypes = [C.c_char_p, C.c_void_p]
         l.ref_config_roundtrip_json.restype = C.c_int
         l.ref_config_roundtrip_json.argtypes = [C.c_char_p, C.c_char_p, C.c_uint32]
+        l.ref_save_exr.restype = C.c_int
+        l.ref_save_exr.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_char_p]
         l.ref_load_image_rgb8.restype = C.c_int
         l.ref_load_image_rgb8.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
         _lib = l
@@ -176,6 +178,12 @@ def config_roundtrip_json(path: str):
     buf = C.create_string_buffer(1 << 16)
     n = lib().ref_config_roundtrip_json(path.encode(), buf, len(buf))
     return buf.value.decode() if n >= 0 else None
+
+
+def save_exr(rgb, path: str, fp16: bool = False) -> int:
+    """SaveEXR of the reference's vendored tinyexr, called like OglPathTracer::SaveResult does; rgb: (h, w, 3) float32."""
+    a = np.ascontiguousarray(rgb, dtype=np.float32)
+    return lib().ref_save_exr(a.ctypes.data, a.shape[1], a.shape[0], int(fp16), path.encode())
 
 
 def load_image_rgb8(path: str):

@@ -31,6 +31,8 @@
 #include <glm/gtc/matrix_transform.hpp>
 #define STB_IMAGE_IMPLEMENTATION
 #include <stb_image.h> // the reference's texture decoder (OglScene.cpp:9-10, 24), vendored under dep/
+#define TINYEXR_IMPLEMENTATION
+#include <tinyexr.h>   // the reference's image writer (OglPathTracer.cpp:8-9, 206), vendored under dep/
 
 static_assert(sizeof(WideBVHNode) == 80, "CWBVH node ABI");
 static_assert(sizeof(Triangle) == 100, "Triangle ABI");
@@ -214,6 +216,16 @@ int ref_load_image_rgb8(const char *path, int *width, int *height, unsigned char
 	if (need <= cap) memcpy(out, data, need);
 	else rc = -2;
 	stbi_image_free(data);
+	return rc;
+}
+
+// SaveEXR(pixels, w, h, 3, save_as_fp16, filename, &err) exactly as OglPathTracer::SaveResult calls it
+// (OglPathTracer.cpp:199-212) on a tightly packed RGB float image. Returns tinyexr's status (0 = success).
+int ref_save_exr(const float *rgb, int width, int height, int save_as_fp16, const char *filename)
+{
+	const char *err = nullptr;
+	const int rc = SaveEXR(rgb, width, height, 3, save_as_fp16, filename, &err);
+	if (err) free((void *)err);
 	return rc;
 }
 

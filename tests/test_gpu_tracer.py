@@ -177,7 +177,14 @@ def test_save_exr(A, tmp_path):
         tr.save_exr(p, fp16)
         r = read_exr(p)
         got = np.stack([r["data"]["R"], r["data"]["G"], r["data"]["B"]], axis=2)
-        exp = img.astype(np.float16).astype(np.float32) if fp16 else img
+        if fp16:  # the file is written by the same code as A.write_exr (pinned against tinyexr in test_capi_host.py)
+            q = str(tmp_path / "w.exr")
+            A.write_exr(q, img, fp16=True)
+            w = read_exr(q)
+            exp = np.stack([w["data"]["R"], w["data"]["G"], w["data"]["B"]], axis=2)
+            assert np.abs(exp - img).max() <= np.abs(img).max() * 2.0 ** -10
+        else:
+            exp = img
         assert np.array_equal(got, exp)
     with pytest.raises(A.AdyptError):
         tr.save_exr("/nonexistent_dir/x.exr")
