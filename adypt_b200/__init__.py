@@ -35,7 +35,7 @@ EXPORTS = [
     "adypt_tracer_stats", "adypt_write_exr", "adypt_debug_math",
     "adypt_host_scene_load_obj", "adypt_host_scene_from_triangles", "adypt_host_scene_destroy", "adypt_host_scene_build_bvh",
     "adypt_host_scene_load_bvh", "adypt_host_scene_save_bvh", "adypt_host_scene_get", "adypt_host_scene_upload",
-    "adypt_config_set_default", "adypt_config_load", "adypt_config_to_json", "adypt_config_save",
+    "adypt_config_format_double", "adypt_config_set_default", "adypt_config_load", "adypt_config_to_json", "adypt_config_save",
     "adypt_group_create", "adypt_group_destroy", "adypt_group_set_camera", "adypt_group_set_sun_visibility", "adypt_group_set_russian_roulette", "adypt_group_render",
     "adypt_group_read", "adypt_group_save_exr", "adypt_tracer_stream",
 ]

@@ -6,9 +6,8 @@
 //     overflows 64 bits) -- so  "fov": 45  is rejected and must be  45.0  (InstanceConfig.cpp:17-18,
 //     dep/rapidjson/document.h:972-977);
 //   * output is rapidjson's PrettyWriter layout: 4-space indent, one array element per line, doubles printed
-//     as the shortest round-trip decimal with rapidjson's fixed/exponent switch-over (dtoa.h Prettify).
-//     Known difference: rapidjson's Grisu2 is not always shortest/closest and may end a 17-digit value in another
-//     final digit (0.30000001192092898 for 0.3f where this writes ...896); both texts parse to the same double.
+//     with rapidjson's own digit generation (Grisu2, not always the shortest: 0.3f comes out as
+//     0.30000001192092898) and fixed/exponent switch-over (dtoa.h Prettify) -- the text is byte-identical.
 // A small recursive-descent JSON reader replaces rapidjson here; numbers follow its normal-precision path
 // (64-bit digit accumulation, then one multiply/divide by a power of ten).
 #include <algorithm>
@@ -246,19 +245,166 @@ std::string undefined(const char *type, const char *key, const char *where)
 	return std::string("[PARSER]ERR: undefined ") + type + " \"" + key + "\" in " + where;
 }
 
-// rapidjson Writer::WriteDouble: shortest round-trip digits, then dtoa.h Prettify
+// ---- double -> decimal digits the way rapidjson's Writer does it (internal/dtoa.h: Grisu2, then Prettify), so that a
+// saved .config has the reference's text byte for byte. Grisu2 (Loitsch, PLDI 2010) works on 64-bit "do-it-yourself"
+// floats: the value and its rounding boundaries are scaled by a cached power of ten c_k ~ 10^k so that the product's
+// exponent lands in a fixed window, digits are peeled off the upper boundary until they identify the interval, and a
+// final "weeding" step moves the last digit towards the value. It is correct but not always shortest, which is why
+// std::to_chars cannot stand in for it.
+
+struct DiyFp {
+	uint64_t f = 0;
+	int e = 0;
+	DiyFp() {}
+	DiyFp(uint64_t f_, int e_) : f(f_), e(e_) {}
+	explicit DiyFp(double d)
+	{
+		uint64_t u;
+		memcpy(&u, &d, 8);
+		const int biased = (int)((u >> 52) & 0x7ff);
+		const uint64_t frac = u & 0xfffffffffffffull;
+		if (biased) { f = frac | (1ull << 52); e = biased - 0x3ff - 52; }
+		else { f = frac; e = 1 - 0x3ff - 52; }
+	}
+	DiyFp times(const DiyFp &r) const // upper 64 bits of the product, rounded on the 65th
+	{
+		const unsigned __int128 p = (unsigned __int128)f * r.f;
+		uint64_t h = (uint64_t)(p >> 64);
+		if ((uint64_t)p & (1ull << 63)) ++h;
+		return DiyFp(h, e + r.e + 64);
+	}
+	DiyFp normalized() const
+	{
+		const int s = __builtin_clzll(f);
+		return DiyFp(f << s, e - s);
+	}
+	void boundaries(DiyFp *minus, DiyFp *plus) const
+	{
+		DiyFp pl((f << 1) + 1, e - 1);
+		while (!(pl.f & (1ull << 53))) { pl.f <<= 1; --pl.e; }
+		pl.f <<= 10;
+		pl.e -= 10;
+		DiyFp mi = f == (1ull << 52) ? DiyFp((f << 2) - 1, e - 2) : DiyFp((f << 1) - 1, e - 1);
+		mi.f <<= mi.e - pl.e;
+		mi.e = pl.e;
+		*minus = mi;
+		*plus = pl;
+	}
+};
+
+// c_k for k = -348, -340, ..., 340: the 64-bit significand of 10^k rounded to nearest and its binary exponent,
+// computed exactly with a little big-integer arithmetic the first time they are needed
+const DiyFp *cached_powers()
+{
+	static const std::vector<DiyFp> table = [] {
+		typedef std::vector<uint32_t> Big; // little-endian base 2^32
+		auto mul_small = [](Big &x, uint32_t m) {
+			uint64_t carry = 0;
+			for (uint32_t &w : x) { const uint64_t t = (uint64_t)w * m + carry; w = (uint32_t)t; carry = t >> 32; }
+			if (carry) x.push_back((uint32_t)carry);
+		};
+		auto div_small = [](Big &x, uint32_t v) {
+			uint64_t rem = 0;
+			for (size_t i = x.size(); i-- > 0;) { const uint64_t t = (rem << 32) | x[i]; x[i] = (uint32_t)(t / v); rem = t % v; }
+			while (x.size() > 1 && x.back() == 0) x.pop_back();
+		};
+		auto bit_length = [](const Big &x) { return (int)(x.size() - 1) * 32 + (32 - __builtin_clz(x.back())); };
+		auto bit = [](const Big &x, int i) { return i < 0 ? 0u : (x[(size_t)i / 32] >> (i % 32)) & 1u; };
+		std::vector<DiyFp> t;
+		for (int k = -348; k <= 340; k += 8) {
+			Big n(1, 1u);
+			int scale = 0; // value = n * 2^-scale
+			if (k >= 0)
+				for (int i = 0; i < k; ++i) mul_small(n, 10);
+			else {
+				scale = 64 + 64 + (int)(-k * 3.33) + 8;
+				n.assign((size_t)scale / 32 + 1, 0u);
+				n[(size_t)scale / 32] = 1u << (scale % 32);
+				for (int i = 0; i < -k; ++i) div_small(n, 10); // nested floor divisions = floor(2^scale / 10^-k)
+			}
+			const int len = bit_length(n);
+			uint64_t f = 0;
+			for (int i = 0; i < 64; ++i) f = (f << 1) | bit(n, len - 1 - i);
+			int e = len - 64 - scale;
+			if (bit(n, len - 65)) {
+				if (++f == 0) { f = 1ull << 63; ++e; }
+			}
+			t.push_back(DiyFp(f, e));
+		}
+		return t;
+	}();
+	return table.data();
+}
+
+// digits of a positive finite double: buffer[0..*length) and *k with value = digits * 10^k (dtoa.h Grisu2 + DigitGen)
+void grisu2(double value, char *buffer, int *length, int *k)
+{
+	static const uint32_t kPow10[] = {1, 10, 100, 1000, 10000, 100000, 1000000, 10000000, 100000000, 1000000000};
+	const DiyFp v(value);
+	DiyFp w_m, w_p;
+	v.boundaries(&w_m, &w_p);
+	// the cached power that brings w_p's exponent into the digit-generation window
+	const double dk = (-61 - w_p.e) * 0.30102999566398114 + 347;
+	int kk = (int)dk;
+	if (dk - kk > 0.0) ++kk;
+	const unsigned index = (unsigned)((kk >> 3) + 1);
+	*k = -(-348 + (int)(index << 3));
+	const DiyFp c = cached_powers()[index];
+	const DiyFp W = v.normalized().times(c);
+	DiyFp Wp = w_p.times(c), Wm = w_m.times(c);
+	++Wm.f;
+	--Wp.f;
+	uint64_t delta = Wp.f - Wm.f;
+	const uint64_t one_f = 1ull << -Wp.e, wp_w = Wp.f - W.f;
+	uint32_t p1 = (uint32_t)(Wp.f >> -Wp.e);
+	uint64_t p2 = Wp.f & (one_f - 1);
+	auto weed = [&](uint64_t rest, uint64_t ten_kappa, uint64_t dist) { // move the last digit towards the value
+		while (rest < dist && delta - rest >= ten_kappa && (rest + ten_kappa < dist || dist - rest > rest + ten_kappa - dist)) {
+			--buffer[*length - 1];
+			rest += ten_kappa;
+		}
+	};
+	int kappa = 9;
+	for (int i = 1; i < 9; ++i)
+		if (p1 < kPow10[i]) { kappa = i; break; }
+	*length = 0;
+	while (kappa > 0) {
+		const uint32_t unit = kPow10[kappa - 1];
+		const uint32_t d = p1 / unit;
+		p1 %= unit;
+		if (d || *length) buffer[(*length)++] = (char)('0' + d);
+		--kappa;
+		const uint64_t rest = ((uint64_t)p1 << -Wp.e) + p2;
+		if (rest <= delta) {
+			*k += kappa;
+			weed(rest, (uint64_t)kPow10[kappa] << -Wp.e, wp_w);
+			return;
+		}
+	}
+	for (;;) {
+		p2 *= 10;
+		delta *= 10;
+		const char d = (char)(p2 >> -Wp.e);
+		if (d || *length) buffer[(*length)++] = (char)('0' + d);
+		p2 &= one_f - 1;
+		--kappa;
+		if (p2 < delta) {
+			*k += kappa;
+			const int index10 = -kappa;
+			weed(p2, one_f, wp_w * (index10 < 9 ? kPow10[index10] : 0));
+			return;
+		}
+	}
+}
+
+// rapidjson Writer::WriteDouble -> internal::dtoa: Grisu2 digits, then Prettify's choice of fixed or exponent form
 std::string fmt_double(double v)
 {
 	if (v == 0.0) return std::signbit(v) ? "-0.0" : "0.0";
-	char buf[64];
-	auto r = std::to_chars(buf, buf + sizeof(buf), std::fabs(v), std::chars_format::scientific);
-	std::string sci(buf, r.ptr); // d[.ddd]e[+-]XX
-	const size_t epos = sci.find('e');
-	std::string digits = sci.substr(0, epos);
-	digits.erase(std::remove(digits.begin(), digits.end(), '.'), digits.end());
-	const int exp10 = atoi(sci.c_str() + epos + 1);
-	const int length = (int)digits.size();
-	const int k = exp10 - (length - 1); // value = digits * 10^k
+	char buf[32];
+	int length = 0, k = 0;
+	grisu2(std::fabs(v), buf, &length, &k);
+	const std::string digits(buf, (size_t)length);
 	const int kk = length + k;
 	std::string out = v < 0 ? "-" : "";
 	if (0 <= k && kk <= 21) out += digits + std::string((size_t)k, '0') + ".0";
@@ -405,6 +551,18 @@ int adypt_config_load(const char *path, adypt_instance_config *c)
 	NEED_FLOAT(cam, "pitch", "cam_obj", out.cam.pitch)
 	NEED_VEC3(cam, "position", "cam_obj", out.cam.position)
 	*c = out;
+	return ADYPT_OK;
+	});
+}
+
+int adypt_config_format_double(double value, char out[32])
+{
+	return adypt::guarded([&]() -> int {
+	if (!out) return fail(ADYPT_EINVAL, "out is NULL");
+	if (!std::isfinite(value)) return fail(ADYPT_EINVAL, "NaN and infinity have no JSON text");
+	const std::string t = fmt_double(value);
+	if (t.size() >= 32) return fail(ADYPT_ERANGE, "number text too long");
+	memcpy(out, t.c_str(), t.size() + 1);
 	return ADYPT_OK;
 	});
 }

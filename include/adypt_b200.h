@@ -293,6 +293,9 @@ int adypt_config_load(const char *path, adypt_instance_config *config);      /* 
                                                  "[PARSER]ERR: ..." line the reference prints is in adypt_last_error() */
 int adypt_config_to_json(const adypt_instance_config *config, char *buf, uint64_t cap, uint64_t *needed); /* GetJson */
 int adypt_config_save(const adypt_instance_config *config, const char *path); /* InstanceConfig::SaveToFile */
+/* The text a finite double gets in a saved .config: rapidjson's Writer::WriteDouble (Grisu2 digits, then Prettify).
+ * out must hold 32 bytes; NaN / infinity give ADYPT_EINVAL (rapidjson's writer refuses them too). */
+int adypt_config_format_double(double value, char out[32]);
 
 #ifdef __cplusplus
 }

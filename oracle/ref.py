@@ -180,6 +180,17 @@ def config_roundtrip_json(path: str):
     return buf.value.decode() if n >= 0 else None
 
 
+def dtoa(values):
+    """rapidjson's own double formatting (what its Writer emits) for an array of doubles -> list of str."""
+    v = np.ascontiguousarray(values, dtype=np.float64)
+    buf = C.create_string_buffer(32 * max(1, v.size))
+    l = lib()
+    l.ref_dtoa.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+    l.ref_dtoa(v.ctypes.data, v.size, buf)
+    raw = buf.raw
+    return [raw[32 * i: 32 * i + 32].split(b"\0", 1)[0].decode() for i in range(v.size)]
+
+
 def save_exr(rgb, path: str, fp16: bool = False) -> int:
     """SaveEXR of the reference's vendored tinyexr, called like OglPathTracer::SaveResult does; rgb: (h, w, 3) float32."""
     a = np.ascontiguousarray(rgb, dtype=np.float32)

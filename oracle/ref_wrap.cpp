@@ -29,6 +29,7 @@
 #include "BVH/WideBVHBuilder.hpp"
 #include "InstanceConfig.hpp"
 #include <glm/gtc/matrix_transform.hpp>
+#include <rapidjson/internal/dtoa.h>
 #define STB_IMAGE_IMPLEMENTATION
 #include <stb_image.h> // the reference's texture decoder (OglScene.cpp:9-10, 24), vendored under dep/
 #define TINYEXR_IMPLEMENTATION
@@ -227,6 +228,16 @@ int ref_save_exr(const float *rgb, int width, int height, int save_as_fp16, cons
 	const int rc = SaveEXR(rgb, width, height, 3, save_as_fp16, filename, &err);
 	if (err) free((void *)err);
 	return rc;
+}
+
+// rapidjson's double -> text (Writer::WriteDouble -> internal::dtoa, dep/rapidjson/internal/dtoa.h) for n doubles;
+// each result is NUL-terminated at out + 32 * i. Pins the product's own Grisu2 + Prettify.
+void ref_dtoa(const double *values, unsigned long long n, char *out)
+{
+	for (unsigned long long i = 0; i < n; ++i) {
+		char *end = rapidjson::internal::dtoa(values[i], out + 32 * i, 324);
+		*end = 0;
+	}
 }
 
 // glm::inverse(mat4) of the reference's vendored glm (dep/glm/detail/func_matrix.inl:294-351),
