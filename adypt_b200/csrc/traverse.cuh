@@ -12,8 +12,8 @@
 // node and the Woop dot chains.
 //
 // Memory: node = 5 x LDG.128 and Woop = 3 x LDG.128 through the read-only path (L1 + L2; C1/C2 BVHs are
-// L2-resident on B200), traversal stack = SSTACK entries per lane in shared memory ([entry][thread], so a
-// warp's 8-byte accesses are conflict-free) with a local-memory overflow that real scenes never reach.
+// L2-resident on B200), traversal stack = kSmemStack entries per lane in shared memory (per warp [entry][lane],
+// so a warp's 8-byte accesses are conflict-free) with a local-memory overflow that real scenes never reach.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -40,10 +40,24 @@ struct TraceParams {
 };
 
 constexpr int kTraceBlock = 128;      // threads per CTA
-constexpr int kSmemStack = 8;         // stack entries per lane kept in shared memory
-constexpr int kLocalStack = 56;       // overflow entries (local memory); total 64 like the oracle
+#ifndef ADYPT_SMEM_STACK
+#define ADYPT_SMEM_STACK 8
+#endif
+constexpr int kSmemStack = ADYPT_SMEM_STACK;  // stack entries per lane kept in shared memory
+constexpr int kLocalStack = 64 - kSmemStack;  // overflow entries (local memory); total 64 like the oracle
 constexpr unsigned kPoolChunk = 256;  // most ray indices a warp takes per atomicAdd (small batches take fewer, see launch_trace)
 constexpr unsigned kFullMask = 0xffffffffu;
+
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v)
+{
+	asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr)
+{
+	float4 v;
+	asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+	return v;
+}
 
 __device__ __forceinline__ float dot3_fma(float ax, float ay, float az, const float4 m)
 {
@@ -118,21 +132,44 @@ __device__ __forceinline__ uint32_t test_children4(uint32_t meta4, uint32_t octi
 // the group is empty; 12 = K 2 with both triangles' rows fetched before the first test. Only the warp-level
 // interleaving differs: each ray's own sequence of node steps and triangle tests -- and therefore every result and
 // counter -- is the same. A warp no longer waits for its one lane with nine triangles: -12 % time on C2.
-template <bool ANY, bool STATS = false, int CVT_PLANES = 4, int MIN_CTAS = 8, int TRI_BATCH = 12>
+//
+// STAGED: ray set-up (two 16-byte loads, clamp, IEEE normalise, three IEEE reciprocals: ~100 instructions) is done by the
+// whole warp for the next 32 rays of its pool at once and parked in shared memory (48 B per ray); an idle lane then picks
+// its ray up with three LDS.128. Unstaged, the same code runs at every refill for the ~6 lanes that happen to be idle, and
+// the warp waits on the (cold, HBM) ray loads five times as often. Same arithmetic per ray, so same results.
+template <bool ANY, bool STATS = false, int CVT_PLANES = 4, int MIN_CTAS = 8, int TRI_BATCH = 12, bool STAGED = true>
 __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const TraceParams p)
 {
 	const uint32_t magic = p.magic;
-	__shared__ uint2 s_stack[kSmemStack][kTraceBlock];
+	// Shared memory, one region per warp: [stack: kSmemStack entries x 32 lanes x 8 B][stage: 3 rows x 32 entries x 16 B].
+	// Every address is formed from ONE register, lane_addr = region + 8 * lane (stack entry sp of this lane is at
+	// lane_addr + 256 * sp; 8-byte accesses of a warp are conflict-free), and so are the lane number and its lt-mask:
+	// left to itself ptxas re-derives all of these from S2R tid / cta-id reads at every push, pop and refill.
+	constexpr unsigned kWarpStack = kSmemStack * 256u, kWarpRegion = kWarpStack + (STAGED ? 3u * 512u : 0u);
+	static_assert(kWarpRegion % 256u == 0u, "lane bits are taken from the low byte of the address");
+	__shared__ __align__(256) unsigned char s_mem[(kTraceBlock / 32) * kWarpRegion];
 	uint2 l_stack[kLocalStack];
 
-	const unsigned tid = threadIdx.x;
-	const unsigned lane = tid & 31u;
-	const unsigned lt_mask = (1u << lane) - 1u;
+	uint32_t lane_addr = (uint32_t)__cvta_generic_to_shared(s_mem) + (threadIdx.x >> 5) * kWarpRegion + (threadIdx.x & 31u) * 8u;
+	asm volatile("mov.u32 %0, %0;" : "+r"(lane_addr)); // opaque, so that it is held in a register (-3.6 % time)
+	const unsigned lane = (lane_addr >> 3) & 31u;
+	const unsigned lt_mask = ~(0xffffffffu << lane);
 	const unsigned long long n_rays = p.n_ptr ? *p.n_ptr : p.n;
+	const uint4 *nodes_base = p.nodes;
+	const float4 *woop_base = p.woop;
+#ifdef ADYPT_PTR_REGS
+	asm volatile("mov.u64 %0, %0;" : "+l"(nodes_base));
+#if ADYPT_PTR_REGS > 1
+	asm volatile("mov.u64 %0, %0;" : "+l"(woop_base));
+#endif
+#endif
 
 	// warp-uniform pool of ray indices
 	unsigned long long pool_next = 0, pool_end = 0;
 	bool exhausted = false;
+	// STAGED: entries [stage_pos, stage_cnt) of the warp's 32-entry stage hold rays stage_base + entry, set up and untaken
+	unsigned long long stage_base = 0;
+	unsigned stage_pos = 0, stage_cnt = 0;
 
 	// per-lane ray state. sp doubles as the lane's status: >= 0 traversing (stack depth), kIdle = no ray,
 	// kUnsaved = ray finished, result still in registers (stored at the next refill)
@@ -162,6 +199,62 @@ __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const Trac
 				if (p.out_uv) p.out_uv[ray_idx] = make_float2(hit_u, hit_v);
 			}
 		}
+		if (STAGED) {
+			while (idle != 0) {
+				if (stage_pos == stage_cnt) {
+					if (exhausted) break;
+					if (pool_next >= pool_end) {
+						unsigned long long b = 0;
+						if (lane == 0) b = atomicAdd(p.counter, (unsigned long long)p.pool_chunk);
+						b = __shfl_sync(kFullMask, b, 0);
+						if (b >= n_rays) { exhausted = true; break; }
+						pool_next = b;
+						pool_end = (b + p.pool_chunk < n_rays) ? b + p.pool_chunk : n_rays;
+					}
+					const unsigned long long left = pool_end - pool_next;
+					stage_cnt = left < 32ull ? (unsigned)left : 32u;
+					stage_base = pool_next;
+					pool_next += stage_cnt;
+					stage_pos = 0;
+					__syncwarp(); // the previous stage's readers are done
+					if (lane < stage_cnt) {
+						// ray setup, traversal.glsl:16-35
+						const unsigned long long r = stage_base + lane;
+						const float4 r0 = __ldg(p.rays + 2 * r), r1 = __ldg(p.rays + 2 * r + 1);
+						const float ooeps = 5.42101086242752217e-20f; // exp2(-64)
+						float sx = fabsf(r1.x) > ooeps ? r1.x : (r1.x >= 0.0f ? ooeps : -ooeps);
+						float sy = fabsf(r1.y) > ooeps ? r1.y : (r1.y >= 0.0f ? ooeps : -ooeps);
+						float sz = fabsf(r1.z) > ooeps ? r1.z : (r1.z >= 0.0f ? ooeps : -ooeps);
+						const float len2 = __fadd_rn(__fadd_rn(__fmul_rn(sx, sx), __fmul_rn(sy, sy)), __fmul_rn(sz, sz));
+						const float inv = __frcp_rn(__fsqrt_rn(len2)); // 1/x correctly rounded == IEEE 1.0f / x
+						sx = __fmul_rn(sx, inv); sy = __fmul_rn(sy, inv); sz = __fmul_rn(sz, inv);
+						const uint32_t oi = 7u - ((sx < 0.0f ? 1u : 0u) | (sy < 0.0f ? 2u : 0u) | (sz < 0.0f ? 4u : 0u));
+						const uint32_t slot = lane_addr + (lane_addr & 0xffu) + kWarpStack; // region + stack + 16 * lane
+						sts128(slot, r0);
+						sts128(slot + 512u, make_float4(sx, sy, sz, __uint_as_float(oi)));
+						sts128(slot + 1024u, make_float4(__frcp_rn(sx), __frcp_rn(sy), __frcp_rn(sz), 0.0f));
+					}
+					__syncwarp();
+				}
+				const unsigned cand = stage_pos + (unsigned)__popc(idle & lt_mask);
+				const bool take = sp < 0 && cand < stage_cnt;
+				if (take) {
+					const uint32_t slot = (lane_addr & ~0xffu) + kWarpStack + cand * 16u;
+					const float4 a = lds128(slot), b = lds128(slot + 512u), c = lds128(slot + 1024u);
+					ray_idx = stage_base + cand;
+					ox = a.x; oy = a.y; oz = a.z; tmin = a.w;
+					dx = b.x; dy = b.y; dz = b.z; octinv = __float_as_uint(b.w);
+					idx = c.x; idy = c.y; idz = c.z;
+					hit_t = 1e9f; hit_idx = -1; hit_u = 0.0f; hit_v = 0.0f;
+					ng = make_uint2(0u, 0x80000000u);
+					tg = make_uint2(0u, 0u);
+					sp = 0;
+				}
+				const unsigned took = __ballot_sync(kFullMask, take);
+				stage_pos += (unsigned)__popc(took);
+				idle &= ~took;
+			}
+		} else
 		while (idle != 0 && !exhausted) {
 			if (pool_next >= pool_end) {
 				unsigned long long b = 0;
@@ -211,7 +304,7 @@ __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const Trac
 					const uint32_t base = ng.x;
 					ng.y &= ~(1u << bit);
 					if (ng.y > 0x00ffffffu) {
-						if (sp < kSmemStack) s_stack[sp][tid] = ng;
+						if (sp < kSmemStack) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(lane_addr + (uint32_t)sp * 256u), "r"(ng.x), "r"(ng.y) : "memory");
 						else if (sp < kSmemStack + kLocalStack) l_stack[sp - kSmemStack] = ng;
 						++sp;
 						if (STATS && (unsigned long long)sp > st_depth) st_depth = sp;
@@ -219,7 +312,7 @@ __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const Trac
 					if (STATS) ++st_nodes;
 					const uint32_t slot = (bit - 24u) ^ octinv;
 					const uint32_t rel = (uint32_t)__popc(imask & ~(0xffffffffu << slot));
-					const uint4 *np = p.nodes + (size_t)(base + rel) * 5u;
+					const uint4 *np = nodes_base + (size_t)(base + rel) * 5u;
 					const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
 
 					const float aix = __fmul_rn(__uint_as_float((n0.w & 0xffu) << 23), idx);
@@ -276,8 +369,8 @@ __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const Trac
 						const bool two = tg.y != 0u;
 						const uint32_t tr1 = tg.x + (uint32_t)(__ffs((int)tg.y) - 1);
 						tg.y &= tg.y - 1u; // no-op on 0
-						const float4 *wa = p.woop + (size_t)tr0 * 3u;
-						const float4 *wb = p.woop + (size_t)(two ? tr1 : tr0) * 3u;
+						const float4 *wa = woop_base + (size_t)tr0 * 3u;
+						const float4 *wb = woop_base + (size_t)(two ? tr1 : tr0) * 3u;
 						const float4 a0 = __ldg(wa), a1 = __ldg(wa + 1), a2 = __ldg(wa + 2);
 						const float4 b0 = __ldg(wb), b1 = __ldg(wb + 1), b2 = __ldg(wb + 2);
 						ADYPT_WOOP_TEST(tr0, a0, a1, a2);
@@ -287,7 +380,7 @@ __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const Trac
 				for (int batch = 0; tg.y != 0u && (TRI_BATCH == 0 || batch < TRI_BATCH); ++batch) { // :213-243
 					const uint32_t tr = tg.x + (uint32_t)(__ffs((int)tg.y) - 1);
 					tg.y &= tg.y - 1u;
-					const float4 *wp = p.woop + (size_t)tr * 3u;
+					const float4 *wp = woop_base + (size_t)tr * 3u;
 					const float4 m0 = __ldg(wp), m1 = __ldg(wp + 1), m2 = __ldg(wp + 2);
 					ADYPT_WOOP_TEST(tr, m0, m1, m2);
 					if (ANY && finished) break;
@@ -298,7 +391,8 @@ __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const Trac
 					if (sp == 0) finished = true;
 					else {
 						--sp;
-						ng = (sp < kSmemStack) ? s_stack[sp][tid] : l_stack[(sp - kSmemStack) < kLocalStack ? (sp - kSmemStack) : (kLocalStack - 1)];
+						if (sp < kSmemStack) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ng.x), "=r"(ng.y) : "r"(lane_addr + (uint32_t)sp * 256u) : "memory");
+						else ng = l_stack[(sp - kSmemStack) < kLocalStack ? (sp - kSmemStack) : (kLocalStack - 1)];
 					}
 				}
 

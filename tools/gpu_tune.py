@@ -15,6 +15,8 @@ def timed(fn, n=5):
     return min(ts), float(np.median(ts))
 
 def main():
+    if os.environ.get('TUNE_LIB'):  # an experimental build from tools/build_variant.py
+        A.LIB_PATH = os.path.abspath(os.environ['TUNE_LIB']); print('library', A.LIB_PATH)
     mesh = W.city(183, 1)
     t0 = time.time(); hs = host.build_scene(mesh); print('build %.1fs' % (time.time() - t0))
     sc = hs.upload(0)
@@ -28,9 +30,11 @@ def main():
     st = torch.cuda.current_stream().cuda_stream
     base = None
     res = {}
-    for variant in (0, 1, 5):
-        for thr in (24, 28, 32):
-            for ctas in (0,):
+    variants = tuple(int(v) for v in os.environ.get('TUNE_VARIANTS', '0,8').split(','))
+    thresholds = tuple(int(v) for v in os.environ.get('TUNE_THRESHOLDS', '24,28,30,32').split(','))
+    for variant in variants:
+        for thr in thresholds:
+            for ctas in (int(os.environ.get('TUNE_CTAS', '0')),):
                 sc.configure(ctas, thr, variant)
                 mn, md = timed(lambda: sc.trace_closest(d_rays, d_tri, d_t, d_uv, stream=st))
                 if base is None: base = d_tri.clone()
@@ -43,7 +47,7 @@ def main():
     mn, md = timed(lambda: sc.trace_closest(d_prim, d_tri[:1000000], d_t[:1000000], d_uv[:1000000], stream=st))
     print(f'C2-scene 1M primary rays: {mn:.3f} ms {1e3/mn:.0f} Mrays/s')
     occ = torch.empty(n, dtype=torch.uint8, device='cuda')
-    for v in (0, 1, 5):
+    for v in variants:
         sc.configure(0, best[1], v)
         mn, md = timed(lambda: sc.trace_any(d_rays, occ, stream=st))
         print(f'any-hit 8M variant {v}: {mn:.3f} ms {n/mn/1e3:.0f} Mrays/s')
