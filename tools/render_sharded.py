@@ -70,6 +70,9 @@ def main():
     tr.accumulate(0, 16)  # warm-up (allocations, clocks)
     tr.sync()
     if world > 1:
+        warm = torch.zeros_like(acc)  # NCCL sets its channels and buffers up at the first collective of a size class
+        dist.all_reduce(warm, op=dist.ReduceOp.SUM)
+        del warm
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
