@@ -18,7 +18,7 @@ BINDIR = os.path.join(HERE, "bin")
 CLI = os.path.join(BINDIR, "adypt_headless")
 
 CU_SOURCES = ["scene.cu", "tracer.cu", "group.cu"]
-CPP_SOURCES = ["hostmath.cpp", "exr.cpp", "host/bvh_build.cpp", "host/obj_loader.cpp", "host/host_api.cpp", "host/config.cpp", "host/image_decode.cpp", "host/jpeg_decode.cpp"]
+CPP_SOURCES = ["hostmath.cpp", "exr.cpp", "host/bvh_build.cpp", "host/obj_loader.cpp", "host/host_api.cpp", "host/config.cpp", "host/image_decode.cpp", "host/image_decode_more.cpp", "host/jpeg_decode.cpp"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -13,6 +13,8 @@ struct DecodedImage { // RGB8, top row first (what stbi_load(..., 3) returns)
 // PNG / JPEG / TGA file -> RGB8; false when the file is missing or in a format that is not decoded
 bool decode_image_file(const char *path, DecodedImage *out);
 bool decode_jpeg(const std::vector<uint8_t> &file, DecodedImage *out); // jpeg_decode.cpp
+// GIF / PSD / PIC / PNM / HDR (image_decode_more.cpp); *recognised = the file carries one of their signatures
+bool decode_rare_formats(const std::vector<uint8_t> &file, DecodedImage *out, bool *recognised);
 } // namespace host
 } // namespace adypt
 

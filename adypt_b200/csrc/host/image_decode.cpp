@@ -4,8 +4,8 @@
 // BMP (uncompressed, 4/8-bit palette, 16/24/32-bit) and TGA (true-colour, 15/16-bit, grey, grey+alpha,
 // colour-mapped; raw or RLE, either origin). Conversions to 3 channels follow
 // stb_image's rules (grey replicated, alpha dropped, 16-bit samples truncated to their high byte, 1/2/4-bit grey
-// scaled by 255/85/17). PSD/GIF/HDR/PNM are not decoded: such a texture fails to load, which the reference
-// handles by giving the material texture index -1 (OglScene.cpp:27-32).
+// scaled by 255/85/17). GIF, PSD, PIC, PGM / PPM and HDR live in image_decode_more.cpp. A file none of them accepts fails
+// to load, which the reference handles by giving the material texture index -1 (OglScene.cpp:27-32).
 #include <zlib.h>
 #include <cstdint>
 #include <cstdio>
@@ -392,6 +392,9 @@ bool decode_image_file(const char *path, DecodedImage *img)
 	if (decode_png(file, img)) return true;
 	if (file.size() > 2 && file[0] == 'B' && file[1] == 'M') return decode_bmp(file, img);
 	if (decode_jpeg(file, img)) return true;
+	bool recognised = false;
+	if (decode_rare_formats(file, img, &recognised)) return true; // GIF, PSD, PIC, PGM / PPM, HDR (image_decode_more.cpp)
+	if (recognised) return false;                                 // one of those, but corrupt: stb_image stops there too
 	return decode_tga(file, img); // TGA has no magic number: like stb_image, try it last, on the header's plausibility
 }
 
