@@ -48,6 +48,7 @@ constexpr int kLocalStack = 64 - kSmemStack;  // overflow entries (local memory)
 constexpr unsigned kPoolChunk = 256;  // most ray indices a warp takes per atomicAdd (small batches take fewer, see launch_trace)
 constexpr unsigned kFullMask = 0xffffffffu;
 
+
 __device__ __forceinline__ void sts128(uint32_t addr, float4 v)
 {
 	asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
@@ -141,6 +142,7 @@ template <bool ANY, bool STATS = false, int CVT_PLANES = 4, int MIN_CTAS = 8, in
 __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const TraceParams p)
 {
 	const uint32_t magic = p.magic;
+	constexpr int NODE_REPS = ANY ? 2 : 1;
 	// Shared memory, one region per warp: [stack: kSmemStack entries x 32 lanes x 8 B][stage: 3 rows x 32 entries x 16 B].
 	// Every address is formed from ONE register, lane_addr = region + 8 * lane (stack entry sp of this lane is at
 	// lane_addr + 256 * sp; 8-byte accesses of a warp are conflict-free), and so are the lane number and its lt-mask:
@@ -295,6 +297,13 @@ __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const Trac
 		unsigned busy;
 		do {
 			if (sp >= 0) {
+				bool finished = false;
+				// NODE_REPS node steps (with the pop a lane needs in between), then ONE triangle section: any-hit rays test
+				// few triangles, so the section runs for half as many rounds at twice the lanes (+7 %); for closest-hit
+				// rays the lanes that wait with their triangles through the second node step cost as much as that saves
+				// (measured 1.80 vs 1.76 ms), so they keep one node step per round.
+#pragma unroll 1
+				for (int rep = 0; rep < NODE_REPS; ++rep) {
 				if (TRI_BATCH > 0 && tg.y != 0u) {
 					// triangles left over from the previous round: no node step yet
 				} else if (ng.y > 0x00ffffffu) {
@@ -343,7 +352,15 @@ __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const Trac
 				// above 0x00ffffff at ray start and after every pop (only groups with inner hits are pushed), and a
 				// group that loses its last inner hit is replaced at the bottom of the same round.
 
-				bool finished = false;
+				if (rep + 1 < NODE_REPS && !finished && tg.y == 0u && ng.y <= 0x00ffffffu) { // pop between node steps
+					if (sp == 0) { finished = true; ng.y = 0u; }
+					else {
+						--sp;
+						if (sp < kSmemStack) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ng.x), "=r"(ng.y) : "r"(lane_addr + (uint32_t)sp * 256u) : "memory");
+						else ng = l_stack[(sp - kSmemStack) < kLocalStack ? (sp - kSmemStack) : (kLocalStack - 1)];
+					}
+				}
+				}
 				// Woop test of leaf reference TR with rows M0..M2 (:221-241)
 #define ADYPT_WOOP_TEST(TR, M0, M1, M2) \
 	do { \
