@@ -92,10 +92,8 @@ struct Parser {
 				++digits;
 				++p;
 			}
-		bool frac_or_exp = false;
 		if (p < end && *p == '.') {
 			++p;
-			frac_or_exp = true;
 			if (p >= end || *p < '0' || *p > '9') { ok = false; return; }
 			if (!use_double) {
 				while (p < end && *p >= '0' && *p <= '9') {
@@ -120,7 +118,6 @@ struct Parser {
 		int exp = 0;
 		if (p < end && (*p == 'e' || *p == 'E')) {
 			if (!use_double) { d = (double)i; use_double = true; }
-			frac_or_exp = true;
 			++p;
 			bool eneg = false;
 			if (p < end && (*p == '+' || *p == '-')) eneg = *p++ == '-';
@@ -146,7 +143,6 @@ struct Parser {
 			double r = e10 < -308 ? fast_path(fast_path(d, -308), e10 + 308) : fast_path(d, e10);
 			v.d = minus ? -r : r;
 			v.is_double = true;
-			(void)frac_or_exp;
 		} else {
 			v.is_double = false;
 			v.d = minus ? -(double)i : (double)i;

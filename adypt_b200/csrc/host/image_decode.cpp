@@ -231,7 +231,7 @@ bool decode_tga(const std::vector<uint8_t> &f, DecodedImage *img)
 			} else if (rgb16)
 				read_rgb16(px);
 			else
-				for (int j = 0; j < comp; ++j) px[j] = (uint8_t)u8();
+				for (int j = 0; j < comp && j < 4; ++j) px[j] = (uint8_t)u8();
 		}
 		memcpy(&data[i * comp], px, (size_t)comp);
 		--run;
