@@ -227,3 +227,47 @@ def test_fuzz_triangle_soups(A, cpu, seed):
     assert 0.05 < (g["tri"] >= 0).mean() < 0.99
     assert sc.trace_stats(rays)["max_stack"] == o["counters"]["max_stack"]
     assert sc.trace_stats(rays)["nodes"] == o["counters"]["nodes"] and sc.trace_stats(rays)["tris"] == o["counters"]["tris"]
+
+
+def test_stack_deeper_than_the_shared_memory_part(A, cpu):
+    """Clusters of triangles on a geometric progression of scales give a wide tree that is a long chain of nodes with
+    several inner children each; rays along the chain defer a sibling group at every level, so the traversal stack grows
+    past the 8 entries a lane keeps in shared memory (reference default stackSize: 12, unchecked) and uses the
+    local-memory part. Results and counters must still equal the oracle's."""
+    from adypt_b200 import host, workloads as W
+    levels, per, ratio = 120, 64, 1.25
+    rng = np.random.default_rng(3)
+    tris = []
+    for i in range(levels):
+        s = ratio ** i
+        c = np.array([3.0 * s, 0.0, 0.0])
+        for _ in range(per):
+            p = c + (rng.random(3) - 0.5) * s * 0.8
+            tris.append([p, p + (rng.random(3) - 0.5) * s * 0.3, p + (rng.random(3) - 0.5) * s * 0.3])
+    pos = np.array(tris, dtype=np.float32)
+    mats = host.materials_array(W.tiny_scene("strip").materials)
+    hs = host.HostScene.from_triangles(pos, np.zeros(len(pos), dtype=np.int32), mats).build_bvh()
+    n = 4000
+    rays = np.zeros((n, 8), dtype=np.float32)
+    rays[:, 0] = 3.0 * ratio ** (levels - 1) * 1.5
+    rays[:, 1:3] = (rng.random((n, 2)) - 0.5) * 0.2
+    rays[:, 3] = 1e-4
+    target = np.zeros((n, 3))
+    target[:, 0] = 3.0
+    target[:, 1:] = (rng.random((n, 2)) - 0.5) * 0.5
+    d = target - rays[:, :3]
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays[:, 4:7] = d
+    back = rays.copy()
+    back[:, 0] = 0.0
+    back[:, 4:7] = -d
+    rays = np.concatenate([rays, back])
+    woop = cpu.build_woop(hs.tris, hs.tri_indices)
+    o = cpu.trace_closest(hs.nodes, hs.tri_indices, woop, rays)
+    assert o["counters"]["max_stack"] > 12
+    sc = hs.upload(0)
+    assert_same_hits(sc.trace_closest(rays), o)
+    assert np.array_equal(sc.trace_any(rays), cpu.trace_any(hs.nodes, woop, rays)["occluded"])
+    st = sc.trace_stats(rays)
+    assert st["max_stack"] == o["counters"]["max_stack"]
+    assert st["nodes"] == o["counters"]["nodes"] and st["tris"] == o["counters"]["tris"]
