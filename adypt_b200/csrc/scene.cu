@@ -124,6 +124,10 @@ int launch_trace(adypt_scene *s, const float4 *d_rays, uint64_t n, int32_t *d_tr
 		unsigned long long chunk = n / (warps * 6ull);
 		chunk = (chunk / 32ull) * 32ull;
 		p.pool_chunk = (uint32_t)(chunk < 32ull ? 32ull : chunk > kPoolChunk ? kPoolChunk : chunk);
+		// guided tail: a request is 1 / 2^shift of the rays not yet handed out, 2^shift >= 4 x the warps (factors 1 / 2 / 4 / 8
+		// measured 1.810 / 1.770 / 1.733 / 1.739 ms on C2 against 1.823 ms with fixed-size pools)
+		p.guided_shift = 0;
+		while ((1ull << p.guided_shift) < warps * 4ull) ++p.guided_shift;
 	}
 	ADYPT_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned long long), stream));
 	// code-generation variants of the same algorithm (identical results); 0 = tuned default: 4 conversion planes on
@@ -460,6 +464,7 @@ int adypt_trace_stats(adypt_scene *s, const float *rays, uint64_t n, int memspac
 	p.stats = d_stats;
 	p.magic = 0x4B000000u;
 	p.pool_chunk = kPoolChunk;
+	p.guided_shift = 0;
 	p.refill_threshold = s->refill_threshold > 0 ? s->refill_threshold : 28;
 	ADYPT_CUDA(cudaMemset(p.counter, 0, sizeof(unsigned long long)));
 	trace_kernel<false, true><<<(unsigned)s->sm_count * 4u, kTraceBlock>>>(p);

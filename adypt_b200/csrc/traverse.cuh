@@ -36,7 +36,8 @@ struct TraceParams {
 	unsigned long long *stats;              // STATS kernels only: [0] nodes visited [1] triangles tested [2] hits [3] max stack depth
 	int refill_threshold;                   // leave the traversal loop when fewer lanes than this are busy
 	uint32_t magic;                         // 0x4B000000, passed as data so ptxas keeps it in a register (see byte_to_float)
-	uint32_t pool_chunk;                    // ray indices a warp takes per atomicAdd (multiple of 32, <= kPoolChunk)
+	uint32_t pool_chunk;                    // most ray indices a warp takes per atomicAdd (multiple of 32, <= kPoolChunk)
+	uint32_t guided_shift;                  // a warp asks for (rays not yet handed out) >> guided_shift, within [32, pool_chunk]
 };
 
 constexpr int kTraceBlock = 128;      // threads per CTA
@@ -58,6 +59,14 @@ __device__ __forceinline__ float4 lds128(uint32_t addr)
 	float4 v;
 	asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
 	return v;
+}
+
+// Guided self-scheduling of the ray pools: with a fixed 256-ray pool the warps of a launch finish up to one pool (~0.25 ms
+// on C2) apart and the SMs idle through that tail; asking for a share of what is LEFT makes the last pools 32 rays long.
+__device__ __forceinline__ uint32_t next_chunk(unsigned long long left, uint32_t shift, uint32_t most)
+{
+	const unsigned long long share = (left >> shift) & ~31ull;
+	return share >= most ? most : (share < 32ull ? 32u : (uint32_t)share);
 }
 
 __device__ __forceinline__ float dot3_fma(float ax, float ay, float az, const float4 m)
@@ -169,6 +178,7 @@ __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const Trac
 	// warp-uniform pool of ray indices
 	unsigned long long pool_next = 0, pool_end = 0;
 	bool exhausted = false;
+	uint32_t my_chunk = p.pool_chunk; // size of this warp's next request (guided: shrinks towards the end of the batch)
 	// STAGED: entries [stage_pos, stage_cnt) of the warp's 32-entry stage hold rays stage_base + entry, set up and untaken
 	unsigned long long stage_base = 0;
 	unsigned stage_pos = 0, stage_cnt = 0;
@@ -207,11 +217,12 @@ __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const Trac
 					if (exhausted) break;
 					if (pool_next >= pool_end) {
 						unsigned long long b = 0;
-						if (lane == 0) b = atomicAdd(p.counter, (unsigned long long)p.pool_chunk);
+						if (lane == 0) b = atomicAdd(p.counter, (unsigned long long)my_chunk);
 						b = __shfl_sync(kFullMask, b, 0);
 						if (b >= n_rays) { exhausted = true; break; }
 						pool_next = b;
-						pool_end = (b + p.pool_chunk < n_rays) ? b + p.pool_chunk : n_rays;
+						pool_end = (b + my_chunk < n_rays) ? b + my_chunk : n_rays;
+						my_chunk = next_chunk(n_rays - pool_end, p.guided_shift, p.pool_chunk);
 					}
 					const unsigned long long left = pool_end - pool_next;
 					stage_cnt = left < 32ull ? (unsigned)left : 32u;
@@ -260,11 +271,12 @@ __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const Trac
 		while (idle != 0 && !exhausted) {
 			if (pool_next >= pool_end) {
 				unsigned long long b = 0;
-				if (lane == 0) b = atomicAdd(p.counter, (unsigned long long)p.pool_chunk);
+				if (lane == 0) b = atomicAdd(p.counter, (unsigned long long)my_chunk);
 				b = __shfl_sync(kFullMask, b, 0);
 				if (b >= n_rays) { exhausted = true; break; }
 				pool_next = b;
-				pool_end = (b + p.pool_chunk < n_rays) ? b + p.pool_chunk : n_rays;
+				pool_end = (b + my_chunk < n_rays) ? b + my_chunk : n_rays;
+				my_chunk = next_chunk(n_rays - pool_end, p.guided_shift, p.pool_chunk);
 			}
 			const unsigned long long cand = pool_next + __popc(idle & lt_mask);
 			const bool take = sp < 0 && cand < pool_end;
