@@ -178,7 +178,6 @@ __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const Trac
 	// warp-uniform pool of ray indices
 	unsigned long long pool_next = 0, pool_end = 0;
 	bool exhausted = false;
-	uint32_t my_chunk = p.pool_chunk; // size of this warp's next request (guided: shrinks towards the end of the batch)
 	// STAGED: entries [stage_pos, stage_cnt) of the warp's 32-entry stage hold rays stage_base + entry, set up and untaken
 	unsigned long long stage_base = 0;
 	unsigned stage_pos = 0, stage_cnt = 0;
@@ -217,12 +216,12 @@ __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const Trac
 					if (exhausted) break;
 					if (pool_next >= pool_end) {
 						unsigned long long b = 0;
-						if (lane == 0) b = atomicAdd(p.counter, (unsigned long long)my_chunk);
+						const uint32_t request = next_chunk(n_rays - pool_end, p.guided_shift, p.pool_chunk); // pool_end: where this warp's last pool ended
+						if (lane == 0) b = atomicAdd(p.counter, (unsigned long long)request);
 						b = __shfl_sync(kFullMask, b, 0);
 						if (b >= n_rays) { exhausted = true; break; }
 						pool_next = b;
-						pool_end = (b + my_chunk < n_rays) ? b + my_chunk : n_rays;
-						my_chunk = next_chunk(n_rays - pool_end, p.guided_shift, p.pool_chunk);
+						pool_end = (b + request < n_rays) ? b + request : n_rays;
 					}
 					const unsigned long long left = pool_end - pool_next;
 					stage_cnt = left < 32ull ? (unsigned)left : 32u;
@@ -271,12 +270,12 @@ __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const Trac
 		while (idle != 0 && !exhausted) {
 			if (pool_next >= pool_end) {
 				unsigned long long b = 0;
-				if (lane == 0) b = atomicAdd(p.counter, (unsigned long long)my_chunk);
+				const uint32_t request = next_chunk(n_rays - pool_end, p.guided_shift, p.pool_chunk);
+				if (lane == 0) b = atomicAdd(p.counter, (unsigned long long)request);
 				b = __shfl_sync(kFullMask, b, 0);
 				if (b >= n_rays) { exhausted = true; break; }
 				pool_next = b;
-				pool_end = (b + my_chunk < n_rays) ? b + my_chunk : n_rays;
-				my_chunk = next_chunk(n_rays - pool_end, p.guided_shift, p.pool_chunk);
+				pool_end = (b + request < n_rays) ? b + request : n_rays;
 			}
 			const unsigned long long cand = pool_next + __popc(idle & lt_mask);
 			const bool take = sp < 0 && cand < pool_end;
