@@ -148,10 +148,6 @@ int launch_trace(adypt_scene *s, const float4 *d_rays, uint64_t n, int32_t *d_tr
 	case 6: trace_kernel<false, false, 5, 8, 12><<<grid, kTraceBlock, 0, stream>>>(p); break;
 	case 7: trace_kernel<false, false, 4, 8, 1><<<grid, kTraceBlock, 0, stream>>>(p); break;
 	case 8: trace_kernel<false, false, 4, 8, 12, false><<<grid, kTraceBlock, 0, stream>>>(p); break; // ray set-up at refill time
-#ifdef ADYPT_EXPERIMENT_OCC
-	case 9: trace_kernel<false, false, 4, 7, 12, true><<<grid, kTraceBlock, 0, stream>>>(p); break;
-	case 10: trace_kernel<false, false, 4, 6, 12, true><<<grid, kTraceBlock, 0, stream>>>(p); break;
-#endif
 	default: trace_kernel<false><<<grid, kTraceBlock, 0, stream>>>(p); break;
 	}
 	count_launch();
@@ -371,7 +367,7 @@ int adypt_trace_configure(adypt_scene *s, int ctas_per_sm, int refill_threshold,
 {
 	return guarded([&]() -> int {
 	if (!s) return fail(ADYPT_EINVAL, "scene is NULL");
-	if (ctas_per_sm < 0 || refill_threshold < 0 || refill_threshold > 32 || variant < 0 || variant > 10) return fail(ADYPT_EINVAL, "bad tuning value");
+	if (ctas_per_sm < 0 || refill_threshold < 0 || refill_threshold > 32 || variant < 0 || variant > 8) return fail(ADYPT_EINVAL, "bad tuning value");
 	s->ctas_per_sm = ctas_per_sm;
 	s->refill_threshold = refill_threshold;
 	s->variant = variant;
