@@ -13,10 +13,11 @@ for i, l in enumerate(out):
         m2 = re.match(r"\s+/\* 0x([0-9a-f]{16}) \*/", out[i + 1])
         hi = int(m2.group(1), 16)
         ins.append((m.group(2).strip(), (hi >> 41) & 0xF, (hi >> 45) & 1, (hi >> 52) & 0x3F))
-idx = [k for k, (t, *_r) in enumerate(ins) if t.split()[-0].startswith("I2F.U8") or " I2F.U8" in t or t.startswith("I2F.U8")]
+idx = [k for k, (t, *_r) in enumerate(ins) if "I2F.U8" in t]
 a, b = idx[0], idx[-1]
-# node step = from the node's first LDG before the first I2F to the last LOP3 writing the hit mask; approximate by a window
-lo = max(k for k in range(a) if ins[k][0].startswith("LDC.64")) if any(ins[k][0].startswith("LDC.64") for k in range(a)) else a
+# node step = from the load of the node array's base (the LDC.64 before the first conversion) to the BSYNC that closes it
+before = [k for k in range(a) if ins[k][0].startswith("LDC.64")]
+lo = before[-1] if before else a
 hi_ = next(k for k in range(b, len(ins)) if ins[k][0].startswith("BSYNC"))
 def summ(name, r):
     seg = ins[r[0]:r[1]]
