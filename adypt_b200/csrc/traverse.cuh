@@ -389,6 +389,25 @@ __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const Trac
 			else { hit_u = tu; hit_v = tv; hit_idx = (int32_t)(TR); } \
 		} \
 	} while (0)
+#define ADYPT_WOOP_EVAL(M0, M1, M2, TT, TU, TV) \
+	do { \
+		const float toz = __fsub_rn(M0.w, dot3_fma(ox, oy, oz, M0)); \
+		const float tidz = __frcp_rn(dot3_fma(dx, dy, dz, M0)); \
+		TT = __fmul_rn(toz, tidz); \
+		const float tox = __fadd_rn(M1.w, dot3_fma(ox, oy, oz, M1)); \
+		TU = __fmaf_rn(TT, dot3_fma(dx, dy, dz, M1), tox); \
+		const float toy = __fadd_rn(M2.w, dot3_fma(ox, oy, oz, M2)); \
+		TV = __fmaf_rn(TT, dot3_fma(dx, dy, dz, M2), toy); \
+	} while (0)
+#define ADYPT_WOOP_ACCEPT(TR, TT, TU, TV) \
+	do { \
+		if (STATS) ++st_tris; \
+		if (TT > tmin && TT < hit_t && TU >= 0.0f && TU <= 1.0f && TV >= 0.0f && __fadd_rn(TU, TV) <= 1.0f) { \
+			hit_t = TT; \
+			if (ANY) finished = true; /* :480-483 */ \
+			else { hit_u = TU; hit_v = TV; hit_idx = (int32_t)(TR); } \
+		} \
+	} while (0)
 				if (TRI_BATCH == 12) {
 					// batch of two with both fetches in flight before the first test
 					if (tg.y != 0u) {
@@ -401,8 +420,19 @@ __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const Trac
 						const float4 *wb = woop_base + (size_t)(two ? tr1 : tr0) * 3u;
 						const float4 a0 = __ldg(wa), a1 = __ldg(wa + 1), a2 = __ldg(wa + 2);
 						const float4 b0 = __ldg(wb), b1 = __ldg(wb + 1), b2 = __ldg(wb + 2);
-						ADYPT_WOOP_TEST(tr0, a0, a1, a2);
-						if (two && !(ANY && finished)) ADYPT_WOOP_TEST(tr1, b0, b1, b2);
+						if (!ANY) {
+							// both triangles' t, u, v first (they do not depend on hit_t, so ptxas can interleave the two chains;
+							// a lane with one triangle evaluates it twice, wb == wa), then the acceptance tests in the reference's
+							// order. -1 % time; any-hit rays mostly stop at their first triangle and keep the sequential form.
+							float tt0, tu0, tv0, tt1, tu1, tv1;
+							ADYPT_WOOP_EVAL(a0, a1, a2, tt0, tu0, tv0);
+							ADYPT_WOOP_EVAL(b0, b1, b2, tt1, tu1, tv1);
+							ADYPT_WOOP_ACCEPT(tr0, tt0, tu0, tv0);
+							if (two) ADYPT_WOOP_ACCEPT(tr1, tt1, tu1, tv1);
+						} else {
+							ADYPT_WOOP_TEST(tr0, a0, a1, a2);
+							if (two && !finished) ADYPT_WOOP_TEST(tr1, b0, b1, b2);
+						}
 					}
 				} else
 				for (int batch = 0; tg.y != 0u && (TRI_BATCH == 0 || batch < TRI_BATCH); ++batch) { // :213-243
@@ -414,6 +444,8 @@ __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const Trac
 					if (ANY && finished) break;
 				}
 #undef ADYPT_WOOP_TEST
+#undef ADYPT_WOOP_EVAL
+#undef ADYPT_WOOP_ACCEPT
 
 				if (!finished && (TRI_BATCH == 0 || tg.y == 0u) && ng.y <= 0x00ffffffu) { // :245-250
 					if (sp == 0) finished = true;
