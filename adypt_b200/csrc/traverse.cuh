@@ -103,7 +103,7 @@ __device__ __forceinline__ float byte_to_float(uint32_t word, uint32_t magic)
 
 // one group of four children (one 32-bit lane of each quantised plane), traversal.glsl:86-143 / :145-202
 template <int K, int CVT_PLANES>
-__device__ __forceinline__ uint32_t test_child(uint32_t child_bits4, uint32_t bit_index4, uint32_t s_lox, uint32_t s_loy, uint32_t s_loz,
+__device__ __forceinline__ uint32_t test_child(uint32_t meta_oct4, uint32_t s_lox, uint32_t s_loy, uint32_t s_loz,
                                                uint32_t s_hix, uint32_t s_hiy, uint32_t s_hiz, float aix, float aiy, float aiz,
                                                float aox, float aoy, float aoz, float tmin, float hit_t, uint32_t magic)
 {
@@ -116,9 +116,10 @@ __device__ __forceinline__ uint32_t test_child(uint32_t child_bits4, uint32_t bi
 	const float ctmin = fmaxf(fmaxf(txmin, tymin), fmaxf(tzmin, tmin));
 	const float ctmax = fminf(fminf(txmax, tymax), fminf(tzmax, hit_t));
 	if (ctmin <= ctmax) {
-		const uint32_t bits = (child_bits4 >> (8 * K)) & 0xffu;
-		const uint32_t idx = (bit_index4 >> (8 * K)) & 0xffu;
-		return bits << idx;
+		// the child's meta byte (count bits 7..5, bit index 4..0, already XOR-ed with the octant for inner children),
+		// zero-extended by one PRMT; the funnel shift takes its amount modulo 32, so the index needs no mask
+		const uint32_t b = __byte_perm(meta_oct4, 0u, 0x4440u | K);
+		return __funnelshift_l(0u, b >> 5, b);
 	}
 	return 0u;
 }
@@ -130,9 +131,8 @@ __device__ __forceinline__ uint32_t test_children4(uint32_t meta4, uint32_t octi
                                                    float tmin, float hit_t, uint32_t magic)
 {
 	const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-	const uint32_t bit_index4 = (meta4 ^ (octinv4 & ((is_inner4 >> 4) * 0xffu))) & 0x1f1f1f1fu;
-	const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
-#define ADYPT_CHILD(K) test_child<K, CVT_PLANES>(child_bits4, bit_index4, s_lox, s_loy, s_loz, s_hix, s_hiy, s_hiz, aix, aiy, aiz, aox, aoy, aoz, tmin, hit_t, magic)
+	const uint32_t meta_oct4 = meta4 ^ (octinv4 & ((is_inner4 >> 4) * 0xffu)); // octinv only touches index bits 2..0 of inner children
+#define ADYPT_CHILD(K) test_child<K, CVT_PLANES>(meta_oct4, s_lox, s_loy, s_loz, s_hix, s_hiy, s_hiz, aix, aiy, aiz, aox, aoy, aoz, tmin, hit_t, magic)
 	return ADYPT_CHILD(0) | ADYPT_CHILD(1) | ADYPT_CHILD(2) | ADYPT_CHILD(3);
 #undef ADYPT_CHILD
 }
