@@ -159,7 +159,7 @@ def run_reference(args, rank, world):
     dt = (time.perf_counter() - t0) / args.steps
     v = n / dt / 1e6
     sample = f"first {n} of the {rays.shape[0]} rays per step, {cores} threads"
-    cfg = workload_config(rays.shape[0], {"triangles": int(mesh.n_tris)})
+    cfg = workload_config(rays.shape[0], {"triangles": int(mesh.n_tris), "timing": "wall clock around the timed steps on the host cores (no GPU work in this arm)"})
     emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
