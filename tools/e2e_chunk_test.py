@@ -1,5 +1,6 @@
+"""Times adypt_trace_closest on pinned HOST arrays (the e2e leg of bench.py) for the current ADYPT_HOST_CHUNK (GPU box only)."""
 import os, sys, time, numpy as np, torch
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import adypt_b200 as A
 from adypt_b200 import host, workloads as W
 mesh = W.city(183, 1); hs = host.build_scene(mesh); sc = hs.upload(0)
