@@ -366,7 +366,7 @@ bool decode_psd(const std::vector<uint8_t> &file, DecodedImage *img)
 	const int pixel_count = w * h;
 	std::vector<uint8_t> out((size_t)pixel_count * 4, 0);
 	if (compression) {
-		s.skip(h * channels * 2); // per-row byte counts
+		s.skip((int)(uint32_t)((uint64_t)h * (uint64_t)channels * 2u)); // per-row byte counts (wraps like stb_image's int product)
 		for (int ch = 0; ch < 4; ++ch) {
 			uint8_t *p = out.data() + ch;
 			if (ch >= channels) {
