@@ -23,6 +23,9 @@ CPP_SOURCES = ["hostmath.cpp", "exr.cpp", "host/bvh_build.cpp", "host/obj_loader
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-fmad=false", "-DADYPT_NO_FMAD", "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off",
+    # host code only: signed overflow wraps. The file decoders follow stb_image's int arithmetic (IDCT, colour conversion),
+    # which overflows on corrupt input; with -fwrapv that is defined behaviour and gives what stb_image computes on x86
+    "-Xcompiler", "-fwrapv",
 ]
 
 
