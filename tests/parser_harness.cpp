@@ -31,15 +31,24 @@ int main(int, char **argv)
 {
 	DIR *d = opendir(argv[1]);
 	if (!d) return 2;
-	int ok = 0, bad = 0;
+	int ok = 0, bad = 0, built = 0;
 	while (dirent *e = readdir(d)) {
 		if (e->d_name[0] == '.') continue;
 		const std::string p = std::string(argv[1]) + "/" + e->d_name;
 		bool good = false;
 		try {
 			if (ends_with(p, ".obj")) {
-				adypt_host_scene scene;
-				good = adypt::host::load_obj(p.c_str(), &scene).empty();
+				// through the C-ABI: load, then build the SBVH + wide BVH over whatever coordinates the file held (NaN, inf, ...)
+				adypt_host_scene *scene = nullptr;
+				good = adypt_host_scene_load_obj(p.c_str(), &scene) == ADYPT_OK;
+				if (good) {
+					adypt_bvh_config cfg;
+					cfg.max_spatial_depth = 48;
+					cfg.triangle_sah = 0.3f;
+					cfg.node_sah = 1.0f;
+					if (adypt_host_scene_build_bvh(scene, &cfg) == ADYPT_OK) ++built;
+				}
+				adypt_host_scene_destroy(scene);
 			} else if (ends_with(p, ".config")) {
 				adypt_instance_config c;
 				good = adypt_config_load(p.c_str(), &c) == ADYPT_OK;
@@ -57,6 +66,6 @@ int main(int, char **argv)
 		}
 		good ? ++ok : ++bad;
 	}
-	printf("accepted %d refused %d\n", ok, bad);
+	printf("accepted %d refused %d built %d\n", ok, bad, built);
 	return 0;
 }

@@ -1,6 +1,7 @@
 """The host-side file parsers (OBJ / MTL, .config, .bvh cache) under AddressSanitizer + UndefinedBehaviorSanitizer: random
 OBJ / MTL pairs, and byte-mutated, truncated and padded copies of valid .config and .bvh files. These files come from
-users, so whatever they hold the parsers may refuse them but must not read or write out of bounds. No GPU needed:
+users, so whatever they hold the parsers may refuse them but must not read or write out of bounds; every OBJ that loads
+also goes through the SBVH + wide-BVH builder with whatever coordinates it held (NaN, inf, huge). No GPU needed:
 tests/parser_harness.cpp links the host sources only."""
 import json
 import os
@@ -53,7 +54,7 @@ def test_parsers_are_clean_under_asan_and_ubsan(tmp_path):
     n = 0
     # OBJ / MTL: random pairs in odd spellings (the generator of the parity fuzz test), each next to its own m.mtl
     rnd = random.Random(7)
-    for trial in range(150):
+    for trial in range(100):
         d = tmp_path / f"obj{trial}"
         d.mkdir()
         p = _fuzz_obj(rnd, str(d))
@@ -61,7 +62,7 @@ def test_parsers_are_clean_under_asan_and_ubsan(tmp_path):
         os.replace(os.path.join(str(d), "m.mtl"), str(corpus / "m.mtl"))  # the last one stays: every t*.obj names m.mtl
         (corpus / f"{n:05d}.obj").write_bytes(data)
         n += 1
-        for m in _mutations(data, rng, 3):
+        for m in _mutations(data, rng, 1):
             (corpus / f"{n:05d}.obj").write_bytes(m)
             n += 1
     # .config: the valid file and mutations of its text
@@ -85,4 +86,5 @@ def test_parsers_are_clean_under_asan_and_ubsan(tmp_path):
     r = subprocess.run([exe, str(corpus)], capture_output=True, text=True, env=env, timeout=900)
     assert r.returncode == 0, (r.stdout[-500:], r.stderr[-3000:])
     accepted = int(r.stdout.split("accepted")[1].split()[0])
-    assert accepted >= 100 and n > 1000, (r.stdout, n)
+    built = int(r.stdout.split("built")[1].split()[0])
+    assert accepted >= 100 and built >= 80 and n > 800, (r.stdout, n)
