@@ -736,3 +736,21 @@ def test_decoders_are_clean_under_asan_and_ubsan(tmp_path):
     r = subprocess.run([exe, str(corpus)], capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0, (r.stdout[-500:], r.stderr[-2000:])
     assert "decoded" in r.stdout and n > 900
+
+
+def test_decoders_match_committed_stb_image_answers(tmp_path):
+    """tests/golden/texture_files.npz (made by tests/golden/make_texture_golden.py from the reference's own stb_image):
+    62 image files in all nine formats with the pixels stbi_load returned for them -- or its refusal. Needs no reference."""
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "texture_files.npz"))
+    names = [str(n) for n in z["names"]]
+    formats = set()
+    for i, name in enumerate(names):
+        got = _decode_ours(tmp_path, z[f"file_{i}"].tobytes())
+        shape = tuple(int(v) for v in z[f"shape_{i}"])
+        if shape == (0, 0, 0):
+            assert got is None, name
+            continue
+        assert got is not None and got.shape == shape, name
+        assert np.array_equal(got.reshape(-1), z[f"pixels_{i}"]), name
+        formats.add(name.rsplit(".", 1)[1])
+    assert {"png", "jpg", "bmp", "tga", "gif", "psd", "pic", "ppm", "pgm", "hdr"} <= formats, formats
