@@ -105,6 +105,22 @@ int main(int argc, char **argv)
 		else config = a;
 	}
 	if (!config || spp < 0) return usage();
+	{ // --gpus / --device are checked against the box before the (expensive) OBJ load and BVH build
+		int n_devices = 0;
+		if (adypt_device_count(&n_devices) != ADYPT_OK || n_devices < 1) {
+			fprintf(stderr, "adypt_headless: no CUDA device (%s)\n", adypt_last_error());
+			return 1;
+		}
+		const int most = n_devices < 64 ? n_devices : 64;
+		if (gpus < 1 || gpus > most) {
+			fprintf(stderr, "adypt_headless: --gpus %d is outside 1..%d (devices on this box, at most 64)\n", gpus, most);
+			return 2;
+		}
+		if (device < 0 || device >= n_devices) {
+			fprintf(stderr, "adypt_headless: --device %d is outside 0..%d\n", device, n_devices - 1);
+			return 2;
+		}
+	}
 
 	if (gpus > 1 && !viewer) return render_on_group(config, spp, gpus, out, fp16, seed, cache, sun_visibility, rr_start);
 

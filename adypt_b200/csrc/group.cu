@@ -151,21 +151,32 @@ int adypt_group_render(adypt_group *g, int32_t total_spp)
 	const int n_blocks = (total_spp + L - 1) / L;
 	for (int k = 0; k < n_blocks; ++k) {
 		const int first = k * L, cnt = (first + L <= total_spp) ? L : total_spp - first;
-		ADYPT_TRY(adypt_tracer_accumulate(g->tracers[(size_t)(k % n)], first, cnt));
+		const int rc = adypt_tracer_accumulate(g->tracers[(size_t)(k % n)], first, cnt);
+		if (rc != ADYPT_OK) {
+			const std::string why = adypt_last_error();
+			for (adypt_tracer *t : g->tracers) adypt_tracer_sync(t); // the other devices' queued blocks finish before we report
+			return fail(rc, why);
+		}
 	}
 	if (n > 1) {
-		ADYPT_NCCL(g_nccl.GroupStart());
-		float *root = nullptr;
+		// everything that can fail on our side is fetched BEFORE the NCCL group opens; inside it an early return would
+		// leave the thread's group open and every later NCCL call of the process queued for ever
+		std::vector<float *> bufs((size_t)n, nullptr);
+		std::vector<cudaStream_t> streams((size_t)n, nullptr);
 		uint64_t count = 0;
-		ADYPT_TRY(adypt_tracer_sum_buffer(g->tracers[0], &root, &count));
 		for (int i = 0; i < n; ++i) {
-			float *buf = nullptr;
-			ADYPT_TRY(adypt_tracer_sum_buffer(g->tracers[(size_t)i], &buf, nullptr));
-			cudaStream_t st = nullptr;
-			ADYPT_TRY(adypt_tracer_stream(g->tracers[(size_t)i], (void **)&st));
-			ADYPT_NCCL(g_nccl.Reduce(buf, i == 0 ? root : buf, (size_t)count, ncclFloat, ncclSum, 0, g->comms[(size_t)i], st));
+			ADYPT_TRY(adypt_tracer_sum_buffer(g->tracers[(size_t)i], &bufs[(size_t)i], &count));
+			ADYPT_TRY(adypt_tracer_stream(g->tracers[(size_t)i], (void **)&streams[(size_t)i]));
 		}
-		ADYPT_NCCL(g_nccl.GroupEnd());
+		ADYPT_NCCL(g_nccl.GroupStart());
+		ncclResult_t first_error = ncclSuccess;
+		for (int i = 0; i < n && first_error == ncclSuccess; ++i)
+			first_error = g_nccl.Reduce(bufs[(size_t)i], bufs[(size_t)i], (size_t)count, ncclFloat, ncclSum, 0, g->comms[(size_t)i], streams[(size_t)i]);
+		const ncclResult_t end = g_nccl.GroupEnd(); // always closed
+		if (first_error != ncclSuccess || end != ncclSuccess) {
+			for (adypt_tracer *t : g->tracers) adypt_tracer_sync(t); // nobody keeps running with a half-reduced buffer
+			return fail(ADYPT_ECUDA, std::string("ncclReduce: ") + g_nccl.GetErrorString(first_error != ncclSuccess ? first_error : end));
+		}
 	}
 	ADYPT_TRY(adypt_tracer_resolve_sum(g->tracers[0]));
 	for (adypt_tracer *t : g->tracers) ADYPT_TRY(adypt_tracer_sync(t));

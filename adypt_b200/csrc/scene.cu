@@ -92,7 +92,7 @@ __global__ void build_woop_kernel(const uint8_t *__restrict__ tris, const int32_
 
 // ------------------------------------------------------------------------------------------------
 int launch_trace(adypt_scene *s, const float4 *d_rays, uint64_t n, int32_t *d_tri, float *d_t, float2 *d_uv, uint8_t *d_occ,
-                 cudaStream_t stream, const unsigned long long *d_n)
+                 cudaStream_t stream, const unsigned long long *d_n, unsigned long long *d_counter)
 {
 	if (n == 0) return ADYPT_OK;
 	const bool any = d_occ != nullptr;
@@ -109,7 +109,7 @@ int launch_trace(adypt_scene *s, const float4 *d_rays, uint64_t n, int32_t *d_tr
 	p.out_occ = d_occ;
 	p.stats = nullptr;
 	p.magic = 0x4B000000u;
-	p.counter = s->d_counters + (s->counter_cursor++ % kCounterRing);
+	p.counter = d_counter ? d_counter : s->d_counters + (s->counter_cursor.fetch_add(1u) % kCounterRing);
 	p.refill_threshold = s->refill_threshold > 0 ? s->refill_threshold : 28;
 	int per_sm = s->ctas_per_sm > 0 ? s->ctas_per_sm : (any ? s->occ_any : s->occ_closest);
 	if (per_sm < 1) per_sm = 1;
@@ -238,25 +238,41 @@ int adypt_scene_create(const adypt_scene_desc *d, adypt_scene **out)
 		const Node *nodes = (const Node *)d->nodes;
 		for (uint32_t i = 0; i < d->n_nodes; ++i) {
 			const Node &n = nodes[i];
-			uint32_t n_inner = 0, max_tri = 0;
+			uint32_t n_inner = 0, max_tri = 0, inner_ordinals = 0;
 			const uint32_t metas[2] = {n.meta_lo, n.meta_hi};
 			for (int k = 0; k < 8; ++k) {
 				const uint32_t m = (metas[k >> 2] >> (8 * (k & 3))) & 0xffu;
 				if (m == 0) continue;
-				if ((m & 0x1fu) >= 24u) ++n_inner;
+				if ((m & 0x1fu) >= 24u) { ++n_inner; inner_ordinals |= 1u << ((m & 0x1fu) - 24u); }
 				else {
 					const uint32_t cnt = __builtin_popcount(m >> 5), end = (m & 0x1fu) + cnt;
 					if (end > max_tri) max_tri = end;
 				}
 			}
+			// the kernel addresses an inner child as child_base + popc(imask & lowmask(ordinal)) (traversal.glsl:61-67)
+			const uint32_t imask = n.head_w >> 24;
 			if (n_inner && (uint64_t)n.child_base + n_inner > d->n_nodes) return fail(ADYPT_EINVAL, "node child index out of range");
+			if ((inner_ordinals & ~imask) != 0u) return fail(ADYPT_EINVAL, "node has an inner child that its imask does not cover");
+			if (imask && (uint64_t)n.child_base + (uint32_t)__builtin_popcount(imask) > d->n_nodes) return fail(ADYPT_EINVAL, "node imask reaches past the node array");
 			if (max_tri && (uint64_t)n.tri_base + max_tri > d->n_refs) return fail(ADYPT_EINVAL, "node triangle index out of range");
 		}
 	}
 
+	// Shading indexes materials[triangle.matid] (pathtracer.glsl:73-76). The OBJ ingest gives faces without a (known) material
+	// id -1 like the reference (Scene.cpp:52); a GL buffer read shrugs that off, a CUDA one faults. Such a scene can still be
+	// traversed; tracers refuse it (adypt_tracer_create).
+	int64_t bad_matid_tri = -1;
+	if (d->triangles && d->n_mats)
+		for (uint32_t i = 0; i < d->n_tris; ++i) {
+			int32_t matid;
+			memcpy(&matid, (const uint8_t *)d->triangles + (size_t)i * 100u + 96u, 4);
+			if (matid < 0 || (uint32_t)matid >= d->n_mats) { bad_matid_tri = (int64_t)i; break; }
+		}
+
 	DeviceGuard g(d->device);
 	if (!g.ok) return fail(ADYPT_ENODEV, "cudaSetDevice failed");
 	adypt_scene *s = new adypt_scene;
+	s->bad_matid_tri = bad_matid_tri;
 	s->device = d->device;
 	s->n_nodes = d->n_nodes;
 	s->n_refs = d->n_refs;
@@ -286,7 +302,7 @@ int adypt_scene_create(const adypt_scene_desc *d, adypt_scene **out)
 		if (e != cudaSuccess) { free_scene(s); return fail(ADYPT_ECUDA, std::string("build_woop_kernel: ") + cudaGetErrorString(e)); }
 	}
 #undef UP
-	if (cudaMalloc((void **)&s->d_counters, (kCounterRing + 4) * sizeof(unsigned long long)) != cudaSuccess) { free_scene(s); return fail(ADYPT_ENOMEM, "cudaMalloc counters"); }
+	if (cudaMalloc((void **)&s->d_counters, kCounterSlots * sizeof(unsigned long long)) != cudaSuccess) { free_scene(s); return fail(ADYPT_ENOMEM, "cudaMalloc counters"); }
 	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->occ_closest, trace_kernel<false>, kTraceBlock, 0);
 	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->occ_any, trace_kernel<true>, kTraceBlock, 0);
 	*out = s;
@@ -399,16 +415,17 @@ static int trace_host(adypt_scene *s, const float *rays, uint64_t n, int32_t *tr
 	for (uint64_t b = 0; b < n; b += chunk, ++k) {
 		const uint64_t m = (n - b < chunk) ? n - b : chunk;
 		cudaStream_t st = s->pipe[k % 3];
+		unsigned long long *ctr = s->d_counters + kCounterPipe + (k % 3); // owned by that stream
 		float4 *d_in = s->stage_in.as<float4>() + 2 * b;
 		ADYPT_CUDA(cudaMemcpyAsync(d_in, rays + 8 * b, (size_t)m * 32u, cudaMemcpyHostToDevice, st));
 		if (occ) {
-			ADYPT_TRY(launch_trace(s, d_in, m, nullptr, nullptr, nullptr, o + o_occ + b, st));
+			ADYPT_TRY(launch_trace(s, d_in, m, nullptr, nullptr, nullptr, o + o_occ + b, st, nullptr, ctr));
 			ADYPT_CUDA(cudaMemcpyAsync(occ + b, o + o_occ + b, (size_t)m, cudaMemcpyDeviceToHost, st));
 		} else {
 			int32_t *d_tri = (int32_t *)(o + o_tri) + b;
 			float *d_t = t ? (float *)(o + o_t) + b : nullptr;
 			float2 *d_uv = uv ? (float2 *)(o + o_uv) + b : nullptr;
-			ADYPT_TRY(launch_trace(s, d_in, m, d_tri, d_t, d_uv, nullptr, st));
+			ADYPT_TRY(launch_trace(s, d_in, m, d_tri, d_t, d_uv, nullptr, st, nullptr, ctr));
 			ADYPT_CUDA(cudaMemcpyAsync(tri + b, d_tri, (size_t)m * 4u, cudaMemcpyDeviceToHost, st));
 			if (t) ADYPT_CUDA(cudaMemcpyAsync(t + b, d_t, (size_t)m * 4u, cudaMemcpyDeviceToHost, st));
 			if (uv) ADYPT_CUDA(cudaMemcpyAsync(uv + 2 * b, d_uv, (size_t)m * 8u, cudaMemcpyDeviceToHost, st));
@@ -450,13 +467,13 @@ int adypt_trace_stats(adypt_scene *s, const float *rays, uint64_t n, int memspac
 	} else if (memspace != ADYPT_MEM_DEVICE)
 		return fail(ADYPT_EINVAL, "bad memspace");
 	ADYPT_TRY(s->stage_out.reserve((size_t)n * 4u + 64u));
-	unsigned long long *d_stats = s->d_counters + kCounterRing; // 4 extra slots behind the ring
+	unsigned long long *d_stats = s->d_counters + kCounterStats;
 	ADYPT_CUDA(cudaMemset(d_stats, 0, 4 * sizeof(unsigned long long)));
 	TraceParams p;
 	p.nodes = s->d_nodes; p.woop = s->d_woop; p.tri_indices = s->d_tri_indices; p.rays = d_rays;
 	p.n = n; p.n_ptr = nullptr;
 	p.out_tri = s->stage_out.as<int32_t>(); p.out_t = nullptr; p.out_uv = nullptr; p.out_occ = nullptr;
-	p.counter = s->d_counters + (s->counter_cursor++ % kCounterRing);
+	p.counter = s->d_counters + (s->counter_cursor.fetch_add(1u) % kCounterRing);
 	p.stats = d_stats;
 	p.magic = 0x4B000000u;
 	p.pool_chunk = kPoolChunk;

@@ -3,6 +3,16 @@
 #include "common.h"
 #include "layouts.h"
 
+namespace adypt {
+// Work counters of the persistent kernels. A slot is zeroed by a memset queued on the launch stream right before the
+// launch that uses it, so a slot may only be shared by launches that are ordered on ONE stream (then a single slot is
+// enough). Every tracer owns a slot (used by all launches on its stream), each of the three pipeline streams of the
+// host-array calls owns one, and launches on caller-provided streams take slots from a ring with an atomic cursor:
+// callers that trace on several of their own streams at once get distinct slots as long as fewer than kCounterRing
+// launches are in flight. Layout of adypt_scene::d_counters: [0, kCounterRing) ring, +0..3 statistics, +4..6 pipeline.
+constexpr unsigned kCounterRing = 256, kCounterStats = kCounterRing, kCounterPipe = kCounterRing + 4, kCounterSlots = kCounterRing + 8;
+} // namespace adypt
+
 struct adypt_scene {
 	int device = 0;
 	int sm_count = 0;
@@ -15,8 +25,9 @@ struct adypt_scene {
 	uchar4 *d_texels = nullptr;        // all textures back to back, RGBX8
 	int4 *d_tex_table = nullptr;       // per texture: (first texel, width, height, 0)
 	uint32_t n_textures = 0;           // TEXTURE_COUNT
-	unsigned long long *d_counters = nullptr; // ring of work counters for the persistent kernels
-	unsigned counter_cursor = 0;
+	unsigned long long *d_counters = nullptr; // work counters of the persistent kernels (layout above)
+	std::atomic<unsigned> counter_cursor{0};
+	int64_t bad_matid_tri = -1; // first triangle whose material id is outside [0, n_mats): such a scene can be traversed but not shaded
 	int ctas_per_sm = 0;       // 0 = occupancy query
 	int refill_threshold = 0;  // 0 = default
 	int variant = 0;           // code-generation variant of the closest-hit kernel (tuning only)
@@ -28,12 +39,11 @@ struct adypt_scene {
 
 namespace adypt {
 
-constexpr unsigned kCounterRing = 256;
-
 // queue a closest-hit (occ == nullptr) or any-hit (occ != nullptr) traversal of n device rays on `stream`;
-// d_n (nullable): the actual ray count lives in device memory and n is only its upper bound
+// d_n (nullable): the actual ray count lives in device memory and n is only its upper bound;
+// d_counter (nullable): a work-counter slot owned by `stream` (see above), else one is taken from the scene's ring
 int launch_trace(adypt_scene *s, const float4 *d_rays, uint64_t n, int32_t *d_tri, float *d_t, float2 *d_uv,
-                 uint8_t *d_occ, cudaStream_t stream, const unsigned long long *d_n = nullptr);
+                 uint8_t *d_occ, cudaStream_t stream, const unsigned long long *d_n = nullptr, unsigned long long *d_counter = nullptr);
 
 inline void count_launch(unsigned n = 1) { g_launches.fetch_add(n); }
 

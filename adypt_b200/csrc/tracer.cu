@@ -563,6 +563,7 @@ namespace {
 
 constexpr int kCountSlots = 72;
 constexpr int kConnBase = 36; // d_counts[kConnBase + b]: length of bounce b's connect queue
+// d_counts[kCountSlots]: the work counter of this tracer's traversal launches (all on t->stream, so one slot is enough; scene.h)
 constexpr unsigned long long kDefaultMaxPaths = 48ull << 20;
 
 void free_tracer(adypt_tracer *t)
@@ -622,7 +623,7 @@ int trace_primary(adypt_tracer *t, float bx, float by)
 	k_generate<<<grid_for(t->npix, 256, s->sm_count), 256, 0, t->stream>>>(t->cam, t->width, t->height, bx, by, t->d_rays[0]);
 	count_launch();
 	ADYPT_CUDA(cudaGetLastError());
-	ADYPT_TRY(launch_trace(s, t->d_rays[0], t->npix, t->d_prim_tri, nullptr, t->d_prim_uv, nullptr, t->stream));
+	ADYPT_TRY(launch_trace(s, t->d_rays[0], t->npix, t->d_prim_tri, nullptr, t->d_prim_uv, nullptr, t->stream, nullptr, t->d_counts + kCountSlots));
 	t->host_segments += t->npix;
 	return ADYPT_OK;
 }
@@ -677,7 +678,7 @@ int run_batch(adypt_tracer *t, int first, int n, bool sum_mode)
 	// connect stage of bounce b: any-hit over the shadow rays queued by the shade kernel, then add the sun term
 	auto connect = [&](int b) -> int {
 		if (!t->sun_visibility) return ADYPT_OK;
-		ADYPT_TRY(launch_trace(s, t->d_conn_rays, total, nullptr, nullptr, nullptr, t->d_conn_occ, t->stream, t->d_counts + kConnBase + b));
+		ADYPT_TRY(launch_trace(s, t->d_conn_rays, total, nullptr, nullptr, nullptr, t->d_conn_occ, t->stream, t->d_counts + kConnBase + b, t->d_counts + kCountSlots));
 		k_connect_apply<<<grid_for(total, 256, s->sm_count), 256, 0, t->stream>>>(t->d_conn_rays, t->d_conn_occ, t->d_counts + kConnBase + b, t->d_color, t->d_ret);
 		count_launch();
 		ADYPT_CUDA(cudaGetLastError());
@@ -690,7 +691,7 @@ int run_batch(adypt_tracer *t, int first, int n, bool sum_mode)
 	int cur = 1;
 	for (int b = 1; b < c.max_bounce; ++b) {
 		// extend: queue length is read on the device
-		ADYPT_TRY(launch_trace(s, t->d_rays[cur], total, t->d_hit_tri, nullptr, t->d_hit_uv, nullptr, t->stream, t->d_counts + b));
+		ADYPT_TRY(launch_trace(s, t->d_rays[cur], total, t->d_hit_tri, nullptr, t->d_hit_uv, nullptr, t->stream, t->d_counts + b, t->d_counts + kCountSlots));
 		B.in_rays = t->d_rays[cur];
 		B.in_count = t->d_counts + b;
 		B.out_rays = t->d_rays[cur ^ 1];
@@ -738,6 +739,8 @@ int adypt_tracer_create(adypt_scene *scene, const adypt_pt_config *config, int32
 	*out = nullptr;
 	if (width <= 0 || height <= 0 || (uint64_t)width * (uint64_t)height >= (1ull << 31)) return fail(ADYPT_EINVAL, "bad image size");
 	if (!scene->d_tris || !scene->d_mats) return fail(ADYPT_EINVAL, "scene has no triangles/materials: traversal-only scenes cannot shade");
+	if (scene->bad_matid_tri >= 0)
+		return fail(ADYPT_EINVAL, "triangle " + std::to_string(scene->bad_matid_tri) + " has a material id outside [0, n_materials) (an OBJ face without a usemtl, or an unknown material): the scene can be traversed but not shaded");
 	ADYPT_TRY(check_config(config));
 	DeviceGuard g(scene->device);
 	adypt_tracer *t = new adypt_tracer;
@@ -756,10 +759,10 @@ int adypt_tracer_create(adypt_scene *scene, const adypt_pt_config *config, int32
 	if (e == cudaSuccess) e = cudaMalloc((void **)&t->d_bias, np * 2u);
 	if (e == cudaSuccess) e = cudaMalloc((void **)&t->d_dirs, (size_t)sobol_max_dim() * 32u * 4u);
 	if (e == cudaSuccess) e = cudaMalloc((void **)&t->d_sobol, (size_t)sobol_max_dim() * 4u * 4096u);
-	if (e == cudaSuccess) e = cudaMalloc((void **)&t->d_counts, kCountSlots * sizeof(unsigned long long));
+	if (e == cudaSuccess) e = cudaMalloc((void **)&t->d_counts, (kCountSlots + 1) * sizeof(unsigned long long));
 	if (e == cudaSuccess) e = cudaMemset(t->d_result, 0, np * 16u);
 	if (e == cudaSuccess) e = cudaMemset(t->d_sum, 0, np * 16u);
-	if (e == cudaSuccess) e = cudaMemset(t->d_counts, 0, kCountSlots * sizeof(unsigned long long));
+	if (e == cudaSuccess) e = cudaMemset(t->d_counts, 0, (kCountSlots + 1) * sizeof(unsigned long long));
 	if (e == cudaSuccess) e = cudaMemcpy(t->d_dirs, sobol_directions(), (size_t)sobol_max_dim() * 32u * 4u, cudaMemcpyHostToDevice);
 	if (e == cudaSuccess) {
 		try {
@@ -879,7 +882,7 @@ int adypt_tracer_primary(adypt_tracer *t, int32_t viewer_type)
 	adypt_scene *s = t->scene;
 	k_generate<<<grid_for(t->npix, 256, s->sm_count), 256, 0, t->stream>>>(t->cam, t->width, t->height, 0.0f, 0.0f, t->d_rays[0]);
 	count_launch();
-	ADYPT_TRY(launch_trace(s, t->d_rays[0], t->npix, t->d_hit_tri, nullptr, t->d_hit_uv, nullptr, t->stream));
+	ADYPT_TRY(launch_trace(s, t->d_rays[0], t->npix, t->d_hit_tri, nullptr, t->d_hit_uv, nullptr, t->stream, nullptr, t->d_counts + kCountSlots));
 	k_view<<<grid_for(t->npix, 256, s->sm_count), 256, 0, t->stream>>>(s->d_tris, s->d_mats, s->d_texels, s->d_tex_table, t->d_hit_tri, t->d_hit_uv, viewer_type, t->npix, t->d_result);
 	count_launch();
 	ADYPT_CUDA(cudaGetLastError());

@@ -114,7 +114,7 @@ int adypt_trace_stats(adypt_scene *scene, const float *rays, uint64_t n, int mem
 /* number of kernel launches adypt_* calls have issued so far on this scene's device (bench accounting) */
 int adypt_launch_count(uint64_t *launches);
 /* tuning knobs of the persistent traversal kernel (0 = default): CTAs per SM, the refill threshold, and a
- * code-generation variant of the closest-hit kernel (0..7; same algorithm, identical results) */
+ * code-generation variant of the traversal kernels (0..8, see launch_trace in csrc/scene.cu; same algorithm, identical results) */
 int adypt_trace_configure(adypt_scene *scene, int ctas_per_sm, int refill_threshold, int variant);
 
 /* ------------------------------------------------------------------------------------------------

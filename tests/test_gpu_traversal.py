@@ -119,6 +119,41 @@ def test_scene_validation_rejects_out_of_range_indices(A):
         A.Scene(g.nodes, g.tri_indices + 1000, None, g.tris, g.mats)
 
 
+def test_scene_validation_covers_imask(A):
+    """A node whose imask does not cover its inner children (a corrupt / stale .bvh cache) is refused: the kernel addresses a
+    child as child_base + popc(imask & lowmask(ordinal)) and would read past the node array (traversal.glsl:61-67)."""
+    g = load_golden("tiny_deep")
+    bad = g.nodes.copy()
+    assert bad[0, 15] != 0, "fixture's root has inner children"
+    bad[0, 15] = 0  # imask byte of m_head.w
+    with pytest.raises(A.AdyptError):
+        A.Scene(bad, g.tri_indices, g.woop)
+    bad = g.nodes.copy()
+    last = np.frombuffer(np.uint32(g.nodes.shape[0] - 1).tobytes(), dtype=np.uint8)
+    bad[0, 16:20] = last  # child_base = last node, but imask names more than one child
+    if bin(int(g.nodes[0, 15])).count("1") > 1:
+        with pytest.raises(A.AdyptError):
+            A.Scene(bad, g.tri_indices, g.woop)
+
+
+def test_material_id_out_of_range_can_be_traced_but_not_shaded(A, cpu):
+    """An OBJ face before the first usemtl gets material id -1 (Scene.cpp:52, tinyobjloader): the reference's GL buffer read
+    shrugs that off, a CUDA read would fault and poison the context. Traversal works; creating a tracer is refused."""
+    g = load_golden("tiny_strip")
+    tris = g.tris.copy()
+    tris.view(np.int32).reshape(tris.shape[0], 25)[0, 24] = -1
+    sc = A.Scene(g.nodes, g.tri_indices, None, tris, g.mats)
+    got = sc.trace_closest(g.rays)
+    exp = cpu.trace_closest(g.nodes, g.tri_indices, g.woop, g.rays)
+    assert np.array_equal(got["tri"], exp["tri"])
+    with pytest.raises(A.AdyptError, match="material id"):
+        A.Tracer(sc, A.PTConfig.make(), 16, 16, bias_seed=1)
+    tris.view(np.int32).reshape(tris.shape[0], 25)[0, 24] = g.mats.shape[0]
+    sc2 = A.Scene(g.nodes, g.tri_indices, None, tris, g.mats)
+    with pytest.raises(A.AdyptError, match="material id"):
+        A.Tracer(sc2, A.PTConfig.make(), 16, 16, bias_seed=1)
+
+
 def test_c1_primary_rays_bit_exact(A, cpu, c1):
     """Config 1: 65 536-triangle lattice, 1M coherent primary rays: ids, t, uv identical to the oracle,
     and ids reproduce the committed digest."""
