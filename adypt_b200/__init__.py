@@ -32,7 +32,7 @@ EXPORTS = [
     "adypt_tracer_primary", "adypt_tracer_sample", "adypt_tracer_accumulate", "adypt_tracer_sum_buffer",
     "adypt_tracer_clear_sum", "adypt_tracer_resolve_sum", "adypt_tracer_spp", "adypt_tracer_read",
     "adypt_tracer_result_buffer", "adypt_tracer_save_exr", "adypt_tracer_sync", "adypt_tracer_primary_rays",
-    "adypt_tracer_stats", "adypt_write_exr", "adypt_debug_math",
+    "adypt_sobol_vector", "adypt_tracer_stats", "adypt_tracer_set_profiling", "adypt_tracer_get_profile", "adypt_trace_kernel_name", "adypt_write_exr", "adypt_debug_math",
     "adypt_host_scene_load_obj", "adypt_host_scene_from_triangles", "adypt_host_scene_destroy", "adypt_host_scene_build_bvh",
     "adypt_host_scene_load_bvh", "adypt_host_scene_save_bvh", "adypt_host_scene_get", "adypt_host_scene_upload",
     "adypt_config_format_double", "adypt_config_set_default", "adypt_config_load", "adypt_config_to_json", "adypt_config_save",
@@ -70,6 +70,15 @@ class PTConfig(C.Structure):
 
 
 _lib = None
+
+
+STAGES = ("generate", "trace_primary", "shade_primary", "trace_bounce", "shade_bounce", "accumulate", "connect", "other")
+
+
+class TracerProfile(C.Structure):  # adypt_tracer_profile
+    _fields_ = [("stage_ms", C.c_double * 8), ("stage_launches", C.c_uint64 * 8), ("trace_nodes", C.c_uint64), ("trace_tris", C.c_uint64),
+                ("trace_hits", C.c_uint64), ("trace_rays", C.c_uint64), ("trace_max_depth", C.c_uint64),
+                ("primary_nodes", C.c_uint64), ("primary_tris", C.c_uint64), ("primary_hits", C.c_uint64), ("primary_rays", C.c_uint64)]
 
 
 def load_library():
@@ -114,8 +123,13 @@ def load_library():
         "adypt_tracer_result_buffer": [vp, vp, vp],
         "adypt_tracer_save_exr": [vp, C.c_char_p, i32],
         "adypt_tracer_sync": [vp],
+        "adypt_tracer_stream": [vp, vp],
         "adypt_tracer_primary_rays": [vp, vp, C.c_int],
         "adypt_tracer_stats": [vp, vp, vp],
+        "adypt_sobol_vector": [C.c_uint32, C.c_uint32, vp],
+        "adypt_tracer_set_profiling": [vp, i32],
+        "adypt_tracer_get_profile": [vp, vp, i32],
+        "adypt_trace_kernel_name": [vp, i32, C.c_char_p, u64],
         "adypt_write_exr": [C.c_char_p, vp, i32, i32, i32],
         "adypt_debug_math": [i32, i32, vp, vp, u64, vp, vp],
     }
@@ -165,6 +179,13 @@ def camera_matrices(fov, yaw, pitch, width, height):
     v = np.zeros(16, dtype=np.float32)
     _check(load_library().adypt_camera_matrices(fov, yaw, pitch, width, height, p.ctypes.data, v.ctypes.data))
     return p, v
+
+
+def sobol_vector(dim: int, index: int) -> np.ndarray:
+    """The vector Sobol::Next writes on call number index (0-based) after Reset(dim) (adypt_sobol_vector; host only)."""
+    out = np.zeros(dim, dtype=np.float32)
+    _check(load_library().adypt_sobol_vector(dim, index, out.ctypes.data))
+    return out
 
 
 def write_exr(path, rgb, fp16=False):
@@ -283,6 +304,22 @@ class Scene:
             _check(load_library().adypt_trace_stats(self._h, rays.ctypes.data, rays.size // 8, MEM_HOST, out))
         return dict(nodes=int(out[0]), tris=int(out[1]), hits=int(out[2]), max_stack=int(out[3]))
 
+    def kernel_name(self, any_hit=False, demangle=True):
+        """Name of the kernel trace_closest / trace_any launch for the current tuning variant (adypt_trace_kernel_name)."""
+        buf = C.create_string_buffer(512)
+        _check(load_library().adypt_trace_kernel_name(self._h, 1 if any_hit else 0, buf, 512))
+        name = buf.value.decode()
+        if demangle:
+            import shutil
+            import subprocess
+            tool = shutil.which("c++filt") or shutil.which("cu++filt")
+            if tool:
+                try:
+                    name = subprocess.run([tool, name], capture_output=True, text=True, timeout=10).stdout.strip() or name
+                except Exception:
+                    pass
+        return name
+
     def trace_any(self, rays, occluded=None, stream=None):
         lib = load_library()
         if _is_device(rays):
@@ -390,6 +427,12 @@ class Tracer:
         _check(load_library().adypt_tracer_spp(self._h, C.byref(v)))
         return v.value
 
+    def stream(self) -> int:
+        """The cudaStream_t (as an integer) the tracer enqueues its work on (adypt_tracer_stream)."""
+        p = C.c_void_p()
+        _check(load_library().adypt_tracer_stream(self._h, C.byref(p)))
+        return p.value or 0
+
     def sync(self):
         _check(load_library().adypt_tracer_sync(self._h))
 
@@ -411,6 +454,18 @@ class Tracer:
         out = np.empty((self.width * self.height, 8), dtype=np.float32)
         _check(load_library().adypt_tracer_primary_rays(self._h, out.ctypes.data, MEM_HOST))
         return out
+
+    def set_profiling(self, stage_times=False, trace_counters=False):
+        """Measurement hooks (adypt_tracer_set_profiling): event pairs around every stage / the instrumented traversal kernel."""
+        _check(load_library().adypt_tracer_set_profiling(self._h, (1 if stage_times else 0) | (2 if trace_counters else 0)))
+
+    def profile(self, reset=True):
+        """dict(stage_ms={name: ms}, stage_launches={name: n}, trace=dict(...) for the bounce queues, primary=dict(...) for the primary rays) since the last reset."""
+        p = TracerProfile()
+        _check(load_library().adypt_tracer_get_profile(self._h, C.byref(p), 1 if reset else 0))
+        return dict(stage_ms={n: p.stage_ms[i] for i, n in enumerate(STAGES)}, stage_launches={n: int(p.stage_launches[i]) for i, n in enumerate(STAGES)},
+                    trace=dict(nodes=int(p.trace_nodes), tris=int(p.trace_tris), hits=int(p.trace_hits), rays=int(p.trace_rays), max_stack=int(p.trace_max_depth)),
+                    primary=dict(nodes=int(p.primary_nodes), tris=int(p.primary_tris), hits=int(p.primary_hits), rays=int(p.primary_rays)))
 
     def stats(self):
         s, l = C.c_uint64(0), C.c_uint64(0)

@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstring>
 #include <mutex>
+#include <vector>
 #include "../../include/adypt_b200.h"
 #include "guard.h"
 
@@ -93,34 +94,47 @@ void camera_matrices(float fov_deg, float yaw_deg, float pitch_deg, int width, i
 
 // ------------------------------------------------------------------------------------------------
 namespace {
-struct JoeKuo {
-	int s;
-	unsigned a;
-	unsigned m[16];
+// Joe-Kuo parameters, five packed words per dimension (layout: tools/derive_sobol_params.py)
+const uint32_t kJoeKuoPacked[] = {
+#include "sobol_joe_kuo.inc"
 };
-const JoeKuo kParams[] = {
-#include "sobol_params.inc"
-};
-constexpr int kMaxDim = (int)(sizeof(kParams) / sizeof(kParams[0]));
-uint32_t g_dirs[kMaxDim][32];
+constexpr int kTableDims = (int)(sizeof(kJoeKuoPacked) / (5 * sizeof(uint32_t)));
+// The reference declares kMatrices[10005][32] and m_x[10005] (Sobol.inl:4, Sobol.hpp:9) but lists 10 000 rows; C++ zero-fills
+// the other five, so dimensions 10 001 .. 10 005 generate the constant 0. Same here.
+constexpr int kMaxDim = 10005;
+static_assert(kTableDims <= kMaxDim, "parameter table larger than the reference's");
+std::vector<uint32_t> g_dirs;
 std::once_flag g_dirs_once;
+
+inline uint32_t packed_bits(const uint32_t *w, int pos, int n) // n <= 17 bits starting at bit pos of the 160-bit record
+{
+	if (n == 0) return 0u;
+	const uint64_t lo = w[pos >> 5], hi = (pos >> 5) + 1 < 5 ? w[(pos >> 5) + 1] : 0u;
+	return (uint32_t)(((lo | (hi << 32)) >> (pos & 31)) & ((1ull << n) - 1ull));
+}
 
 // Bratley-Fox recurrence: m_k = XOR_i 2^i a_i m_{k-i}  ^  2^s m_{k-s} ^ m_{k-s};  v_k = m_k << (32 - k)
 void init_dirs()
 {
-	for (int j = 0; j < kMaxDim; ++j) {
-		const JoeKuo &p = kParams[j];
+	g_dirs.assign((size_t)kMaxDim * 32u, 0u);
+	for (int j = 0; j < kTableDims; ++j) {
+		const uint32_t *w = kJoeKuoPacked + 5 * j;
+		const int s = (int)packed_bits(w, 0, 5);
+		const uint32_t a = packed_bits(w, 5, 16);
 		uint32_t m[32];
+		int pos = 21;
 		for (int k = 0; k < 32; ++k) {
-			if (p.s == 0) m[k] = 1u; // dimension 1: van der Corput
-			else if (k < p.s) m[k] = p.m[k];
-			else {
-				uint32_t x = m[k - p.s] ^ (m[k - p.s] << p.s);
-				for (int i = 1; i < p.s; ++i)
-					if ((p.a >> (p.s - 1 - i)) & 1u) x ^= m[k - i] << i;
+			if (s == 0) m[k] = 1u; // dimension 1: van der Corput
+			else if (k < s) {
+				m[k] = (packed_bits(w, pos, k) << 1) | 1u; // m_{k+1} is odd and below 2^(k+1)
+				pos += k;
+			} else {
+				uint32_t x = m[k - s] ^ (m[k - s] << s);
+				for (int i = 1; i < s; ++i)
+					if ((a >> (s - 1 - i)) & 1u) x ^= m[k - i] << i;
 				m[k] = x;
 			}
-			g_dirs[j][k] = m[k] << (31 - k);
+			g_dirs[(size_t)j * 32u + (size_t)k] = m[k] << (31 - k);
 		}
 	}
 }
@@ -131,7 +145,7 @@ int sobol_max_dim() { return kMaxDim; }
 const uint32_t *sobol_directions()
 {
 	std::call_once(g_dirs_once, init_dirs);
-	return &g_dirs[0][0];
+	return g_dirs.data();
 }
 
 void sobol_vector(uint32_t dim, uint32_t index, float *out)
@@ -169,6 +183,16 @@ extern "C" int adypt_camera_matrices(float fov_deg, float yaw_deg, float pitch_d
 	return adypt::guarded([&]() -> int {
 	if (!projection || !view || width <= 0 || height <= 0) return ADYPT_EINVAL;
 	adypt::camera_matrices(fov_deg, yaw_deg, pitch_deg, width, height, projection, view);
+	return ADYPT_OK;
+	});
+}
+
+extern "C" int adypt_sobol_vector(uint32_t dim, uint32_t index, float *out)
+{
+	return adypt::guarded([&]() -> int {
+	if (!out && dim) return adypt::fail(ADYPT_EINVAL, "out is NULL");
+	if (dim > (uint32_t)adypt::sobol_max_dim()) return adypt::fail(ADYPT_ERANGE, "the reference's Sobol table has 10005 dimensions");
+	adypt::sobol_vector(dim, index, out);
 	return ADYPT_OK;
 	});
 }

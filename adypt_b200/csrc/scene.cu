@@ -91,8 +91,35 @@ __global__ void build_woop_kernel(const uint8_t *__restrict__ tris, const int32_
 }
 
 // ------------------------------------------------------------------------------------------------
+// The kernel a launch uses. Variants are code-generation variants of the same algorithm (identical results; tuning and
+// A/B measurements only); 0 = tuned default: 4 conversion planes on the I2F pipe, 8 CTAs/SM, triangle batch 2 with both
+// fetches up front, staged ray set-up. `stats` selects the instrumented build (work counters; slower).
+TraceKernel trace_kernel_for(bool any, bool stats, int variant)
+{
+	if (stats) return any ? trace_kernel<true, true> : trace_kernel<false, true>;
+	if (any) switch (variant) {
+	case 1: return trace_kernel<true, false, 2, 8, 0>;
+	case 2: return trace_kernel<true, false, 2, 8, 2>;
+	case 5: return trace_kernel<true, false, 4, 8, 2>;
+	case 8: return trace_kernel<true, false, 4, 8, 12, false>;
+	default: return trace_kernel<true>;
+	}
+	switch (variant) {
+	case 1: return trace_kernel<false, false, 2, 8, 0>; // unbounded triangle loop
+	case 2: return trace_kernel<false, false, 2, 8, 2>;
+	case 3: return trace_kernel<false, false, 2, 8, 12>;
+	case 4: return trace_kernel<false, false, 3, 8, 12>;
+	case 5: return trace_kernel<false, false, 4, 8, 2>;
+	case 6: return trace_kernel<false, false, 5, 8, 12>;
+	case 7: return trace_kernel<false, false, 4, 8, 1>;
+	case 8: return trace_kernel<false, false, 4, 8, 12, false>; // ray set-up at refill time
+	default: return trace_kernel<false>;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
 int launch_trace(adypt_scene *s, const float4 *d_rays, uint64_t n, int32_t *d_tri, float *d_t, float2 *d_uv, uint8_t *d_occ,
-                 cudaStream_t stream, const unsigned long long *d_n, unsigned long long *d_counter)
+                 cudaStream_t stream, const unsigned long long *d_n, unsigned long long *d_counter, unsigned long long *d_stats)
 {
 	if (n == 0) return ADYPT_OK;
 	const bool any = d_occ != nullptr;
@@ -107,7 +134,6 @@ int launch_trace(adypt_scene *s, const float4 *d_rays, uint64_t n, int32_t *d_tr
 	p.out_t = d_t;
 	p.out_uv = d_uv;
 	p.out_occ = d_occ;
-	p.stats = nullptr;
 	p.magic = 0x4B000000u;
 	p.counter = d_counter ? d_counter : s->d_counters + (s->counter_cursor.fetch_add(1u) % kCounterRing);
 	p.refill_threshold = s->refill_threshold > 0 ? s->refill_threshold : 28;
@@ -130,26 +156,8 @@ int launch_trace(adypt_scene *s, const float4 *d_rays, uint64_t n, int32_t *d_tr
 		while ((1ull << p.guided_shift) < warps * 4ull) ++p.guided_shift;
 	}
 	ADYPT_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned long long), stream));
-	// code-generation variants of the same algorithm (identical results); 0 = tuned default: 4 conversion planes on
-	// the I2F pipe, 8 CTAs/SM, triangle batch 2 with both fetches up front
-	if (any) switch (s->variant) {
-	case 1: trace_kernel<true, false, 2, 8, 0><<<grid, kTraceBlock, 0, stream>>>(p); break;
-	case 2: trace_kernel<true, false, 2, 8, 2><<<grid, kTraceBlock, 0, stream>>>(p); break;
-	case 5: trace_kernel<true, false, 4, 8, 2><<<grid, kTraceBlock, 0, stream>>>(p); break;
-	case 8: trace_kernel<true, false, 4, 8, 12, false><<<grid, kTraceBlock, 0, stream>>>(p); break;
-	default: trace_kernel<true><<<grid, kTraceBlock, 0, stream>>>(p); break;
-	}
-	else switch (s->variant) {
-	case 1: trace_kernel<false, false, 2, 8, 0><<<grid, kTraceBlock, 0, stream>>>(p); break; // unbounded triangle loop
-	case 2: trace_kernel<false, false, 2, 8, 2><<<grid, kTraceBlock, 0, stream>>>(p); break;
-	case 3: trace_kernel<false, false, 2, 8, 12><<<grid, kTraceBlock, 0, stream>>>(p); break;
-	case 4: trace_kernel<false, false, 3, 8, 12><<<grid, kTraceBlock, 0, stream>>>(p); break;
-	case 5: trace_kernel<false, false, 4, 8, 2><<<grid, kTraceBlock, 0, stream>>>(p); break;
-	case 6: trace_kernel<false, false, 5, 8, 12><<<grid, kTraceBlock, 0, stream>>>(p); break;
-	case 7: trace_kernel<false, false, 4, 8, 1><<<grid, kTraceBlock, 0, stream>>>(p); break;
-	case 8: trace_kernel<false, false, 4, 8, 12, false><<<grid, kTraceBlock, 0, stream>>>(p); break; // ray set-up at refill time
-	default: trace_kernel<false><<<grid, kTraceBlock, 0, stream>>>(p); break;
-	}
+	p.stats = d_stats;
+	trace_kernel_for(any, d_stats != nullptr, s->variant)<<<grid, kTraceBlock, 0, stream>>>(p);
 	count_launch();
 	ADYPT_CUDA(cudaGetLastError());
 	return ADYPT_OK;
@@ -468,24 +476,24 @@ int adypt_trace_stats(adypt_scene *s, const float *rays, uint64_t n, int memspac
 		return fail(ADYPT_EINVAL, "bad memspace");
 	ADYPT_TRY(s->stage_out.reserve((size_t)n * 4u + 64u));
 	unsigned long long *d_stats = s->d_counters + kCounterStats;
-	ADYPT_CUDA(cudaMemset(d_stats, 0, 4 * sizeof(unsigned long long)));
-	TraceParams p;
-	p.nodes = s->d_nodes; p.woop = s->d_woop; p.tri_indices = s->d_tri_indices; p.rays = d_rays;
-	p.n = n; p.n_ptr = nullptr;
-	p.out_tri = s->stage_out.as<int32_t>(); p.out_t = nullptr; p.out_uv = nullptr; p.out_occ = nullptr;
-	p.counter = s->d_counters + (s->counter_cursor.fetch_add(1u) % kCounterRing);
-	p.stats = d_stats;
-	p.magic = 0x4B000000u;
-	p.pool_chunk = kPoolChunk;
-	p.guided_shift = 0;
-	p.refill_threshold = s->refill_threshold > 0 ? s->refill_threshold : 28;
-	ADYPT_CUDA(cudaMemset(p.counter, 0, sizeof(unsigned long long)));
-	trace_kernel<false, true><<<(unsigned)s->sm_count * 4u, kTraceBlock>>>(p);
-	count_launch();
+	ADYPT_CUDA(cudaMemset(d_stats, 0, kStatSlots * sizeof(unsigned long long)));
+	ADYPT_TRY(launch_trace(s, d_rays, n, s->stage_out.as<int32_t>(), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, d_stats));
 	ADYPT_CUDA(cudaDeviceSynchronize());
 	unsigned long long h[4];
 	ADYPT_CUDA(cudaMemcpy(h, d_stats, sizeof(h), cudaMemcpyDeviceToHost));
 	for (int i = 0; i < 4; ++i) out[i] = h[i];
+	return ADYPT_OK;
+	});
+}
+
+int adypt_trace_kernel_name(adypt_scene *s, int32_t any_hit, char *buf, uint64_t cap)
+{
+	return guarded([&]() -> int {
+	if (!s || !buf || cap == 0) return fail(ADYPT_EINVAL, "NULL argument");
+	DeviceGuard g(s->device);
+	const char *name = nullptr;
+	ADYPT_CUDA(cudaFuncGetName(&name, (const void *)trace_kernel_for(any_hit != 0, false, s->variant)));
+	snprintf(buf, (size_t)cap, "%s", name ? name : "");
 	return ADYPT_OK;
 	});
 }

@@ -9,8 +9,9 @@ namespace adypt {
 // enough). Every tracer owns a slot (used by all launches on its stream), each of the three pipeline streams of the
 // host-array calls owns one, and launches on caller-provided streams take slots from a ring with an atomic cursor:
 // callers that trace on several of their own streams at once get distinct slots as long as fewer than kCounterRing
-// launches are in flight. Layout of adypt_scene::d_counters: [0, kCounterRing) ring, +0..3 statistics, +4..6 pipeline.
-constexpr unsigned kCounterRing = 256, kCounterStats = kCounterRing, kCounterPipe = kCounterRing + 4, kCounterSlots = kCounterRing + 8;
+// launches are in flight. Layout of adypt_scene::d_counters: [0, kCounterRing) ring, +0..4 statistics, +8..10 pipeline.
+constexpr unsigned kStatSlots = 5; // nodes visited, triangles tested, rays that hit, deepest stack, rays traced
+constexpr unsigned kCounterRing = 256, kCounterStats = kCounterRing, kCounterPipe = kCounterRing + 8, kCounterSlots = kCounterRing + 12;
 } // namespace adypt
 
 struct adypt_scene {
@@ -41,9 +42,15 @@ namespace adypt {
 
 // queue a closest-hit (occ == nullptr) or any-hit (occ != nullptr) traversal of n device rays on `stream`;
 // d_n (nullable): the actual ray count lives in device memory and n is only its upper bound;
-// d_counter (nullable): a work-counter slot owned by `stream` (see above), else one is taken from the scene's ring
+// d_counter (nullable): a work-counter slot owned by `stream` (see above), else one is taken from the scene's ring;
+// d_stats (nullable): kStatSlots counters the INSTRUMENTED kernel adds its work to (measurement runs only)
 int launch_trace(adypt_scene *s, const float4 *d_rays, uint64_t n, int32_t *d_tri, float *d_t, float2 *d_uv,
-                 uint8_t *d_occ, cudaStream_t stream, const unsigned long long *d_n = nullptr, unsigned long long *d_counter = nullptr);
+                 uint8_t *d_occ, cudaStream_t stream, const unsigned long long *d_n = nullptr, unsigned long long *d_counter = nullptr,
+                 unsigned long long *d_stats = nullptr);
+
+struct TraceParams;
+using TraceKernel = void (*)(const TraceParams);
+TraceKernel trace_kernel_for(bool any, bool stats, int variant);
 
 inline void count_launch(unsigned n = 1) { g_launches.fetch_add(n); }
 

@@ -547,7 +547,12 @@ struct adypt_tracer {
 	int32_t *d_hit_tri = nullptr;
 	float2 *d_hit_uv = nullptr;
 	float4 *d_color = nullptr, *d_ret = nullptr;
-	unsigned long long *d_counts = nullptr; // [max_bounce + 1] queue lengths, [kConnBase + b] connect queues, [kCountSlots-1] = segments
+	// device counters, sized from maxBounce: [0, max_bounce] queue lengths, [conn_base + b] connect queues, [seg_slot] segments
+	// statistic, [work_slot] the work counter of this tracer's traversal launches (all on t->stream, so one is enough; scene.h)
+	unsigned long long *d_counts = nullptr;
+	int n_slots = 0, conn_base = 0, seg_slot = 0, work_slot = 0;
+	int dims_cap = 0;            // Sobol dimensions d_dirs / d_sobol are sized for
+	size_t sobol_cap = 0;        // floats in d_sobol
 	// connect stage (off by default: the reference's sun test is commented out, pathtracer.glsl:132)
 	bool sun_visibility = false;
 	float sun_dir[3] = {0.f, 0.f, 0.f};
@@ -557,19 +562,71 @@ struct adypt_tracer {
 	unsigned long long conn_capacity = 0;
 	uint64_t launches_at_create = 0;
 	uint64_t host_segments = 0;  // primary segments (known on the host)
+	// measurement hooks (adypt_tracer_set_profiling): CUDA events around every stage launch, and / or the instrumented
+	// traversal kernel that counts the nodes and triangles the wavefront's rays touch. Off by default.
+	int profiling = 0;
+	std::vector<cudaEvent_t> ev_pool;
+	size_t ev_used = 0;
+	struct Span { int stage; size_t e0, e1; };
+	std::vector<Span> spans;
+	double stage_ms[ADYPT_STAGE_COUNT] = {0};
+	uint64_t stage_launches[ADYPT_STAGE_COUNT] = {0};
+	unsigned long long *d_trace_stats = nullptr; // 2 x kStatSlots counters (bounce queues, primary rays), profiling bit 1
 };
 
 namespace {
 
-constexpr int kCountSlots = 72;
-constexpr int kConnBase = 36; // d_counts[kConnBase + b]: length of bounce b's connect queue
-// d_counts[kCountSlots]: the work counter of this tracer's traversal launches (all on t->stream, so one slot is enough; scene.h)
 constexpr unsigned long long kDefaultMaxPaths = 48ull << 20;
+
+// ---- stage timing: an event pair around each stage launch while profiling bit 0 is set; resolved on request
+int resolve_spans(adypt_tracer *t)
+{
+	if (t->spans.empty()) return ADYPT_OK;
+	ADYPT_CUDA(cudaStreamSynchronize(t->stream));
+	for (const adypt_tracer::Span &sp : t->spans) {
+		float ms = 0.0f;
+		ADYPT_CUDA(cudaEventElapsedTime(&ms, t->ev_pool[sp.e0], t->ev_pool[sp.e1]));
+		t->stage_ms[sp.stage] += (double)ms;
+		t->stage_launches[sp.stage] += 1;
+	}
+	t->spans.clear();
+	t->ev_used = 0;
+	return ADYPT_OK;
+}
+
+struct StageTimer { // records on construction and in end(); a no-op unless stage timing is on
+	adypt_tracer *t;
+	size_t e0 = 0;
+	int stage;
+	bool on;
+	StageTimer(adypt_tracer *tr, int st) : t(tr), stage(st), on((tr->profiling & 1) != 0)
+	{
+		if (!on) return;
+		if (t->ev_used + 2 > 8192) resolve_spans(t); // bounded pool: a long render is folded into the sums as it goes
+		while (t->ev_pool.size() < t->ev_used + 2) {
+			cudaEvent_t e = nullptr;
+			if (cudaEventCreate(&e) != cudaSuccess) { on = false; return; }
+			t->ev_pool.push_back(e);
+		}
+		e0 = t->ev_used;
+		t->ev_used += 2;
+		cudaEventRecord(t->ev_pool[e0], t->stream);
+	}
+	void end()
+	{
+		if (!on) return;
+		cudaEventRecord(t->ev_pool[e0 + 1], t->stream);
+		t->spans.push_back({stage, e0, e0 + 1});
+		on = false;
+	}
+};
 
 void free_tracer(adypt_tracer *t)
 {
 	DeviceGuard g(t->device);
 	if (t->stream) cudaStreamSynchronize(t->stream);
+	for (cudaEvent_t e : t->ev_pool) cudaEventDestroy(e);
+	cudaFree(t->d_trace_stats);
 	cudaFree(t->d_result); cudaFree(t->d_sum); cudaFree(t->d_prim_tri); cudaFree(t->d_prim_uv); cudaFree(t->d_bias);
 	cudaFree(t->d_dirs); cudaFree(t->d_sobol); cudaFree(t->d_rays[0]); cudaFree(t->d_rays[1]); cudaFree(t->d_hit_tri);
 	cudaFree(t->d_hit_uv); cudaFree(t->d_color); cudaFree(t->d_ret); cudaFree(t->d_counts); cudaFree(t->d_conn_rays); cudaFree(t->d_conn_occ);
@@ -577,11 +634,45 @@ void free_tracer(adypt_tracer *t)
 	delete t;
 }
 
-int check_config(const adypt_pt_config *c)
+int check_config(const adypt_pt_config *c, bool roulette)
 {
 	if (c->max_bounce < 1) return fail(ADYPT_EINVAL, "maxBounce must be >= 1");
-	if (2 * c->max_bounce > sobol_max_dim()) return fail(ADYPT_ERANGE, "maxBounce needs more Sobol dimensions than are built in (2*maxBounce <= 64)");
+	// the reference's generator carries 10 005 dimensions (Sobol.hpp:9) and uses 2*maxBounce of them (OglPathTracer.cpp:139)
+	if (2ll * c->max_bounce > sobol_max_dim()) return fail(ADYPT_ERANGE, "maxBounce needs more Sobol dimensions than the reference's table has (2*maxBounce <= 10005)");
+	if (roulette && 3ll * c->max_bounce > sobol_max_dim()) return fail(ADYPT_ERANGE, "Russian roulette needs 3*maxBounce Sobol dimensions (<= 10005)");
 	if (c->subpixel < 1 || c->tmp_lifetime < 1) return fail(ADYPT_EINVAL, "subpixel and tmpLifetime must be >= 1");
+	return ADYPT_OK;
+}
+
+// buffers whose size follows the configuration: queue counters (maxBounce) and the direction numbers (2 or 3 x maxBounce dimensions)
+int alloc_config_buffers(adypt_tracer *t)
+{
+	const int mb = t->cfg.max_bounce;
+	const int n_slots = 2 * (mb + 2) + 2;
+	if (n_slots != t->n_slots) {
+		unsigned long long keep = 0;
+		if (t->d_counts) {
+			ADYPT_CUDA(cudaStreamSynchronize(t->stream));
+			ADYPT_CUDA(cudaMemcpy(&keep, t->d_counts + t->seg_slot, sizeof(keep), cudaMemcpyDeviceToHost));
+			cudaFree(t->d_counts);
+			t->d_counts = nullptr;
+		}
+		ADYPT_CUDA(cudaMalloc((void **)&t->d_counts, (size_t)n_slots * sizeof(unsigned long long)));
+		ADYPT_CUDA(cudaMemset(t->d_counts, 0, (size_t)n_slots * sizeof(unsigned long long)));
+		t->n_slots = n_slots;
+		t->conn_base = mb + 2;
+		t->seg_slot = n_slots - 2;
+		t->work_slot = n_slots - 1;
+		ADYPT_CUDA(cudaMemcpy(t->d_counts + t->seg_slot, &keep, sizeof(keep), cudaMemcpyHostToDevice));
+	}
+	long long dims = 3ll * mb; // room for the opt-in roulette draws, as far as the table goes
+	if (dims > sobol_max_dim()) dims = sobol_max_dim();
+	if ((int)dims > t->dims_cap) {
+		if (t->d_dirs) { ADYPT_CUDA(cudaStreamSynchronize(t->stream)); cudaFree(t->d_dirs); t->d_dirs = nullptr; }
+		ADYPT_CUDA(cudaMalloc((void **)&t->d_dirs, (size_t)dims * 32u * 4u));
+		ADYPT_CUDA(cudaMemcpy(t->d_dirs, sobol_directions(), (size_t)dims * 32u * 4u, cudaMemcpyHostToDevice));
+		t->dims_cap = (int)dims;
+	}
 	return ADYPT_OK;
 }
 
@@ -598,9 +689,14 @@ int alloc_wavefront(adypt_tracer *t)
 	int S = t->cfg.tmp_lifetime;
 	const unsigned long long by_mem = std::max(1ull, kDefaultMaxPaths / (unsigned long long)t->npix);
 	if ((unsigned long long)S > by_mem) S = (int)by_mem;
-	if (S > 4096) S = 4096; // d_sobol holds 4096 sample vectors
 	const unsigned long long cap = (unsigned long long)S * t->npix;
 	if (cap >= (1ull << 32)) return fail(ADYPT_ERANGE, "batch too large for 32-bit path ids");
+	const size_t sobol_need = (size_t)t->dims_cap * (size_t)S;
+	if (sobol_need > t->sobol_cap) {
+		if (t->d_sobol) { ADYPT_CUDA(cudaStreamSynchronize(t->stream)); cudaFree(t->d_sobol); t->d_sobol = nullptr; t->sobol_cap = 0; }
+		ADYPT_CUDA(cudaMalloc((void **)&t->d_sobol, sobol_need * 4u));
+		t->sobol_cap = sobol_need;
+	}
 	if (cap == t->capacity && S == t->batch_samples) return ADYPT_OK;
 	cudaFree(t->d_rays[0]); cudaFree(t->d_rays[1]); cudaFree(t->d_hit_tri); cudaFree(t->d_hit_uv); cudaFree(t->d_color); cudaFree(t->d_ret);
 	t->d_rays[0] = t->d_rays[1] = nullptr; t->d_hit_tri = nullptr; t->d_hit_uv = nullptr; t->d_color = t->d_ret = nullptr;
@@ -620,10 +716,15 @@ int alloc_wavefront(adypt_tracer *t)
 int trace_primary(adypt_tracer *t, float bx, float by)
 {
 	adypt_scene *s = t->scene;
+	StageTimer tg(t, ADYPT_STAGE_GENERATE);
 	k_generate<<<grid_for(t->npix, 256, s->sm_count), 256, 0, t->stream>>>(t->cam, t->width, t->height, bx, by, t->d_rays[0]);
 	count_launch();
 	ADYPT_CUDA(cudaGetLastError());
-	ADYPT_TRY(launch_trace(s, t->d_rays[0], t->npix, t->d_prim_tri, nullptr, t->d_prim_uv, nullptr, t->stream, nullptr, t->d_counts + kCountSlots));
+	tg.end();
+	StageTimer tt(t, ADYPT_STAGE_TRACE_PRIMARY);
+	ADYPT_TRY(launch_trace(s, t->d_rays[0], t->npix, t->d_prim_tri, nullptr, t->d_prim_uv, nullptr, t->stream, nullptr, t->d_counts + t->work_slot,
+	                       (t->profiling & 2) ? t->d_trace_stats + kStatSlots : nullptr));
+	tt.end();
 	t->host_segments += t->npix;
 	return ADYPT_OK;
 }
@@ -652,15 +753,18 @@ int run_batch(adypt_tracer *t, int first, int n, bool sum_mode)
 		t->prim_block = block;
 	}
 	const int dims = A.dims;
+	StageTimer ts(t, ADYPT_STAGE_OTHER);
 	k_sobol<<<(dims * n + 127) / 128, 128, 0, t->stream>>>(t->d_dirs, dims, first, n, t->d_sobol);
 	count_launch();
-	ADYPT_CUDA(cudaMemsetAsync(t->d_counts, 0, (size_t)(kCountSlots - 1) * sizeof(unsigned long long), t->stream));
+	ADYPT_CUDA(cudaMemsetAsync(t->d_counts, 0, (size_t)t->seg_slot * sizeof(unsigned long long), t->stream)); // queue lengths only
+	ts.end();
+	unsigned long long *trace_stats = (t->profiling & 2) ? t->d_trace_stats : nullptr;
 	ShadeBuffers B;
 	B.tris = s->d_tris; B.mats = s->d_mats; B.texels = s->d_texels; B.tex_table = s->d_tex_table; B.bias = t->d_bias; B.sobol = t->d_sobol;
 	B.prim_tri = t->d_prim_tri; B.prim_uv = t->d_prim_uv;
 	B.in_rays = nullptr; B.in_tri = t->d_hit_tri; B.in_uv = t->d_hit_uv; B.in_count = nullptr;
 	B.out_rays = t->d_rays[1]; B.out_count = t->d_counts + 1;
-	B.color = t->d_color; B.ret = t->d_ret; B.segments = t->d_counts + (kCountSlots - 1);
+	B.color = t->d_color; B.ret = t->d_ret; B.segments = t->d_counts + t->seg_slot;
 	const unsigned long long total = (unsigned long long)n * t->npix;
 	B.conn_rays = nullptr; B.conn_count = nullptr;
 	B.sun_dir[0] = t->sun_dir[0]; B.sun_dir[1] = t->sun_dir[1]; B.sun_dir[2] = t->sun_dir[2];
@@ -673,41 +777,53 @@ int run_batch(adypt_tracer *t, int first, int n, bool sum_mode)
 			t->conn_capacity = total;
 		}
 		B.conn_rays = t->d_conn_rays;
-		B.conn_count = t->d_counts + kConnBase;
+		B.conn_count = t->d_counts + t->conn_base;
 	}
 	// connect stage of bounce b: any-hit over the shadow rays queued by the shade kernel, then add the sun term
 	auto connect = [&](int b) -> int {
 		if (!t->sun_visibility) return ADYPT_OK;
-		ADYPT_TRY(launch_trace(s, t->d_conn_rays, total, nullptr, nullptr, nullptr, t->d_conn_occ, t->stream, t->d_counts + kConnBase + b, t->d_counts + kCountSlots));
-		k_connect_apply<<<grid_for(total, 256, s->sm_count), 256, 0, t->stream>>>(t->d_conn_rays, t->d_conn_occ, t->d_counts + kConnBase + b, t->d_color, t->d_ret);
+		StageTimer tc(t, ADYPT_STAGE_CONNECT);
+		ADYPT_TRY(launch_trace(s, t->d_conn_rays, total, nullptr, nullptr, nullptr, t->d_conn_occ, t->stream, t->d_counts + t->conn_base + b, t->d_counts + t->work_slot));
+		k_connect_apply<<<grid_for(total, 256, s->sm_count), 256, 0, t->stream>>>(t->d_conn_rays, t->d_conn_occ, t->d_counts + t->conn_base + b, t->d_color, t->d_ret);
 		count_launch();
 		ADYPT_CUDA(cudaGetLastError());
+		tc.end();
 		return ADYPT_OK;
 	};
-	k_shade_primary<<<grid_for(total, 256, s->sm_count), 256, 0, t->stream>>>(B, A, t->cam);
-	count_launch();
-	ADYPT_CUDA(cudaGetLastError());
+	{
+		StageTimer tp(t, ADYPT_STAGE_SHADE_PRIMARY);
+		k_shade_primary<<<grid_for(total, 256, s->sm_count), 256, 0, t->stream>>>(B, A, t->cam);
+		count_launch();
+		ADYPT_CUDA(cudaGetLastError());
+		tp.end();
+	}
 	ADYPT_TRY(connect(0));
 	int cur = 1;
 	for (int b = 1; b < c.max_bounce; ++b) {
 		// extend: queue length is read on the device
-		ADYPT_TRY(launch_trace(s, t->d_rays[cur], total, t->d_hit_tri, nullptr, t->d_hit_uv, nullptr, t->stream, t->d_counts + b, t->d_counts + kCountSlots));
+		StageTimer te(t, ADYPT_STAGE_TRACE_BOUNCE);
+		ADYPT_TRY(launch_trace(s, t->d_rays[cur], total, t->d_hit_tri, nullptr, t->d_hit_uv, nullptr, t->stream, t->d_counts + b, t->d_counts + t->work_slot, trace_stats));
+		te.end();
 		B.in_rays = t->d_rays[cur];
 		B.in_count = t->d_counts + b;
 		B.out_rays = t->d_rays[cur ^ 1];
 		B.out_count = t->d_counts + b + 1;
-		if (t->sun_visibility) B.conn_count = t->d_counts + kConnBase + b;
+		if (t->sun_visibility) B.conn_count = t->d_counts + t->conn_base + b;
+		StageTimer tb(t, ADYPT_STAGE_SHADE_BOUNCE);
 		k_shade_bounce<<<grid_for(total, 256, s->sm_count), 256, 0, t->stream>>>(B, A, b, c.ray_tmin);
 		count_launch();
 		ADYPT_CUDA(cudaGetLastError());
+		tb.end();
 		ADYPT_TRY(connect(b));
 		cur ^= 1;
 	}
 	const int g = grid_for(t->npix, 256, s->sm_count);
+	StageTimer ta(t, ADYPT_STAGE_ACCUMULATE);
 	if (sum_mode) k_accumulate_sum<<<g, 256, 0, t->stream>>>(t->d_ret, t->d_sum, t->npix, n, c.clamp);
 	else k_accumulate_mean<<<g, 256, 0, t->stream>>>(t->d_ret, t->d_result, t->npix, first, n, c.clamp);
 	count_launch();
 	ADYPT_CUDA(cudaGetLastError());
+	ta.end();
 	return ADYPT_OK;
 }
 
@@ -741,7 +857,7 @@ int adypt_tracer_create(adypt_scene *scene, const adypt_pt_config *config, int32
 	if (!scene->d_tris || !scene->d_mats) return fail(ADYPT_EINVAL, "scene has no triangles/materials: traversal-only scenes cannot shade");
 	if (scene->bad_matid_tri >= 0)
 		return fail(ADYPT_EINVAL, "triangle " + std::to_string(scene->bad_matid_tri) + " has a material id outside [0, n_materials) (an OBJ face without a usemtl, or an unknown material): the scene can be traversed but not shaded");
-	ADYPT_TRY(check_config(config));
+	ADYPT_TRY(check_config(config, false));
 	DeviceGuard g(scene->device);
 	adypt_tracer *t = new adypt_tracer;
 	t->scene = scene;
@@ -757,13 +873,8 @@ int adypt_tracer_create(adypt_scene *scene, const adypt_pt_config *config, int32
 	if (e == cudaSuccess) e = cudaMalloc((void **)&t->d_prim_tri, np * 4u);
 	if (e == cudaSuccess) e = cudaMalloc((void **)&t->d_prim_uv, np * 8u);
 	if (e == cudaSuccess) e = cudaMalloc((void **)&t->d_bias, np * 2u);
-	if (e == cudaSuccess) e = cudaMalloc((void **)&t->d_dirs, (size_t)sobol_max_dim() * 32u * 4u);
-	if (e == cudaSuccess) e = cudaMalloc((void **)&t->d_sobol, (size_t)sobol_max_dim() * 4u * 4096u);
-	if (e == cudaSuccess) e = cudaMalloc((void **)&t->d_counts, (kCountSlots + 1) * sizeof(unsigned long long));
 	if (e == cudaSuccess) e = cudaMemset(t->d_result, 0, np * 16u);
 	if (e == cudaSuccess) e = cudaMemset(t->d_sum, 0, np * 16u);
-	if (e == cudaSuccess) e = cudaMemset(t->d_counts, 0, (kCountSlots + 1) * sizeof(unsigned long long));
-	if (e == cudaSuccess) e = cudaMemcpy(t->d_dirs, sobol_directions(), (size_t)sobol_max_dim() * 32u * 4u, cudaMemcpyHostToDevice);
 	if (e == cudaSuccess) {
 		try {
 			t->h_bias.resize(np * 2u);
@@ -777,6 +888,13 @@ int adypt_tracer_create(adypt_scene *scene, const adypt_pt_config *config, int32
 	if (e != cudaSuccess) {
 		free_tracer(t);
 		return fail(e == cudaErrorMemoryAllocation ? ADYPT_ENOMEM : ADYPT_ECUDA, std::string("tracer allocation: ") + cudaGetErrorString(e));
+	}
+	{
+		const int rc = alloc_config_buffers(t);
+		if (rc != ADYPT_OK) {
+			free_tracer(t);
+			return rc;
+		}
 	}
 	t->cam.tmin = config->ray_tmin;
 	const float ident[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
@@ -800,13 +918,12 @@ int adypt_tracer_set_config(adypt_tracer *t, const adypt_pt_config *config)
 {
 	return guarded([&]() -> int {
 	if (!t || !config) return fail(ADYPT_EINVAL, "tracer/config is NULL");
-	ADYPT_TRY(check_config(config));
-	if (t->rr_start >= 0 && 3 * config->max_bounce > sobol_max_dim())
-		return fail(ADYPT_ERANGE, "Russian roulette needs 3*maxBounce Sobol dimensions (<= 64)");
+	ADYPT_TRY(check_config(config, t->rr_start >= 0));
+	DeviceGuard g(t->device);
 	t->cfg = *config;
 	t->cam.tmin = config->ray_tmin; // update_config_args, OglPathTracer.cpp:216
 	t->prim_valid = false;
-	return ADYPT_OK;
+	return alloc_config_buffers(t);
 	});
 }
 
@@ -814,8 +931,7 @@ int adypt_tracer_set_russian_roulette(adypt_tracer *t, int32_t start_bounce)
 {
 	return guarded([&]() -> int {
 	if (!t) return fail(ADYPT_EINVAL, "tracer is NULL");
-	if (start_bounce >= 0 && 3 * t->cfg.max_bounce > sobol_max_dim())
-		return fail(ADYPT_ERANGE, "Russian roulette needs 3*maxBounce Sobol dimensions (<= 64)");
+	if (start_bounce >= 0) ADYPT_TRY(check_config(&t->cfg, true));
 	t->rr_start = start_bounce < 0 ? -1 : start_bounce;
 	return ADYPT_OK;
 	});
@@ -882,7 +998,7 @@ int adypt_tracer_primary(adypt_tracer *t, int32_t viewer_type)
 	adypt_scene *s = t->scene;
 	k_generate<<<grid_for(t->npix, 256, s->sm_count), 256, 0, t->stream>>>(t->cam, t->width, t->height, 0.0f, 0.0f, t->d_rays[0]);
 	count_launch();
-	ADYPT_TRY(launch_trace(s, t->d_rays[0], t->npix, t->d_hit_tri, nullptr, t->d_hit_uv, nullptr, t->stream, nullptr, t->d_counts + kCountSlots));
+	ADYPT_TRY(launch_trace(s, t->d_rays[0], t->npix, t->d_hit_tri, nullptr, t->d_hit_uv, nullptr, t->stream, nullptr, t->d_counts + t->work_slot));
 	k_view<<<grid_for(t->npix, 256, s->sm_count), 256, 0, t->stream>>>(s->d_tris, s->d_mats, s->d_texels, s->d_tex_table, t->d_hit_tri, t->d_hit_uv, viewer_type, t->npix, t->d_result);
 	count_launch();
 	ADYPT_CUDA(cudaGetLastError());
@@ -1074,6 +1190,46 @@ int adypt_debug_math(int32_t device, int32_t op, const float *x, const float *y,
 	});
 }
 
+int adypt_tracer_set_profiling(adypt_tracer *t, int32_t flags)
+{
+	return guarded([&]() -> int {
+	if (!t || flags < 0 || flags > 3) return fail(ADYPT_EINVAL, "bad argument");
+	DeviceGuard g(t->device);
+	ADYPT_TRY(resolve_spans(t));
+	if ((flags & 2) && !t->d_trace_stats) {
+		ADYPT_CUDA(cudaMalloc((void **)&t->d_trace_stats, 2 * kStatSlots * sizeof(unsigned long long)));
+		ADYPT_CUDA(cudaMemset(t->d_trace_stats, 0, 2 * kStatSlots * sizeof(unsigned long long)));
+	}
+	t->profiling = flags;
+	return ADYPT_OK;
+	});
+}
+
+int adypt_tracer_get_profile(adypt_tracer *t, adypt_tracer_profile *out, int32_t reset)
+{
+	return guarded([&]() -> int {
+	if (!t || !out) return fail(ADYPT_EINVAL, "NULL argument");
+	DeviceGuard g(t->device);
+	ADYPT_TRY(resolve_spans(t));
+	memset(out, 0, sizeof(*out));
+	for (int i = 0; i < ADYPT_STAGE_COUNT; ++i) {
+		out->stage_ms[i] = t->stage_ms[i];
+		out->stage_launches[i] = t->stage_launches[i];
+	}
+	if (t->d_trace_stats) {
+		unsigned long long h[2 * kStatSlots]; // [0, kStatSlots) bounce queues, [kStatSlots, 2 kStatSlots) primary rays
+		ADYPT_CUDA(cudaStreamSynchronize(t->stream));
+		ADYPT_CUDA(cudaMemcpy(h, t->d_trace_stats, sizeof(h), cudaMemcpyDeviceToHost));
+		out->trace_nodes = h[0]; out->trace_tris = h[1]; out->trace_hits = h[2]; out->trace_max_depth = h[3] > h[kStatSlots + 3] ? h[3] : h[kStatSlots + 3]; out->trace_rays = h[4];
+		out->primary_nodes = h[kStatSlots]; out->primary_tris = h[kStatSlots + 1]; out->primary_hits = h[kStatSlots + 2]; out->primary_rays = h[kStatSlots + 4];
+		if (reset) ADYPT_CUDA(cudaMemset(t->d_trace_stats, 0, sizeof(h)));
+	}
+	if (reset)
+		for (int i = 0; i < ADYPT_STAGE_COUNT; ++i) { t->stage_ms[i] = 0.0; t->stage_launches[i] = 0; }
+	return ADYPT_OK;
+	});
+}
+
 int adypt_tracer_stats(adypt_tracer *t, uint64_t *segments, uint64_t *launches)
 {
 	return guarded([&]() -> int {
@@ -1081,7 +1237,7 @@ int adypt_tracer_stats(adypt_tracer *t, uint64_t *segments, uint64_t *launches)
 	DeviceGuard g(t->scene->device);
 	unsigned long long dev = 0;
 	ADYPT_CUDA(cudaStreamSynchronize(t->stream));
-	ADYPT_CUDA(cudaMemcpy(&dev, t->d_counts + (kCountSlots - 1), sizeof(dev), cudaMemcpyDeviceToHost));
+	ADYPT_CUDA(cudaMemcpy(&dev, t->d_counts + t->seg_slot, sizeof(dev), cudaMemcpyDeviceToHost));
 	if (segments) *segments = t->host_segments + dev;
 	if (launches) *launches = g_launches.load() - t->launches_at_create;
 	return ADYPT_OK;

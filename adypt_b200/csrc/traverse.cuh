@@ -33,7 +33,7 @@ struct TraceParams {
 	float2 *__restrict__ out_uv;            // closest, nullable
 	uint8_t *__restrict__ out_occ;          // any
 	unsigned long long *counter;            // zeroed before launch
-	unsigned long long *stats;              // STATS kernels only: [0] nodes visited [1] triangles tested [2] hits [3] max stack depth
+	unsigned long long *stats;              // STATS kernels only: [0] nodes visited [1] triangles tested [2] hits [3] max stack depth [4] rays
 	int refill_threshold;                   // leave the traversal loop when fewer lanes than this are busy
 	uint32_t magic;                         // 0x4B000000, passed as data so ptxas keeps it in a register (see byte_to_float)
 	uint32_t pool_chunk;                    // most ray indices a warp takes per atomicAdd (multiple of 32, <= kPoolChunk)
@@ -466,6 +466,7 @@ __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const Trac
 		atomicAdd(p.stats + 1, st_tris);
 		atomicAdd(p.stats + 2, st_hits);
 		atomicMax(p.stats + 3, st_depth);
+		if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(p.stats + 4, n_rays);
 	}
 }
 

@@ -1,14 +1,23 @@
 #!/usr/bin/env python3
-"""Headline benchmark: Mrays/s closest-hit on incoherent rays (BASELINE.json configs[1], "C2").
-
-Workload: ~1.0M-triangle procedural box city, 8M incoherent cosine-weighted bounce rays spawned from the hits
-of 1000x1000 primary rays. One "step" = one closest-hit pass over the whole 8M-ray batch.
+"""Benchmark of the hot path (BASELINE.json): Mrays/s closest-hit on incoherent rays per B200 and on N GPUs, and 1080p
+path samples/s.
 
   python bench.py [--gpus N] [--steps K] [--warmup W]            product arm (CUDA, sm_100a)
-  python bench.py --impl reference [...]                          reference arm: the reference's traversal.glsl on the CPU
-  torchrun --nproc-per-node N bench.py --gpus N ...               one rank per GPU, weak scaling (each rank
-                                                                  traces its own 8M-ray batch, no collective)
-Prints ONE JSON line on rank 0. See DESIGN.md §6 for how every field is measured.
+  python bench.py --impl reference [...]                          reference arm: the reference's own shaders on the host cores
+  torchrun --nproc-per-node N bench.py --gpus N ...               one rank per GPU
+
+ONE JSON line on rank 0. The headline (metric / value / e2e / roofline / cpu_baseline) is configs[1] ("C2"): a ~1.0M-triangle
+procedural box city, 8M incoherent cosine-weighted bounce rays spawned from the hits of 1000x1000 primary rays; one step = one
+closest-hit pass over a rank's whole 8M-ray batch (weak scaling: every rank has its own batch, no collective). `aux` carries
+the other measured legs, each with its own keys:
+  aux.c3         configs[2]: 1920x1080, 64 spp, maxBounce 5, wavefront path tracer -- the metric's second half ("1080p path
+                 samples/s") with its own roofline, cpu_baseline and e2e (every rank renders the whole image: weak)
+  aux.c5         configs[4]: 3840x2160, 1024 spp sample-sharded over the N ranks (blocks of tmpLifetime samples round-robin,
+                 pathtracer.glsl:113-127,206-211), ONE NCCL all-reduce of the 132.7 MB sum buffer inside the timed region:
+                 STRONG scaling; compared with the 1-GPU running-mean image (rmse_vs_1gpu)
+  aux.c2_strong  ONE 8M-ray batch cut into contiguous ranges (sharding.ray_range_for_rank), no collective: strong scaling
+  aux.any_hit    the any-hit kernel (traversal.glsl:257-494) over the same rays
+  aux.c4         configs[3] (N = 1 only): 10M-triangle city, closest + any-hit, parity on an oracle slice
 """
 import argparse
 import json
@@ -23,25 +32,58 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-from adypt_b200 import workloads as W  # noqa: E402
+from adypt_b200 import sharding  # noqa: E402  (pure Python)
+from adypt_b200 import workloads as W  # noqa: E402  (pure numpy)
 
 METRIC = "Mrays/s closest-hit (incoherent)"
 UNIT = "Mrays/s"
 CELLS, SCENE_SEED, RAY_SEED, PRIMARY = 183, 1, 42, 1000
+C4_CELLS = 577
 CACHE = os.path.join(ROOT, ".cache", "scenes")
+PT_CFG = dict(max_bounce=5, subpixel=8, tmp_lifetime=16, ray_tmin=1e-4, clamp=4.0, sun=(1.0, 1.0, 1.0))
+C3 = dict(width=1920, height=1080, spp=64)
+C5 = dict(width=3840, height=2160, spp=1024)
+C2_WORKLOAD = "C2: 1M-tri procedural box city (cells=183, seed=1), 8M incoherent cosine-diffuse bounce rays, closest-hit"
+C3_WORKLOAD = ("C3: 1920x1080, 64 spp, maxBounce 5 (primary + 4 bounces), mixed-material 1M-tri city (cells=183, seed=1), pathtracer.glsl "
+               "semantics: no Russian roulette (the reference has none)")
+C5_WORKLOAD = "C5: 3840x2160, 1024 spp, the C3 scene, sample-sharded in tmpLifetime blocks over the GPUs, one all-reduce of the sum buffer"
+L2_NOTE = "GPU arm: a 256 MiB buffer is written between timed steps, outside the events (rays 256 MB + BVH 66 MB also exceed the 126 MB L2)"
 
 
 def log(*a):
     print("[bench]", *a, file=sys.stderr, flush=True)
 
 
-def build_inputs(mixed=False, rank=0, barrier=None):
-    """C2 scene arrays from the product's own host stages (adypt_b200.host): Triangle[] assembly and the
-    from-scratch SBVH -> CWBVH builder, byte-identical to the reference's src/BVH pipeline (tests/
-    test_host_builder.py). The node/index arrays are cached in the reference's own .bvh format
-    (WideBVH.cpp:9-66), as Instance::Initialize does (Instance.cpp:19-31). Nothing here touches oracle/."""
+def workload_config(n_rays, n_tris):
+    """The `config` object: identical in both arms (what differs between them -- timing method, parallelism -- has its own
+    top-level keys)."""
+    return {"workload": C2_WORKLOAD, "triangles": int(n_tris), "rays_per_step": int(n_rays), "ray_seed": RAY_SEED, "l2": L2_NOTE}
+
+
+def peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst copy)"
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+def committed_traffic(name):
+    """DRAM bytes per launch of the dominant kernel, from the committed `ncu --set full` capture (cannot be measured live:
+    a number printed under a profiler is never a bench value). Labelled with the commit the capture was taken at."""
+    p = os.path.join(ROOT, "profiles", name)
+    if not os.path.exists(p):
+        return None, None
+    j = json.load(open(p))
+    return j.get("dram_bytes_per_launch"), {"file": "profiles/" + name, "captured_at": j.get("head", j.get("captured_at", "unknown")), "kernel": j.get("kernel")}
+
+
+# ------------------------------------------------------------------------------------------------ inputs
+def build_inputs(mixed=False, rank=0, barrier=None, cells=CELLS):
+    """Scene arrays from the product's own host stages (adypt_b200.host): Triangle[] assembly and the from-scratch SBVH ->
+    CWBVH builder, byte-identical to the reference's src/BVH pipeline (tests/test_host_builder.py). The node/index arrays are
+    cached in the reference's own .bvh format (WideBVH.cpp:9-66), as Instance::Initialize does (Instance.cpp:19-31)."""
     from adypt_b200 import host
-    mesh = W.city(CELLS, SCENE_SEED, mixed_materials=mixed)
+    mesh = W.city(cells, SCENE_SEED, mixed_materials=mixed)
     hs = host.HostScene.from_triangles(mesh.positions(), mesh.face_mat, host.materials_array(mesh.materials))
     os.makedirs(CACHE, exist_ok=True)
     bvh_path = os.path.join(CACHE, mesh.name + ".bvh")
@@ -50,20 +92,36 @@ def build_inputs(mixed=False, rank=0, barrier=None):
     if not hs.load_bvh(bvh_path):
         t0 = time.perf_counter()
         hs.build_bvh()
-        log(f"built CWBVH in {time.perf_counter() - t0:.1f} s")
+        log(f"built CWBVH of {mesh.name} in {time.perf_counter() - t0:.1f} s")
         hs.save_bvh(bvh_path)
     if barrier is not None and rank == 0:
         barrier()
     return mesh, hs
 
 
-def workload_config(n_rays, extra=None):
-    c = {"workload": "C2: 1M-tri procedural box city (cells=183, seed=1), 8M incoherent cosine-diffuse bounce rays, closest-hit",
-         "triangles": None, "rays_per_step": int(n_rays), "ray_seed": RAY_SEED,
-         "timing": "cuda events per step on the launch stream; 256 MiB L2 flush between steps (outside the events)"}
-    if extra:
-        c.update(extra)
-    return c
+def reference_inputs(mixed=False):
+    """The reference arm's arrays come from the reference's OWN pipeline (oracle/_ref/libadypt_ref.so: src/Util/Scene.cpp +
+    src/BVH/*.cpp compiled unmodified): OBJ -> Triangle[] -> SBVH -> CWBVH, Woop rows as OglScene::init_triangles builds them.
+    No library of the product is loaded in that process."""
+    from oracle import ref
+    if not ref.available():
+        raise SystemExit("bench.py --impl reference: oracle/_ref/libadypt_ref.so is missing (build it with `make -C oracle ref` where "
+                         "/root/reference exists); refusing to substitute the product's builder")
+    mesh = W.city(CELLS, SCENE_SEED, mixed_materials=mixed)
+    os.makedirs(CACHE, exist_ok=True)
+    obj = mesh.write_obj(CACHE)
+    t0 = time.perf_counter()
+    bvh = ref.build(obj)
+    log(f"reference pipeline: {mesh.name}: {bvh.n_tris} tris, {bvh.n_nodes} nodes, {bvh.n_refs} refs ({time.perf_counter() - t0:.1f} s)")
+    return mesh, bvh
+
+
+def glsl_or_die():
+    from oracle import glsl_ref
+    if not glsl_ref.available():
+        raise SystemExit("bench.py: oracle/_ref/libadypt_glsl.so (the reference's shaders compiled for the CPU) is missing; build it with "
+                         "`make -C oracle ref` where /root/reference exists. Refusing to report the oracle port as \"reference\".")
+    return glsl_ref
 
 
 class ClockSampler(threading.Thread):
@@ -94,57 +152,94 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_tracer(bvh):
-    """The CPU implementation timed as the baseline: the reference's own shaders/traversal.glsl compiled for the CPU
-    (oracle/_ref/libadypt_glsl.so, kind "reference") when that build exists, else the oracle's C++ port (kind "port")."""
-    from oracle import cpu, glsl_ref
-    if glsl_ref.available():
-        return (lambda r: glsl_ref.trace_closest(bvh.nodes, bvh.tri_indices, bvh.woop, r)[0]), "reference", \
-            "the reference's shaders/traversal.glsl compiled for the CPU from its own text (oracle/glsl_transpile.py)"
-    return (lambda r: cpu.trace_closest(bvh.nodes, bvh.tri_indices, bvh.woop, r, want_t=False)["tri"]), "port", \
-        "multithreaded C++ port of shaders/traversal.glsl (oracle/oracle.cpp)"
+def bytes_per_ray(nodes, tris, hits, n):
+    """Algorithmic bytes: 80 B per node visited + 48 B per triangle tested + 4 B index remap per hit + 32 B ray in
+    + 16 B hit out."""
+    return 80.0 * nodes / n + 48.0 * tris / n + 4.0 * hits / n + 32.0 + 16.0
 
 
-def cpu_leg(bvh, rays, budget_s=10.0):
-    """The CPU baseline on all host threads over a bounded sample (+ the oracle's counters on the same sample)."""
-    from oracle import cpu
-    cores = cpu.hardware_threads()
+# ------------------------------------------------------------------------------------------------ CPU legs (reference's shaders)
+def time_cpu_rays(trace, rays, budget_s):
+    """trace(rays[:n]) on a bounded prefix of the batch sized for about budget_s seconds; returns (n, seconds, result)."""
     probe = min(rays.shape[0], 262144)
-    bvh.woop = cpu.build_woop(bvh.tris, bvh.tri_indices)
-    trace, kind, what = cpu_tracer(bvh)
     t0 = time.perf_counter()
     trace(rays[:probe])
     rate = probe / (time.perf_counter() - t0)
     n = int(min(rays.shape[0], max(probe, rate * budget_s)))
     t0 = time.perf_counter()
-    tri = trace(rays[:n])
-    dt = time.perf_counter() - t0
+    out = trace(rays[:n])
+    return n, time.perf_counter() - t0, out
+
+
+def cpu_c2(bvh, rays, budget_s=10.0):
+    """cpu_baseline of the headline: the reference's traversal.glsl compiled for the CPU from its own text, all host threads,
+    on a bounded prefix of the same batch; its ids are checked against the oracle port on the same rays."""
+    from oracle import cpu
+    glsl = glsl_or_die()
+    cores = cpu.hardware_threads()
+    n, dt, tri = time_cpu_rays(lambda r: glsl.trace_closest(bvh.nodes, bvh.tri_indices, bvh.woop, r)[0], rays, budget_s)
     r = cpu.trace_closest(bvh.nodes, bvh.tri_indices, bvh.woop, rays[:n], want_t=False)
-    assert np.array_equal(tri, r["tri"]), "CPU baseline and oracle disagree"
-    return dict(value=n / dt / 1e6, unit=UNIT, cores=cores, kind=kind, what=what,
-                sample=f"first {n} of the {rays.shape[0]} rays of the same batch, {cores} threads",
-                per_core=n / dt / 1e6 / cores), r["counters"], n
+    assert np.array_equal(tri, r["tri"]), "reference shader and oracle port disagree"
+    return dict(value=n / dt / 1e6, unit=UNIT, cores=cores, kind="reference",
+                what="the reference's shaders/traversal.glsl compiled for the CPU from its own text (oracle/glsl_transpile.py)",
+                sample=f"first {n} of the {rays.shape[0]} rays of the same batch, {cores} threads", per_core=n / dt / 1e6 / cores), r["counters"], n
 
 
-def bytes_per_ray(nodes, tris, hits, n):
-    """Algorithmic bytes: 80 B per node visited + 48 B per triangle tested + 4 B index remap per
-    hit + 32 B ray in + 16 B hit out."""
-    return 80.0 * nodes / n + 48.0 * tris / n + 4.0 * hits / n + 32.0 + 16.0
+def cpu_render(bvh, width, height, spp, bias):
+    """The reference's pathtracer.glsl dispatched spp times over a width x height image on the host cores, driven as
+    OglPathTracer::Trace does (OglPathTracer.cpp:34-61) with the reference's own Sobol::Next vectors. Returns (seconds, image)."""
+    from oracle import cpu
+    glsl = glsl_or_die()
+    cam = W.city_camera(CELLS)
+    m = cpu.camera_matrices(cam["fov"], cam["yaw"], cam["pitch"], width, height)
+    sob = cpu.sobol_sequence(2 * PT_CFG["max_bounce"], spp)  # == Sobol::Next (tests/test_oracle_pins.py)
+    t0 = time.perf_counter()
+    img, _ = glsl.pt_render(bvh, cam["position"], m["inv_proj"], m["inv_view"], width, height, PT_CFG, bias, sob, 0, spp)
+    return time.perf_counter() - t0, img
 
 
+def reference_bias(npix, seed=7):
+    """The per-pixel Cranley-Patterson bytes the product's tracer derives from bias_seed = 7 (csrc/hostmath.cpp fill_bias: a
+    splitmix64 stream, 8 bytes per step), so both arms shade with the same offsets. The reference itself seeds them from
+    std::random_device (OglPathTracer.cpp:157-161)."""
+    n = npix * 2
+    k = np.arange(1, (n + 7) // 8 + 1, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        s0 = np.uint64(seed) * np.uint64(0x9E3779B97F4A7C15) + np.uint64(0x632BE59BD9B4E019)
+        z = s0 + k * np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return z.astype("<u8").view(np.uint8)[:n].copy()
+
+
+def cpu_c3_baseline(bvh, bias, spp_sample=16):
+    from oracle import cpu
+    cores = cpu.hardware_threads()
+    w, h = C3["width"], C3["height"]
+    dt, _ = cpu_render(bvh, w, h, spp_sample, bias)
+    return dict(value=w * h * spp_sample / dt, unit="path samples/s", cores=cores, kind="reference",
+                what="the reference's shaders/pathtracer.glsl (+ traversal.glsl) compiled for the CPU from its own text, dispatched once per sample",
+                sample=f"the first {spp_sample} of the 64 samples per pixel of the same 1920x1080 image (one tmpLifetime block), {cores} threads", seconds=dt)
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
 def run_reference(args, rank, world):
     if rank != 0:
         return
     from oracle import cpu
-    mesh, bvh = build_inputs()
-    bvh.woop = cpu.build_woop(bvh.tris, bvh.tri_indices)
+    glsl = glsl_or_die()
+    mesh, bvh = reference_inputs()
     cam = W.city_camera(CELLS)
     m = cpu.camera_matrices(cam["fov"], cam["yaw"], cam["pitch"], PRIMARY, PRIMARY)
     prim = cpu.primary_rays(cam["position"], 1e-4, m["inv_proj"], m["inv_view"], PRIMARY, PRIMARY)
     ph = cpu.trace_closest(bvh.nodes, bvh.tri_indices, bvh.woop, prim)
     rays = W.bounce_rays(mesh.positions(), prim, ph["tri"], ph["uv"], per_hit=8, seed=RAY_SEED)
     cores = cpu.hardware_threads()
-    trace, kind, what = cpu_tracer(bvh)
+
+    def trace(r):
+        return glsl.trace_closest(bvh.nodes, bvh.tri_indices, bvh.woop, r)[0]
+
     # bounded sample per step so the whole run ends within minutes on any host
     t0 = time.perf_counter()
     trace(rays[:262144])
@@ -159,37 +254,106 @@ def run_reference(args, rank, world):
     dt = (time.perf_counter() - t0) / args.steps
     v = n / dt / 1e6
     sample = f"first {n} of the {rays.shape[0]} rays per step, {cores} threads"
-    cfg = workload_config(rays.shape[0], {"triangles": int(mesh.n_tris), "timing": "wall clock around the timed steps on the host cores (no GPU work in this arm)"})
-    emit(json.dumps({
+    what = "the reference's shaders/traversal.glsl compiled for the CPU from its own text (oracle/glsl_transpile.py)"
+    out = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": cfg,
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "dtype": "f32", "data": "synthetic", "config": workload_config(rays.shape[0], mesh.n_tris),
+        "timing": "wall clock around the timed steps on the host cores (no GPU work in this arm)",
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample, "what": what},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "inputs": "scene arrays from the reference's own OBJ -> SBVH -> CWBVH pipeline (oracle/_ref/libadypt_ref.so); no product library is loaded",
         "note": "the reference's hot path is GLSL under OpenGL and cannot run headless; timed here on the host cores: " + what,
-    }))
+    }
+    if not args.no_aux:
+        aux = {}
+        # any-hit over the same rays (traversal.glsl:257-494)
+        na, dta, _ = time_cpu_rays(lambda r: glsl.trace_any(bvh.nodes, bvh.woop, r), rays, 8.0)
+        aux["any_hit"] = {"metric": "Mrays/s any-hit (incoherent)", "value": na / dta / 1e6, "unit": UNIT,
+                          "cpu_baseline": {"value": na / dta / 1e6, "unit": UNIT, "cores": cores, "kind": "reference", "sample": f"first {na} of the {rays.shape[0]} rays, {cores} threads"}}
+        # C3 / C5: the reference's pathtracer.glsl on a bounded number of samples of the same images
+        _, mixed = reference_inputs(mixed=True)
+        for key, cfgd, workload, spp_sample in (("c3", C3, C3_WORKLOAD, 16), ("c5", C5, C5_WORKLOAD, 4)):
+            w, h = cfgd["width"], cfgd["height"]
+            dt3, _ = cpu_render(mixed, w, h, spp_sample, reference_bias(w * h))
+            val = w * h * spp_sample / dt3
+            cb = {"value": val, "unit": "path samples/s", "cores": cores, "kind": "reference", "seconds": dt3,
+                  "sample": f"the first {spp_sample} of the {cfgd['spp']} samples per pixel of the same {w}x{h} image, {cores} threads",
+                  "what": "the reference's shaders/pathtracer.glsl (+ traversal.glsl) compiled for the CPU from its own text, dispatched once per sample"}
+            aux[key] = {"metric": "path samples/s", "value": val, "unit": "path samples/s", "config": {"workload": workload}, "scaling": "weak" if key == "c3" else "strong",
+                        "cpu_baseline": cb, "e2e": {"value": val, "unit": "path samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        out["aux"] = aux
+    emit(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------------------ product arm
+class Ctx:
+    pass
+
+
+def max_over_ranks(ctx, x):
+    t = ctx.torch.tensor([float(x)], dtype=ctx.torch.float64, device=ctx.dev)
+    if ctx.dist is not None:
+        ctx.dist.all_reduce(t, op=ctx.dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier(ctx):
+    if ctx.dist is not None:
+        ctx.dist.barrier()
+    ctx.torch.cuda.synchronize()
+
+
+def timed_steps(ctx, step, steps, warmup, flush):
+    """W untimed then K timed steps; CUDA events per step on the launch stream; L2 flushed between steps outside the events.
+    Returns (per-step ms on this rank, launches inside the timed region)."""
+    torch, A = ctx.torch, ctx.A
+    stream = torch.cuda.current_stream()
+    for _ in range(warmup):
+        flush.fill_(1)
+        step()
+    barrier(ctx)
+    l0 = A.launch_count()
+    evs = []
+    for _ in range(steps):
+        flush.fill_(0)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        step()
+        e1.record(stream)
+        evs.append((e0, e1))
+    barrier(ctx)
+    return [a.elapsed_time(b) for a, b in evs], A.launch_count() - l0
 
 
 def run_native(args, rank, world, local_rank):
     import torch
     import adypt_b200 as A
 
-    dist = None
+    ctx = Ctx()
+    ctx.torch, ctx.A, ctx.rank, ctx.world, ctx.local_rank, ctx.args = torch, A, rank, world, local_rank, args
+    ctx.dist = None
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # the collectives of this run (barriers + the C5 all-reduce) are listed on stderr by NCCL itself
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "COLL")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        ctx.dist = dist
     torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
+    ctx.dev = dev = torch.device("cuda", local_rank)
     A.load_library()
+    steps, warmup = args.steps, max(args.warmup, 3)
 
-    mesh, bvh = build_inputs(rank=rank, barrier=dist.barrier if dist is not None else None)
+    mesh, bvh = build_inputs(rank=rank, barrier=ctx.dist.barrier if ctx.dist is not None else None)
     scene = bvh.upload(local_rank)  # OglScene::Initialize: Woop rows are built on the GPU
     tracer = A.Tracer(scene, A.PTConfig.make(), PRIMARY, PRIMARY, bias_seed=7)
     cam = W.city_camera(CELLS)
     tracer.look(cam["position"], cam["yaw"], cam["pitch"], cam["fov"])
     prim = tracer.primary_rays()
     ph = scene.trace_closest(prim)
+    tracer.close()
     # weak scaling: every rank gets its own batch of the same size (different hash seed), no collective
     rays = W.bounce_rays(mesh.positions(), prim, ph["tri"], ph["uv"], per_hit=8, seed=RAY_SEED + rank)
     n = rays.shape[0]
@@ -202,37 +366,11 @@ def run_native(args, rank, world, local_rank):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream()
 
-    def step():
-        scene.trace_closest(d_rays, d_tri, d_t, d_uv, stream=stream.cuda_stream)
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 3)):
-        flush.fill_(1)
-        step()
-    barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.25)
-    l0 = A.launch_count()
-    evs = []
-    for _ in range(args.steps):
-        flush.fill_(0)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        step()
-        e1.record(stream)
-        evs.append((e0, e1))
-    barrier()
-    launches = A.launch_count() - l0
-    step_ms = [a.elapsed_time(b) for a, b in evs]
-    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    ms_per_step = float(total_ms.item()) / args.steps
+    step_ms, launches = timed_steps(ctx, lambda: scene.trace_closest(d_rays, d_tri, d_t, d_uv, stream=stream.cuda_stream), steps, warmup, flush)
+    ms_per_step = max_over_ranks(ctx, sum(step_ms)) / steps
     value = world * n / (ms_per_step * 1e-3) / 1e6
 
     # ---- end to end: host buffers through the C-ABI, H2D + D2H inside the timed region
@@ -242,104 +380,337 @@ def run_native(args, rank, world, local_rank):
     h_uv = torch.empty((n, 2), dtype=torch.float32).pin_memory()
     for _ in range(2):
         scene.trace_closest(h_rays, h_tri, h_t, h_uv, stream=stream.cuda_stream)
-    barrier()
+    barrier(ctx)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         scene.trace_closest(h_rays, h_tri, h_t, h_uv, stream=stream.cuda_stream)
-    barrier()
-    e2e_s = torch.tensor([(time.perf_counter() - t0) / args.steps], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    barrier(ctx)
+    e2e_s = max_over_ranks(ctx, (time.perf_counter() - t0) / steps)
     clocks = sampler.stop()
     assert torch.equal(h_tri.to(dev), d_tri), "host-path results differ from device-path results"
-    e2e = {"value": world * n / float(e2e_s.item()) / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(n * 32), "d2h_bytes_per_step": int(n * 16),
-           "how": "adypt_trace_closest(ADYPT_MEM_HOST) on pinned host arrays (1M-ray chunks pipelined over 3 streams), wall clock around K blocking calls"}
+    chunk = int(os.environ.get("ADYPT_HOST_CHUNK", "0")) or (1 << 19)
+    e2e = {"value": world * n / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(n * 32), "d2h_bytes_per_step": int(n * 16),
+           "how": f"adypt_trace_closest(ADYPT_MEM_HOST) on pinned host arrays ({chunk}-ray chunks pipelined over 3 streams: H2D, traversal, D2H overlap), "
+                  "wall clock around K blocking calls, max over ranks"}
 
     # ---- roofline of the dominant (only) kernel in the step
     st = scene.trace_stats(d_rays)
     bpr = bytes_per_ray(st["nodes"], st["tris"], st["hits"], n)
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst copy)"
-    else:
-        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    peak, peak_src = peak_hbm()
     kernel_ms = float(np.mean(step_ms))
     achieved = bpr * n / (kernel_ms * 1e-3) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "trace_closest_c2_dram.json")
-    if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": "adypt::trace_kernel<false,false>", "bytes_per_ray": bpr, "nodes_per_ray": st["nodes"] / n,
+    traffic, traffic_src = committed_traffic("trace_closest_c2_dram.json")
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "kernel": scene.kernel_name(False), "bytes_per_ray": bpr, "nodes_per_ray": st["nodes"] / n,
                 "tris_per_ray": st["tris"] / n, "hit_fraction": st["hits"] / n, "kernel_ms": kernel_ms, "peak_source": peak_src,
-                "note": "algorithmic bytes (80 B/node + 48 B/Woop + 4 B/hit + 48 B ray io); the 66 MB BVH is L2-resident, so DRAM traffic is far below this"}
+                "note": "algorithmic bytes (80 B/node + 48 B/Woop + 4 B/hit + 48 B ray io) per launch / mean launch time; the 66 MB BVH is L2-resident, so DRAM "
+                        "traffic is far below this and the kernel is bound by instruction issue (DESIGN.md 4.1)"}
 
-    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-           "data": "synthetic", "config": workload_config(n, {"triangles": int(mesh.n_tris), "parallelism": f"{world} independent ray batches (one per GPU), no collective"}),
+           "data": "synthetic", "config": workload_config(n, mesh.n_tris),
+           "timing": "cuda events per step on the launch stream, max over ranks of the K-step sum",
+           "parallelism": f"{world} ray batches of the same size, one per GPU (hash seed 42 + rank), no collective",
            "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks,
            "target": {"Mrays/s": 1500.0, "met": value / world >= 1500.0}}
+
     if not args.no_aux:
-        out["aux"] = path_tracer_aux(A, torch, dist, rank, local_rank, world)
+        aux = {}
+        # ---- any-hit over the same rays
+        d_occ = torch.empty(n, dtype=torch.uint8, device=dev)
+        any_ms, _ = timed_steps(ctx, lambda: scene.trace_any(d_rays, d_occ, stream=stream.cuda_stream), steps, 3, flush)
+        any_step = max_over_ranks(ctx, sum(any_ms)) / steps
+        assert torch.equal(d_occ != 0, d_tri >= 0), "any-hit and closest-hit disagree on which rays hit"
+        aux["any_hit"] = {"metric": "Mrays/s any-hit (incoherent)", "value": world * n / (any_step * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": any_step,
+                          "kernel": scene.kernel_name(True), "scaling": "weak", "occluded_fraction": float((d_occ != 0).float().mean().item()),
+                          "check": "occluded == (closest-hit id != -1) on every ray of the batch"}
+        # ---- ONE batch (rank 0's, seed 42) cut into contiguous ranges: strong scaling, no collective
+        if world > 1:
+            g_rays = rays if rank == 0 else W.bounce_rays(mesh.positions(), prim, ph["tri"], ph["uv"], per_hit=8, seed=RAY_SEED)
+            b, e = sharding.ray_range_for_rank(g_rays.shape[0], rank, world)
+            s_rays = torch.from_numpy(np.ascontiguousarray(g_rays[b:e])).to(dev)
+            s_ms, _ = timed_steps(ctx, lambda: scene.trace_closest(s_rays, d_tri[: e - b], d_t[: e - b], d_uv[: e - b], stream=stream.cuda_stream), steps, 3, flush)
+            worst = max_over_ranks(ctx, sum(s_ms)) / steps
+            aux["c2_strong"] = {"metric": METRIC, "value": g_rays.shape[0] / (worst * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": worst, "scaling": "strong",
+                                "rays_total": int(g_rays.shape[0]), "how": "one 8M-ray batch, contiguous range per rank (sharding.ray_range_for_rank), no collective"}
+            del s_rays
+        else:
+            aux["c2_strong"] = {"metric": METRIC, "value": value, "unit": UNIT, "ms_per_step": ms_per_step, "scaling": "strong", "rays_total": int(n),
+                                "how": "one 8M-ray batch on one GPU (the headline step)"}
+        del d_rays, d_occ, h_rays
+        aux["c3"] = leg_c3(ctx)
+        aux["c5"] = leg_c5(ctx)
+        if world == 1 and not args.no_c4:
+            aux["c4"] = leg_c4(ctx)
+        out["aux"] = aux
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cb, counters, ns = cpu_leg(bvh, rays)
+        from oracle import cpu
+        bvh.woop = cpu.build_woop(bvh.tris, bvh.tri_indices)
+        cb, counters, ns = cpu_c2(bvh, rays)
         out["cpu_baseline"] = cb
         out["roofline"]["oracle_nodes_per_ray"] = counters["nodes"] / ns
         out["roofline"]["oracle_tris_per_ray"] = counters["tris"] / ns
     if rank == 0:
         emit(json.dumps(out))
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+    if ctx.dist is not None:
+        ctx.dist.barrier()
+        ctx.dist.destroy_process_group()
 
 
-def path_tracer_aux(A, torch, dist, rank, local_rank, world):
-    """Second half of BASELINE.json's metric: 1080p path samples/s (configs[2], "C3"): the same city with
-    glossy / mirror / glass / emissive boxes, 1920x1080, maxBounce 5 (4 bounces), 64 spp, no Russian roulette
-    (the reference has none). Each rank renders the full image (weak scaling); wall clock around sample()+sync."""
-    mesh, hs = build_inputs(mixed=True, rank=rank, barrier=dist.barrier if dist is not None else None)
-    scene = hs.upload(local_rank)
-    w, h, spp = 1920, 1080, 64
-    tr = A.Tracer(scene, A.PTConfig.make(sun=(1.0, 1.0, 1.0)), w, h, bias_seed=7)
+def c3_scene(ctx):
+    if getattr(ctx, "mixed", None) is None:
+        mesh, hs = build_inputs(mixed=True, rank=ctx.rank, barrier=ctx.dist.barrier if ctx.dist is not None else None)
+        ctx.mixed = (mesh, hs, hs.upload(ctx.local_rank))
+    return ctx.mixed
+
+
+def leg_c3(ctx):
+    """configs[2]: the metric's second half. Every rank renders the whole 1920x1080 x 64 spp image (weak scaling)."""
+    torch, A = ctx.torch, ctx.A
+    mesh, hs, scene = c3_scene(ctx)
+    w, h, spp = C3["width"], C3["height"], C3["spp"]
+    L = PT_CFG["tmp_lifetime"]
+    tr = A.Tracer(scene, A.PTConfig.make(sun=PT_CFG["sun"]), w, h, bias_seed=7)
     cam = W.city_camera(CELLS)
     tr.look(cam["position"], cam["yaw"], cam["pitch"], cam["fov"])
-    tr.sample(16)
+    st = torch.cuda.ExternalStream(tr.stream())
+    tr.sample(L)  # warm-up: allocations, clocks
     tr.sync()
+    # per-ray work of the wavefront's traversal launches: one untimed render with the instrumented kernel
     tr.primary(0)
+    tr.set_profiling(trace_counters=True)
     s0 = tr.stats()
-    if dist is not None:
-        dist.barrier()
-    t0 = time.perf_counter()
     tr.sample(spp)
-    tr.sync()
-    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=torch.device("cuda", local_rank))
-    if dist is not None:
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    dt = float(dt.item())
-    s1 = tr.stats()
-    seg = s1["segments"] - s0["segments"]
-    out = {"workload": "C3: 1920x1080, 64 spp, maxBounce 5, mixed-material 1M-tri city, wavefront path tracer; no Russian roulette (the reference's pathtracer.glsl has none)",
-           "path_samples_per_s": world * w * h * spp / dt, "path_segments_per_s": world * seg / dt, "segments_per_sample": seg / (w * h * spp),
-           "seconds": dt, "gpu_launches": s1["launches"] - s0["launches"], "scaling": "weak"}
+    pr = tr.profile()
+    cnt, pcnt = pr["trace"], pr["primary"]
+    seg = tr.stats()["segments"] - s0["segments"]
+    # timed renders, stage times from event pairs around every launch
+    reps = 3
+    tr.set_profiling(stage_times=True)
+    tr.profile()
+    step_ms, launches = [], 0
+    for _ in range(reps):
+        tr.primary(0)  # Trace(false): spp back to 0, as the viewer does before "Start"
+        tr.sync()
+        barrier(ctx)
+        l0 = tr.stats()["launches"]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        tr.sample(spp)
+        e1.record(st)
+        tr.sync()
+        step_ms.append(e0.elapsed_time(e1))
+        launches = tr.stats()["launches"] - l0
+    prof = tr.profile()
+    tr.set_profiling()
+    ms = max_over_ranks(ctx, sum(step_ms)) / reps
+    samples = w * h * spp
+    value = ctx.world * samples / (ms * 1e-3)
+
+    # roofline (SURVEY 8d): traversal bytes from the counters + 164 B per shaded segment + 50 B per pixel-sample
+    trace_rays = cnt["rays"] + pcnt["rays"]
+    nodes, tris, hits = cnt["nodes"] + pcnt["nodes"], cnt["tris"] + pcnt["tris"], cnt["hits"] + pcnt["hits"]
+    trace_bytes = 80.0 * nodes + 48.0 * tris + 4.0 * hits + 48.0 * trace_rays
+    # a primary hit is traced once per tmpLifetime block and shaded for each of the block's samples (pathtracer.glsl:113-127)
+    shaded = cnt["hits"] + pcnt["hits"] * L  # segments that fetched a Triangle + Material (misses read neither)
+    shade_bytes = 164.0 * shaded
+    pixel_bytes = 50.0 * samples
+    trace_ms = (prof["stage_ms"]["trace_primary"] + prof["stage_ms"]["trace_bounce"]) / reps
+    trace_launches = (prof["stage_launches"]["trace_primary"] + prof["stage_launches"]["trace_bounce"]) // reps
+    peak, peak_src = peak_hbm()
+    own_ms = float(np.mean(step_ms))
+    roofline = {"bound": "hbm", "kernel": scene.kernel_name(False), "achieved": trace_bytes / (trace_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": trace_bytes / (trace_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                "kernel_ms_per_step": trace_ms, "kernel_launches_per_step": int(trace_launches), "kernel_share_of_step": trace_ms / own_ms,
+                "bytes_per_launch_mean": trace_bytes / max(1, trace_launches), "trace_rays_per_step": int(trace_rays), "bounce_rays_per_step": int(cnt["rays"]),
+                "shaded_segments_per_step": int(shaded), "nodes_per_ray": nodes / trace_rays, "tris_per_ray": tris / trace_rays, "hit_fraction": hits / trace_rays,
+                "bytes_per_path_sample": (trace_bytes + shade_bytes + pixel_bytes) / samples,
+                "step": {"algorithmic_bytes": trace_bytes + shade_bytes + pixel_bytes, "traversal_bytes": trace_bytes, "shading_bytes": shade_bytes, "pixel_bytes": pixel_bytes,
+                         "achieved": (trace_bytes + shade_bytes + pixel_bytes) / (own_ms * 1e-3) / 1e9, "frac": (trace_bytes + shade_bytes + pixel_bytes) / (own_ms * 1e-3) / 1e9 / peak},
+                "stage_ms_per_step": {k: v / reps for k, v in prof["stage_ms"].items()},
+                "note": "dominant kernel = the traversal kernel over all its launches of one 64-spp render (4 primary + 16 bounce queues): algorithmic bytes "
+                        "(80 B/node + 48 B/Woop + 4 B/hit + 48 B ray io, counted by the instrumented kernel on the same queues) / summed launch time (event pairs "
+                        "around every launch); `step` adds 164 B per shaded segment and 50 B per pixel-sample over the whole step time"}
+
+    # end to end through the public API: camera in, 64 x Trace(true), image out to a pinned host buffer
+    host_img = torch.empty((h, w, 4), dtype=torch.float32).pin_memory()
+    tr.look(cam["position"], cam["yaw"], cam["pitch"], cam["fov"])
+    tr.primary(0)
+    tr.sample(spp)
+    tr.read(4, out=host_img)
+    barrier(ctx)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        tr.look(cam["position"], cam["yaw"], cam["pitch"], cam["fov"])  # SetCamera
+        tr.primary(0)                                                    # Trace(false): restart
+        tr.sample(spp)                                                   # 64 x Trace(true)
+        tr.read(4, out=host_img)                                         # glGetTextureImage
+    e2e_s = max_over_ranks(ctx, (time.perf_counter() - t0) / reps)
+    e2e = {"value": ctx.world * samples / e2e_s, "unit": "path samples/s", "h2d_bytes_per_step": 144 + 52, "d2h_bytes_per_step": int(w * h * 16),
+           "how": "Tracer.look (SetCamera: 144-byte camera block + 52-byte argument block, by value) + Tracer.primary (Trace(false)) + Tracer.sample(64) "
+                  "(64 x Trace(true)) + Tracer.read into a pinned host buffer (adypt_tracer_read), wall clock, max over ranks"}
+    out = {"metric": "path samples/s (1080p)", "value": value, "unit": "path samples/s", "ms_per_step": ms, "steps": reps, "higher_is_better": True,
+           "scaling": "weak", "config": {"workload": C3_WORKLOAD, "triangles": int(mesh.n_tris)}, "path_samples_per_s": value,
+           "path_segments_per_s": ctx.world * seg / (ms * 1e-3), "segments_per_sample": seg / samples, "seconds": ms * 1e-3, "gpu_launches": int(launches),
+           "roofline": roofline, "e2e": e2e, "dtype": "f32"}
+    if ctx.rank == 0 and ctx.world == 1 and not ctx.args.no_cpu_baseline:
+        from oracle import cpu
+        hs.woop = cpu.build_woop(hs.tris, hs.tri_indices)
+        out["cpu_baseline"] = cpu_c3_baseline(hs, tr.get_bias())
     # BASELINE.json words configs[2] "4 bounces + Russian roulette": the same render with the opt-in roulette from bounce 1
     tr.set_russian_roulette(1)
     tr.primary(0)
-    tr.sample(16)
-    tr.sync()
+    tr.sample(L)
     tr.primary(0)
     s0 = tr.stats()
-    if dist is not None:
-        dist.barrier()
-    t0 = time.perf_counter()
-    tr.sample(spp)
     tr.sync()
-    dt2 = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=torch.device("cuda", local_rank))
-    if dist is not None:
-        dist.all_reduce(dt2, op=dist.ReduceOp.MAX)
-    dt2 = float(dt2.item())
+    barrier(ctx)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    tr.sample(spp)
+    e1.record(st)
+    tr.sync()
+    ms2 = max_over_ranks(ctx, e0.elapsed_time(e1))
     seg2 = tr.stats()["segments"] - s0["segments"]
-    out["with_russian_roulette"] = {"start_bounce": 1, "path_samples_per_s": world * w * h * spp / dt2, "segments_per_sample": seg2 / (w * h * spp),
-                                    "seconds": dt2, "note": "opt-in extension (adypt_tracer_set_russian_roulette); unbiased, not the reference's image"}
+    out["with_russian_roulette"] = {"start_bounce": 1, "path_samples_per_s": ctx.world * samples / (ms2 * 1e-3), "segments_per_sample": seg2 / samples,
+                                    "seconds": ms2 * 1e-3, "note": "opt-in extension (adypt_tracer_set_russian_roulette); unbiased, not the reference's image"}
+    tr.close()
+    return out
+
+
+def leg_c5(ctx):
+    """configs[4], STRONG scaling: 3840x2160 x 1024 spp; blocks of tmpLifetime samples round-robin over the ranks
+    (pathtracer.glsl:113-127,206-211 couple the samples of a block), every rank adds its blocks' clamped radiance to a sum
+    buffer, ONE all-reduce (NCCL) of that buffer INSIDE the timed region, then sum / count (pathtracer.glsl:224-226 up to the
+    summation order). Device time from events on the tracer's stream, max over ranks."""
+    torch, A, dist = ctx.torch, ctx.A, ctx.dist
+    mesh, hs, scene = c3_scene(ctx)
+    w, h, spp = C5["width"], C5["height"], C5["spp"]
+    L = PT_CFG["tmp_lifetime"]
+    tr = A.Tracer(scene, A.PTConfig.make(sun=PT_CFG["sun"]), w, h, bias_seed=7)
+    cam = W.city_camera(CELLS)
+    tr.look(cam["position"], cam["yaw"], cam["pitch"], cam["fov"])
+    st = torch.cuda.ExternalStream(tr.stream())
+    ptr, nfl = tr.sum_buffer()
+    acc = torch.as_tensor(sharding.DeviceArray(ptr, nfl), device=ctx.dev)
+    reduce_ev = []
+
+    def all_reduce():
+        tr.sync()  # the tracer renders on its own stream; the collective runs on torch's
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        dist.all_reduce(acc, op=dist.ReduceOp.SUM)
+        r1.record()
+        torch.cuda.synchronize()
+        reduce_ev.append(r0.elapsed_time(r1))
+
+    tr.accumulate(0, L)  # warm-up: allocations, clocks
+    tr.sync()
+    if ctx.world > 1:
+        warm = torch.zeros_like(acc)  # one warm-up collective of the same size: NCCL sets up its channels and buffers
+        dist.all_reduce(warm, op=dist.ReduceOp.SUM)
+        del warm
+    barrier(ctx)
+    l0 = tr.stats()["launches"]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record(st)
+    mine = sharding.render_sharded(tr, spp, ctx.rank, ctx.world, all_reduce)
+    e1.record(st)
+    tr.sync()
+    wall = max_over_ranks(ctx, time.perf_counter() - t0)
+    seconds = max_over_ranks(ctx, e0.elapsed_time(e1) * 1e-3)
+    launches = tr.stats()["launches"] - l0
+    samples = w * h * spp
+    out = {"metric": "path samples/s (3840x2160, sample-sharded)", "value": samples / seconds, "unit": "path samples/s", "path_samples_per_s": samples / seconds,
+           "seconds": seconds, "wall_seconds": wall, "scaling": "strong", "higher_is_better": True, "config": {"workload": C5_WORKLOAD, "triangles": int(mesh.n_tris)},
+           "samples_this_rank": int(mine), "blocks_total": (spp + L - 1) // L, "gpu_launches": int(launches),
+           "reduce_ms": max_over_ranks(ctx, reduce_ev[0]) if reduce_ev else 0.0, "reduce_bytes": int(nfl * 4),
+           "reduce": (f"torch.distributed.all_reduce(SUM) over NCCL of the {nfl * 4 / 1e6:.1f} MB sum buffer, inside the timed region" if ctx.world > 1 else "none (one GPU)"),
+           "timing": "cuda events on the tracer's stream around clear + blocks + all-reduce + resolve, max over ranks"}
+    # the N-GPU image against the 1-GPU running mean (the reference's accumulation order): rank 0 renders every sample alone
+    if ctx.rank == 0:
+        rp, rn = tr.result_buffer()
+        got = torch.as_tensor(sharding.DeviceArray(rp, rn), device=ctx.dev).reshape(-1, 4)[:, :3].double()
+        tr2 = A.Tracer(scene, A.PTConfig.make(sun=PT_CFG["sun"]), w, h, bias_seed=7)
+        tr2.look(cam["position"], cam["yaw"], cam["pitch"], cam["fov"])
+        tr2.sample(spp)
+        tr2.sync()
+        qp, qn = tr2.result_buffer()
+        ref = torch.as_tensor(sharding.DeviceArray(qp, qn), device=ctx.dev).reshape(-1, 4)[:, :3].double()
+        out["rmse_vs_1gpu"] = float(torch.sqrt(((got - ref) ** 2).mean()).item())
+        out["max_abs_diff_vs_1gpu"] = float((got - ref).abs().max().item())
+        out["mean_radiance"] = float(got.mean().item())
+        out["rmse_note"] = "against the 1-GPU running mean of all 1024 samples (pathtracer.glsl:224-226): sum-then-divide rounds differently, the samples are identical"
+        del got, ref
+        tr2.close()
+        log(f"C5: {ctx.world} GPU(s), {seconds:.3f} s, reduce {out['reduce_ms']:.3f} ms for {nfl * 4 / 1e6:.1f} MB, rmse vs 1 GPU {out['rmse_vs_1gpu']:.3e}")
+    barrier(ctx)
+    tr.close()
+    return out
+
+
+def leg_c4(ctx):
+    """configs[3] (one GPU): ~10M-triangle city (622 MB of nodes + Woop rows, 5x the L2), 8M closest-hit bounce rays + the
+    any-hit shadow rays of their hits; ids / t / uv against the oracle on a 250k-ray slice."""
+    torch, A = ctx.torch, ctx.A
+    t0 = time.perf_counter()
+    mesh, hs = build_inputs(cells=C4_CELLS)
+    scene = hs.upload(ctx.local_rank)
+    tracer = A.Tracer(scene, A.PTConfig.make(), PRIMARY, PRIMARY, bias_seed=7)
+    cam = W.city_camera(C4_CELLS)
+    tracer.look(cam["position"], cam["yaw"], cam["pitch"], cam["fov"])
+    prim = tracer.primary_rays()
+    ph = scene.trace_closest(prim)
+    tracer.close()
+    rays = W.bounce_rays(mesh.positions(), prim, ph["tri"], ph["uv"], per_hit=8, seed=RAY_SEED)
+    n = rays.shape[0]
+    prep_s = time.perf_counter() - t0
+    dev = ctx.dev
+    d_rays = torch.from_numpy(rays).to(dev)
+    d_tri = torch.empty(n, dtype=torch.int32, device=dev)
+    d_t = torch.empty(n, dtype=torch.float32, device=dev)
+    d_uv = torch.empty((n, 2), dtype=torch.float32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream()
+    steps = 10
+    c_ms, _ = timed_steps(ctx, lambda: scene.trace_closest(d_rays, d_tri, d_t, d_uv, stream=stream.cuda_stream), steps, 3, flush)
+    st = scene.trace_stats(d_rays)
+    tri, uv = d_tri.cpu().numpy(), d_uv.cpu().numpy()
+    shadow = W.shadow_rays(mesh.positions(), tri, uv)
+    ns = shadow.shape[0]
+    d_sh = torch.from_numpy(shadow).to(dev)
+    d_occ = torch.empty(ns, dtype=torch.uint8, device=dev)
+    a_ms, _ = timed_steps(ctx, lambda: scene.trace_any(d_sh, d_occ, stream=stream.cuda_stream), steps, 3, flush)
+    bpr = bytes_per_ray(st["nodes"], st["tris"], st["hits"], n)
+    peak, _ = peak_hbm()
+    cm, am = float(np.mean(c_ms)), float(np.mean(a_ms))
+    traffic, traffic_src = committed_traffic("trace_closest_c4_dram.json")
+    out = {"config": {"workload": f"C4: ~10M-tri procedural box city (cells={C4_CELLS}, seed=1), 8M incoherent closest-hit rays + any-hit shadow rays of their hits towards normalize(0.6,1,0.2)",
+                      "triangles": int(mesh.n_tris)}, "refs": int(hs.tri_indices.size), "nodes": int(hs.nodes.shape[0]),
+           "bvh_bytes": int(hs.nodes.shape[0] * 80 + hs.tri_indices.size * 52), "scene_device_bytes": int(scene.device_bytes()), "prepare_seconds": prep_s,
+           "closest": {"value": n / cm / 1e3, "unit": UNIT, "rays": int(n), "ms_per_step": cm, "nodes_per_ray": st["nodes"] / n, "tris_per_ray": st["tris"] / n,
+                       "hit_fraction": st["hits"] / n, "max_stack": st["max_stack"], "bytes_per_ray": bpr,
+                       "roofline": {"bound": "hbm", "achieved": bpr * n / cm / 1e6, "peak": peak, "unit": "GB/s", "frac": bpr * n / cm / 1e6 / peak, "traffic": traffic, "traffic_source": traffic_src}},
+           "any": {"value": ns / am / 1e3, "unit": UNIT, "rays": int(ns), "ms_per_step": am, "occluded_fraction": float((d_occ != 0).float().mean().item())},
+           "l2_hit": (json.load(open(os.path.join(ROOT, "profiles", "trace_closest_c4_dram.json"))).get("l2_hit_rate") if traffic is not None else None),
+           "dram_bytes": traffic}
+    if not ctx.args.no_cpu_baseline:  # parity at C4 size: the oracle is the checker
+        from oracle import cpu
+        woop = cpu.build_woop(hs.tris, hs.tri_indices)
+        sl = slice(2_000_000, 2_250_000)
+        o = cpu.trace_closest(hs.nodes, hs.tri_indices, woop, rays[sl])
+        t = d_t.cpu().numpy()
+        d_any = torch.empty(n, dtype=torch.uint8, device=dev)
+        scene.trace_any(d_rays, d_any, stream=stream.cuda_stream)
+        torch.cuda.synchronize()
+        oa = cpu.trace_any(hs.nodes, woop, shadow[:250000])
+        out["parity"] = {"oracle_slice_rays": 250000, "ids_equal": float((tri[sl] == o["tri"]).mean()),
+                         "t_bit_equal": float((t[sl].view(np.uint32) == o["t"].view(np.uint32)).mean()),
+                         "uv_bit_equal": float((uv[sl].view(np.uint32) == o["uv"].view(np.uint32)).all(axis=1).mean()),
+                         "any_equals_closest_hit_all_rays": bool(np.array_equal(d_any.cpu().numpy() != 0, tri >= 0)),
+                         "shadow_any_equal": float((d_occ.cpu().numpy()[:250000] == oa["occluded"]).mean())}
+    scene.close()
     return out
 
 
@@ -369,7 +740,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-aux", action="store_true", help="skip the 1080p path-tracing measurement")
+    ap.add_argument("--no-aux", action="store_true", help="headline (C2) only")
+    ap.add_argument("--no-c4", action="store_true", help="skip the 10M-triangle leg (N = 1 only; ~1.5 min of scene preparation)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

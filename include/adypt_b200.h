@@ -166,6 +166,11 @@ int adypt_tracer_set_camera(adypt_tracer *tracer, const float projection[16], co
 int adypt_camera_matrices(float fov_deg, float yaw_deg, float pitch_deg, int32_t width, int32_t height,
                           float projection[16], float view[16]);
 
+/* The vector Sobol::Next writes on its (index+1)-th call after Reset(dim) (src/Util/Sobol.cpp:16-21), in closed form (the
+ * state after n calls is the XOR of the direction numbers selected by the Gray code of n): what the wavefront's samplers use,
+ * here for callers and tests on the host. dim <= 10005 (Sobol.hpp:9), else ADYPT_ERANGE. No GPU needed. */
+int adypt_sobol_vector(uint32_t dim, uint32_t index, float *out);
+
 /* OglPathTracer::Trace(false) (OglPathTracer.cpp:52-60): resets spp to 0 and renders the AOV `viewer_type`
  * (primaryray.glsl:46-94) into the result image. */
 int adypt_tracer_primary(adypt_tracer *tracer, int32_t viewer_type);
@@ -197,6 +202,35 @@ int adypt_tracer_sync(adypt_tracer *tracer);
 int adypt_tracer_primary_rays(adypt_tracer *tracer, float *rays, int memspace);
 /* per-tracer statistics since creation: traced path segments and kernel launches */
 int adypt_tracer_stats(adypt_tracer *tracer, uint64_t *segments, uint64_t *launches);
+
+/* Measurement hooks (bench.py; not in the reference, whose only timer is a wall clock, OglPathTracer.hpp:78-82).
+ * flags bit 0: a CUDA event pair around every stage launch of the wavefront -- adypt_tracer_get_profile then returns the time and
+ * launch count per stage; bit 1: the traversal launches run the INSTRUMENTED kernel, which counts the nodes visited, triangles
+ * tested, hits and rays of the wavefront's queues (the per-ray work behind the roofline's algorithmic bytes, SURVEY.md 8d;
+ * slower, so never set in a timed run). 0 switches both off (the default). */
+enum {
+	ADYPT_STAGE_GENERATE = 0,      /* camera rays */
+	ADYPT_STAGE_TRACE_PRIMARY = 1, /* traversal of the primary rays (once per tmpLifetime block) */
+	ADYPT_STAGE_SHADE_PRIMARY = 2, /* bounce 0 of every sample from the cached primary hit */
+	ADYPT_STAGE_TRACE_BOUNCE = 3,  /* traversal of the bounce queues */
+	ADYPT_STAGE_SHADE_BOUNCE = 4,
+	ADYPT_STAGE_ACCUMULATE = 5,
+	ADYPT_STAGE_CONNECT = 6,       /* optional sun-visibility stage */
+	ADYPT_STAGE_OTHER = 7,         /* Sobol vectors, queue counters */
+	ADYPT_STAGE_COUNT = 8
+};
+typedef struct {
+	double stage_ms[ADYPT_STAGE_COUNT];
+	uint64_t stage_launches[ADYPT_STAGE_COUNT];
+	uint64_t trace_nodes, trace_tris, trace_hits, trace_rays, trace_max_depth; /* the bounce queues (bounce >= 1) */
+	uint64_t primary_nodes, primary_tris, primary_hits, primary_rays;          /* the primary rays (one traversal per tmpLifetime block) */
+} adypt_tracer_profile;
+int adypt_tracer_set_profiling(adypt_tracer *tracer, int32_t flags);
+/* sums since the last reset; blocks until the tracer's stream is idle */
+int adypt_tracer_get_profile(adypt_tracer *tracer, adypt_tracer_profile *out, int32_t reset);
+/* The name (as the driver / ncu / cuobjdump show it, mangled) of the traversal kernel adypt_trace_closest (any_hit = 0) or
+ * adypt_trace_any (any_hit = 1) launches for this scene's current tuning variant. */
+int adypt_trace_kernel_name(adypt_scene *scene, int32_t any_hit, char *buf, uint64_t cap);
 
 /* Evaluates the shading stage's deterministic sin/cos (op 0: out = sin(x), out2 = cos(x)) or pow (op 1: out =
  * pow(x, y)) ON THE GPU for n host values: lets tests check the CUDA copy of the recipe against the CPU oracle's

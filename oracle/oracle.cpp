@@ -31,6 +31,7 @@
 #include <cstdint>
 #include <cstring>
 #include <thread>
+#include <mutex>
 #include <vector>
 
 #include "detmath.h"
@@ -306,34 +307,53 @@ void mat4_rotate(float m[4][4], float angle, Vec3 v)
 
 // ---------------------------------------------------------------------------------------------
 // Sobol (Sobol.cpp:5-21) with direction numbers regenerated from Joe-Kuo parameters
-struct JoeKuo { int s; unsigned a; unsigned m[16]; };
-const JoeKuo kJoeKuo[] = {
-#include "sobol_params.inc"
+// The parameter table is DATA shared with the product (one copy of the published Joe-Kuo constants in the tree, five packed
+// words per dimension; layout in tools/derive_sobol_params.py); the decoder and the recurrence below are the oracle's own.
+const uint32_t kJoeKuoWords[] = {
+#include "../adypt_b200/csrc/sobol_joe_kuo.inc"
 };
-constexpr int kSobolMaxDim = (int)(sizeof(kJoeKuo) / sizeof(kJoeKuo[0]));
-uint32_t g_sobol_v[kSobolMaxDim][32];
-std::atomic<int> g_sobol_ready{0};
+constexpr int kSobolTableDims = (int)(sizeof(kJoeKuoWords) / 20);
+// Sobol.hpp:9 / Sobol.inl:4: 10 005 rows declared, 10 000 listed -- the rest are zero rows (constant 0 output)
+constexpr int kSobolMaxDim = 10005;
+std::vector<uint32_t> g_sobol_rows; // [kSobolMaxDim][32]
+uint32_t (*g_sobol_v)[32] = nullptr;
+std::once_flag g_sobol_once;
+
+struct BitReader { // little-endian bit stream over one 160-bit record
+	const uint32_t *w;
+	int pos = 0;
+	uint32_t take(int n)
+	{
+		uint32_t v = 0;
+		for (int i = 0; i < n; ++i, ++pos) v |= ((w[pos >> 5] >> (pos & 31)) & 1u) << i;
+		return v;
+	}
+};
 
 void sobol_init()
 {
-	if (g_sobol_ready.load()) return;
-	for (int j = 0; j < kSobolMaxDim; ++j) {
-		const JoeKuo &p = kJoeKuo[j];
-		uint32_t m[32];
-		if (p.s == 0) {
-			for (int k = 0; k < 32; ++k) m[k] = 1;
-		} else {
-			for (int k = 0; k < p.s; ++k) m[k] = p.m[k];
-			for (int k = p.s; k < 32; ++k) {
-				uint32_t v = m[k - p.s] ^ (m[k - p.s] << p.s);
-				for (int i = 1; i < p.s; ++i)
-					if ((p.a >> (p.s - 1 - i)) & 1u) v ^= m[k - i] << i;
-				m[k] = v;
+	std::call_once(g_sobol_once, [] {
+		g_sobol_rows.assign((size_t)kSobolMaxDim * 32u, 0u);
+		g_sobol_v = reinterpret_cast<uint32_t (*)[32]>(g_sobol_rows.data());
+		for (int j = 0; j < kSobolTableDims; ++j) {
+			BitReader r{kJoeKuoWords + 5 * j};
+			const int s = (int)r.take(5);
+			const uint32_t a = r.take(16);
+			uint32_t m[32];
+			if (s == 0) {
+				for (int k = 0; k < 32; ++k) m[k] = 1;
+			} else {
+				for (int k = 0; k < s; ++k) m[k] = (r.take(k) << 1) | 1u;
+				for (int k = s; k < 32; ++k) {
+					uint32_t v = m[k - s] ^ (m[k - s] << s);
+					for (int i = 1; i < s; ++i)
+						if ((a >> (s - 1 - i)) & 1u) v ^= m[k - i] << i;
+					m[k] = v;
+				}
 			}
+			for (int k = 0; k < 32; ++k) g_sobol_v[j][k] = m[k] << (31 - k);
 		}
-		for (int k = 0; k < 32; ++k) g_sobol_v[j][k] = m[k] << (31 - k);
-	}
-	g_sobol_ready.store(1);
+	});
 }
 
 inline uint32_t first_zero_bit(uint32_t x) { return x == 0xffffffffu ? 32u : (uint32_t)__builtin_ctz(~x); } // Sobol.cpp:5-14

@@ -5,7 +5,7 @@ place from /root/reference) and, for traversal answers, from the brute-force Woo
 Run in the build container (needs /root/reference):   python tests/golden/make_golden.py
 
 Fixtures (all small):
-  ref_sobol.npz      Sobol::Next output, 64 dims x 300 calls              (src/Util/Sobol.cpp:16-21)
+  ref_sobol.npz      Sobol::Next output, 300 calls: dims 1-64, dims 9901-10005, digest of all 10005              (src/Util/Sobol.cpp:16-21)
   ref_camera.npz     Camera::GetView/GetProjection + glm::inverse for 6 cameras (src/Tracer/Camera.cpp:13-23)
   ref_inverse.npz    glm::inverse on 256 random mat4
   tiny_<kind>.npz    reference-built CWBVH arrays (nodes, tri_indices, woop, tris, mats) of hand-checkable
@@ -47,7 +47,8 @@ def brute(b, rays):
 
 
 def main():
-    save("ref_sobol", seq=ref.sobol_sequence(64, 300))
+    full = ref.sobol_sequence(10005, 300)  # every dimension of the reference's table (Sobol.hpp:9)
+    save("ref_sobol", seq=full[:, :64].copy(), tail=full[:, 9900:].copy(), all_dims_fnv=np.uint64(fnv1a(full)))
     cams = [(45.0, 38.0, -24.0, 1000, 1000), (45.0, 7.0, -31.0, 1920, 1080), (45.0, 0.0, 0.0, 1280, 720),
             (33.3, 181.5, 89.0, 640, 480), (90.0, 359.0, -89.5, 3840, 2160), (60.0, 123.4, 12.3, 333, 777)]
     mats = [ref.camera_matrices(*c) for c in cams]

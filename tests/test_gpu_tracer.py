@@ -160,10 +160,31 @@ def test_config_limits(A):
     g = load_golden("city12")
     sc = A.Scene(g.nodes, g.tri_indices, g.woop, g.tris, g.mats)
     with pytest.raises(A.AdyptError) as e:
-        A.Tracer(sc, A.PTConfig.make(max_bounce=33), 8, 8)
-    assert e.value.code == -6  # ADYPT_ERANGE: 2*maxBounce Sobol dimensions > 64 built in
+        A.Tracer(sc, A.PTConfig.make(max_bounce=5003), 8, 8)
+    assert e.value.code == -6  # ADYPT_ERANGE: 2*maxBounce exceeds the reference's 10 005 Sobol dimensions (Sobol.hpp:9)
+    A.Tracer(sc, A.PTConfig.make(max_bounce=5002), 8, 8).close()
     with pytest.raises(A.AdyptError):
         A.Tracer(A.Scene(g.nodes, g.tri_indices, g.woop), A.PTConfig.make(), 8, 8)  # traversal-only scene cannot shade
+
+
+def test_max_bounce_beyond_64_sobol_dimensions(A, cpu):
+    """maxBounce 40 (80 Sobol dimensions; round 1 stopped at 64) and 150 (300 dimensions, queue counters sized from the
+    configuration): images equal the oracle bit for bit. The reference takes any maxBounce up to 5002 (OglPathTracer.cpp:139,
+    Sobol.hpp:9)."""
+    g = load_golden("city12")
+    for mb, spp in ((40, 20), (150, 4)):
+        cfg = dict(OCFG, max_bounce=mb)
+        sc = A.Scene(g.nodes, g.tri_indices, g.woop, g.tris, g.mats)
+        tr = A.Tracer(sc, A.PTConfig.make(max_bounce=mb, sun=cfg["sun"]), W_, H_, bias_seed=5)
+        cam = g.extra["cam"]
+        tr.look(cam[:3], float(cam[3]), float(cam[4]), float(cam[5]))
+        tr.sample(spp)
+        m = cpu.camera_matrices(float(cam[5]), float(cam[3]), float(cam[4]), W_, H_)
+        exp, _, cnt = cpu.pt_render(g, cam[:3], m["inv_proj"], m["inv_view"], W_, H_, cfg, tr.get_bias(), 0, spp)
+        assert np.array_equal(bits(tr.read(4).reshape(-1, 4)), bits(exp)), mb
+        assert tr.stats()["segments"] == cnt["segments"]
+        tr.close()
+        sc.close()
 
 
 def test_save_exr(A, tmp_path):

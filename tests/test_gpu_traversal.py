@@ -143,8 +143,9 @@ def test_material_id_out_of_range_can_be_traced_but_not_shaded(A, cpu):
     tris = g.tris.copy()
     tris.view(np.int32).reshape(tris.shape[0], 25)[0, 24] = -1
     sc = A.Scene(g.nodes, g.tri_indices, None, tris, g.mats)
-    got = sc.trace_closest(g.rays)
-    exp = cpu.trace_closest(g.nodes, g.tri_indices, g.woop, g.rays)
+    rays = g.extra["rays"]
+    got = sc.trace_closest(rays)
+    exp = cpu.trace_closest(g.nodes, g.tri_indices, g.woop, rays)
     assert np.array_equal(got["tri"], exp["tri"])
     with pytest.raises(A.AdyptError, match="material id"):
         A.Tracer(sc, A.PTConfig.make(), 16, 16, bias_seed=1)

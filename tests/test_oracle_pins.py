@@ -24,15 +24,28 @@ def test_sobol_matches_reference_golden(cpu):
     assert np.all(seq[0] == 0.5)  # first vector is all 0.5
 
 
+def test_sobol_all_10005_dimensions_golden(cpu):
+    """Every dimension the reference carries (Sobol.hpp:9: m_x[10005], Sobol.inl:4: kMatrices[10005][32] with 10 000 rows
+    listed and five zero rows): a digest of Sobol::Next over 10 005 dims x 300 calls, and the last 105 dimensions value by
+    value, both generated from the reference's own generator (tests/golden/make_golden.py)."""
+    z = np.load(os.path.join(GOLDEN, "ref_sobol.npz"))
+    got = cpu.sobol_sequence(10005, 300)
+    assert fnv1a(got) == int(z["all_dims_fnv"]), "Sobol vectors over all 10 005 dimensions differ from the reference's"
+    assert np.array_equal(bits(got[:, 9900:]), bits(z["tail"]))
+    assert np.all(got[:, 10000:] == 0.0) and not np.all(got[1:, 9999] == 0.0)  # the five rows the reference leaves zero
+    for idx in (0, 1, 255, 256, 299):
+        assert np.array_equal(bits(cpu.sobol_at(10005, idx)), bits(got[idx]))
+
+
 def test_sobol_dimension_limit(cpu):
     with pytest.raises(ValueError):
-        cpu.sobol_sequence(65, 1)
+        cpu.sobol_sequence(10006, 1)
 
 
 def test_sobol_directions_live(cpu, refmod):
-    # direction numbers regenerated from Joe-Kuo parameters reproduce the reference generator over 5000 calls
-    a = refmod.sobol_sequence(64, 5000)
-    b = cpu.sobol_sequence(64, 5000)
+    # direction numbers regenerated from Joe-Kuo parameters reproduce the reference generator: all 10 005 dimensions, 2 100 calls
+    a = refmod.sobol_sequence(10005, 2100)
+    b = cpu.sobol_sequence(10005, 2100)
     assert np.array_equal(bits(a), bits(b))
 
 

@@ -64,7 +64,7 @@ def test_gpu_roulette_equals_oracle(A, cpu, start):
 def test_gpu_roulette_needs_enough_sobol_dimensions(A):
     g = load_golden("city12")
     sc = A.Scene(g.nodes, g.tri_indices, g.woop, g.tris, g.mats)
-    tr = A.Tracer(sc, A.PTConfig.make(max_bounce=30), 8, 8, bias_seed=3)  # 2*30 <= 64 but 3*30 > 64
+    tr = A.Tracer(sc, A.PTConfig.make(max_bounce=4000), 8, 8, bias_seed=3)  # 2*4000 <= 10005 but 3*4000 > 10005
     with pytest.raises(A.AdyptError) as e:
         tr.set_russian_roulette(1)
     assert e.value.code == -6
