@@ -90,6 +90,35 @@ __global__ void build_woop_kernel(const uint8_t *__restrict__ tris, const int32_
 	woop[3 * (size_t)i + 2] = make_float4(inv[1][0], inv[1][1], inv[1][2], inv[1][3]);
 }
 
+// Shading records: the wavefront's shading stage gathers one Triangle per segment. The reference's record is
+// 100 bytes at a 100-byte stride (Shape.hpp:70-88) -- 25 scalar loads over 4 or 5 sectors; here it is copied, unchanged, to
+// the start of a 128-byte line (7 vector loads, exactly one L2 line). The shading branch its material selects
+// (pathtracer.glsl:144-201) is also kept as one byte per triangle, so that the stage can regroup a block's segments by
+// branch without touching the record or the material. 1 diffuse (illum 1, and illum 2 with shininess*0.01 <= 0.3), 2 glossy,
+// 3 mirror (illum 3-5), 4 dielectric (6, 7), 5 everything else (passes straight through).
+__global__ void build_shade_records(const uint8_t *__restrict__ tris, const Material *__restrict__ mats, uint32_t n_tris, uint32_t n_mats,
+                                    float4 *__restrict__ shade, uint8_t *__restrict__ tri_class)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_tris) return;
+	const float *p = (const float *)(tris + (size_t)i * 100u);
+	float f[32];
+#pragma unroll
+	for (int k = 0; k < 25; ++k) f[k] = p[k];
+	const int32_t matid = __float_as_int(f[24]);
+	uint32_t cls = 5u;
+	if (matid >= 0 && (uint32_t)matid < n_mats) {
+		const int32_t illum = mats[matid].illum;
+		cls = illum == 1 ? 1u : illum == 2 ? (mats[matid].shininess * 0.01f > 0.3f ? 2u : 1u) : (illum >= 3 && illum <= 5) ? 3u : (illum == 6 || illum == 7) ? 4u : 5u;
+	}
+	f[25] = __uint_as_float(cls);
+#pragma unroll
+	for (int k = 26; k < 32; ++k) f[k] = 0.0f;
+#pragma unroll
+	for (int k = 0; k < 8; ++k) shade[(size_t)i * 8u + k] = make_float4(f[4 * k], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]);
+	tri_class[i] = (uint8_t)cls;
+}
+
 // ------------------------------------------------------------------------------------------------
 // The kernel a launch uses. Variants are code-generation variants of the same algorithm (identical results; tuning and
 // A/B measurements only); 0 = tuned default: 4 conversion planes on the I2F pipe, 8 CTAs/SM, triangle batch 2 with both
@@ -119,7 +148,7 @@ TraceKernel trace_kernel_for(bool any, bool stats, int variant)
 
 // ------------------------------------------------------------------------------------------------
 int launch_trace(adypt_scene *s, const float4 *d_rays, uint64_t n, int32_t *d_tri, float *d_t, float2 *d_uv, uint8_t *d_occ,
-                 cudaStream_t stream, const unsigned long long *d_n, unsigned long long *d_counter, unsigned long long *d_stats)
+                 cudaStream_t stream, const unsigned long long *d_n, unsigned long long *d_counter, unsigned long long *d_stats, const float4 *d_dirs)
 {
 	if (n == 0) return ADYPT_OK;
 	const bool any = d_occ != nullptr;
@@ -128,6 +157,8 @@ int launch_trace(adypt_scene *s, const float4 *d_rays, uint64_t n, int32_t *d_tr
 	p.woop = s->d_woop;
 	p.tri_indices = s->d_tri_indices;
 	p.rays = d_rays;
+	p.dirs = d_dirs ? d_dirs : d_rays + 1;
+	p.ray_stride = d_dirs ? 1u : 2u;
 	p.n = n;
 	p.n_ptr = d_n;
 	p.out_tri = d_tri;
@@ -181,6 +212,8 @@ static void free_scene(adypt_scene *s)
 	cudaFree(s->d_tri_indices);
 	cudaFree(s->d_tris);
 	cudaFree(s->d_mats);
+	cudaFree(s->d_shade);
+	cudaFree(s->d_tri_class);
 	cudaFree(s->d_texels);
 	cudaFree(s->d_tex_table);
 	cudaFree(s->d_counters);
@@ -310,6 +343,17 @@ int adypt_scene_create(const adypt_scene_desc *d, adypt_scene **out)
 		if (e != cudaSuccess) { free_scene(s); return fail(ADYPT_ECUDA, std::string("build_woop_kernel: ") + cudaGetErrorString(e)); }
 	}
 #undef UP
+	if (d->n_tris && d->n_mats) {
+		if (cudaMalloc((void **)&s->d_shade, (size_t)d->n_tris * 128u) != cudaSuccess || cudaMalloc((void **)&s->d_tri_class, (size_t)d->n_tris) != cudaSuccess) {
+			free_scene(s);
+			return fail(ADYPT_ENOMEM, "cudaMalloc shading records");
+		}
+		s->device_bytes += (size_t)d->n_tris * 129u;
+		build_shade_records<<<(d->n_tris + 127) / 128, 128>>>(s->d_tris, s->d_mats, d->n_tris, d->n_mats, s->d_shade, s->d_tri_class);
+		count_launch();
+		cudaError_t e = cudaDeviceSynchronize();
+		if (e != cudaSuccess) { free_scene(s); return fail(ADYPT_ECUDA, std::string("build_shade_records: ") + cudaGetErrorString(e)); }
+	}
 	if (cudaMalloc((void **)&s->d_counters, kCounterSlots * sizeof(unsigned long long)) != cudaSuccess) { free_scene(s); return fail(ADYPT_ENOMEM, "cudaMalloc counters"); }
 	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->occ_closest, trace_kernel<false>, kTraceBlock, 0);
 	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->occ_any, trace_kernel<true>, kTraceBlock, 0);

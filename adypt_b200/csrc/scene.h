@@ -23,6 +23,10 @@ struct adypt_scene {
 	int32_t *d_tri_indices = nullptr;  // n_refs
 	uint8_t *d_tris = nullptr;         // n_tris * 100
 	adypt::Material *d_mats = nullptr; // n_mats
+	// derived at upload, like the Woop rows: the Triangle record on its own 128-byte line (8 x float4: floats 0..24 = the
+	// 100-byte record, float 25 = shading class) and the shading class alone, one byte per triangle
+	float4 *d_shade = nullptr;         // n_tris * 8
+	uint8_t *d_tri_class = nullptr;    // n_tris
 	uchar4 *d_texels = nullptr;        // all textures back to back, RGBX8
 	int4 *d_tex_table = nullptr;       // per texture: (first texel, width, height, 0)
 	uint32_t n_textures = 0;           // TEXTURE_COUNT
@@ -43,10 +47,12 @@ namespace adypt {
 // queue a closest-hit (occ == nullptr) or any-hit (occ != nullptr) traversal of n device rays on `stream`;
 // d_n (nullable): the actual ray count lives in device memory and n is only its upper bound;
 // d_counter (nullable): a work-counter slot owned by `stream` (see above), else one is taken from the scene's ring;
-// d_stats (nullable): kStatSlots counters the INSTRUMENTED kernel adds its work to (measurement runs only)
+// d_stats (nullable): kStatSlots counters the INSTRUMENTED kernel adds its work to (measurement runs only);
+// d_dirs (nullable): the rays come as two arrays, origins+tmin in d_rays and directions in d_dirs (the wavefront's queues), instead of
+// the batch ABI's 32-byte records
 int launch_trace(adypt_scene *s, const float4 *d_rays, uint64_t n, int32_t *d_tri, float *d_t, float2 *d_uv,
                  uint8_t *d_occ, cudaStream_t stream, const unsigned long long *d_n = nullptr, unsigned long long *d_counter = nullptr,
-                 unsigned long long *d_stats = nullptr);
+                 unsigned long long *d_stats = nullptr, const float4 *d_dirs = nullptr);
 
 struct TraceParams;
 using TraceKernel = void (*)(const TraceParams);

@@ -19,6 +19,7 @@
 // double-precision recipes of detmath.cuh -- so images match the CPU oracle bit for bit.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 #include "detmath.cuh"
@@ -113,34 +114,39 @@ __global__ void k_sobol(const uint32_t *__restrict__ dirs, int dims, int first_s
 // shading
 
 struct ShadeBuffers {
-	const uint8_t *__restrict__ tris;        // 100-byte records
+	const float4 *__restrict__ shade;        // 8 x float4 per scene triangle: the Triangle record on a 128-byte line (scene.cu)
+	const uint8_t *__restrict__ tri_class;   // shading branch of a triangle's material (kClass*), for the regrouping pass
 	const Material *__restrict__ mats;
 	const uchar4 *__restrict__ texels;       // diffuse textures, RGBX8 (nullptr when TEXTURE_COUNT == 0)
 	const int4 *__restrict__ tex_table;      // (first texel, width, height, -)
 	const uchar2 *__restrict__ bias;         // uSobolBiasImg
-	const float *__restrict__ sobol;         // [S][2*max_bounce]
+	const float *__restrict__ sobol;         // [S][dims]
 	// primary hit cache (uPrimaryTmpImg): x = tri id bits, zw = uv
 	const int32_t *__restrict__ prim_tri;
 	const float2 *__restrict__ prim_uv;
-	// current queue (bounce >= 1)
-	const float4 *__restrict__ in_rays;      // 2 per entry; .w of the 2nd = path id bits
+	// current queue (bounce >= 1), structure of arrays: ray origins (+ tmin) and directions (.w = path id bits) as the traversal
+	// kernel takes them, the hits it wrote, and per entry the path's throughput + its pixel's bias bytes (xyz = colour,
+	// w = bias.x | bias.y << 8). Shading reads the direction but not the origin, so the two are kept apart.
+	const float4 *__restrict__ in_org;
+	const float4 *__restrict__ in_dir;
 	const int32_t *__restrict__ in_tri;
 	const float2 *__restrict__ in_uv;
+	const float4 *__restrict__ in_state;
 	const unsigned long long *in_count;
 	// next queue
-	float4 *__restrict__ out_rays;
+	float4 *__restrict__ out_org;
+	float4 *__restrict__ out_dir;
+	float4 *__restrict__ out_state;
 	unsigned long long *out_count;
-	// per-path state
-	float4 *__restrict__ color;              // throughput
-	float4 *__restrict__ ret;                // radiance so far; final value once the path ends
+	// per-path radiance so far (final once the path ends); written by bounce 0, then only touched when something is added
+	float4 *__restrict__ ret;
 	unsigned long long *segments;            // statistics
 	// connect stage (optional): shadow rays towards a fixed sun direction for paths that left the scene
 	float4 *__restrict__ conn_rays;          // nullptr when the stage is off
+	float4 *__restrict__ conn_color;         // what the path adds to ret if its shadow ray is unoccluded
 	unsigned long long *conn_count;
 	float sun_dir[3];
 };
-
-__device__ __forceinline__ V3 load3(const float *p) { return v3(p[0], p[1], p[2]); }
 
 __device__ __forceinline__ V3 bary(const float *a, const float *b, const float *c, float u, float v) // :77-85
 {
@@ -173,17 +179,6 @@ __device__ __forceinline__ V3 sample_texture(const uchar4 *__restrict__ texels, 
 	return c00 * w00 + c10 * w10 + c01 * w01 + c11 * w11;
 }
 
-// diffuse colour of FetchInfo (pathtracer.glsl:87-98) / primaryray.glsl:59-71
-__device__ __forceinline__ V3 diffuse_of(const uchar4 *__restrict__ texels, const int4 *__restrict__ tex_table, const Material &m, const float *t, float u, float v)
-{
-	if (texels != nullptr && m.dtex != -1) {
-		const float w = 1.0f - u - v;
-		const float s = t[18] * u + t[20] * v + t[22] * w, tt = t[19] * u + t[21] * v + t[23] * w;
-		return sample_texture(texels, tex_table[m.dtex], s, tt);
-	}
-	return v3(m.dr, m.dg, m.db);
-}
-
 __device__ __forceinline__ V3 sample_hemisphere(float rx, float ry, float e) // :52-64
 {
 	rx *= 6.28318530718f;
@@ -202,43 +197,53 @@ __device__ __forceinline__ V3 align_direction(V3 dir, V3 target) // :66-71
 	return u * dir.x + v * dir.y + target * dir.z;
 }
 
-enum SegmentResult { kEnded = 0, kContinues = 1, kConnects = 2 };
+// What FetchInfo (pathtracer.glsl:73-100) returns for a hit, plus the material fields the switch of Render needs
+struct Surface {
+	V3 normal, origin, emissive, diffuse, specular;
+	int32_t illum;
+	float shininess, ior;
+};
 
-// One segment of Render's loop body after the intersection (pathtracer.glsl:130-201).
-// kContinues: the path goes on with (origin, dir). kEnded: ret is final. kConnects (only when the connect
-// stage is on): the path left the scene; `color` now holds the sun contribution that is added to ret iff the
-// shadow ray from `origin` towards the sun is unoccluded -- the test the reference carries commented out at
-// pathtracer.glsl:132.
-__device__ __forceinline__ SegmentResult shade_segment(const ShadeBuffers &B, const PTArgs &A, int b, int32_t tri_idx, float u, float v, float rx,
-                                              float ry, float xi, V3 &origin, V3 &dir, V3 &color, V3 &ret)
+// FetchInfo for scene triangle tri_idx at (u, v). The Triangle record is read from its 128-byte line: floats 0..24 are the
+// reference's Triangle (Shape.hpp:70-88: p1 p2 p3, n1 n2 n3, tc1 tc2 tc3, matid), so the arithmetic is unchanged.
+__device__ __forceinline__ void fetch_surface(const ShadeBuffers &B, int32_t tri_idx, float u, float v, Surface &s)
 {
-	if (tri_idx == -1) { // :130-135
-		if (B.conn_rays != nullptr) {
-			color = color * v3(A.sun[0], A.sun[1], A.sun[2]);
-			return kConnects;
-		}
-		ret = ret + color * v3(A.sun[0], A.sun[1], A.sun[2]);
-		return kEnded;
-	}
-	const float *t = (const float *)(B.tris + (size_t)tri_idx * 100u);
-	const int32_t matid = *(const int32_t *)(t + 24);
-	const Material m = B.mats[matid];
-	V3 normal = normalize(bary(t + 9, t + 12, t + 15, u, v));
-	origin = bary(t, t + 3, t + 6, u, v); // :138
-	const V3 emissive = v3(m.er, m.eg, m.eb), diffuse = diffuse_of(B.texels, B.tex_table, m, t, u, v), specular = v3(m.sr, m.sg, m.sb);
-	ret = ret + color * emissive;
-	if (b == A.max_bounce - 1) return kEnded; // the loop ends here; the sampled direction would never be used
-	if (m.illum < 6 && dot(dir, normal) > 0.0f) normal = -normal; // :141-142
+	const float4 *rec = B.shade + (size_t)tri_idx * 8u;
+	const float4 r0 = __ldg(rec), r1 = __ldg(rec + 1), r2 = __ldg(rec + 2), r3 = __ldg(rec + 3), r4 = __ldg(rec + 4), r6 = __ldg(rec + 6);
+	const float t[18] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, r3.w, r4.x, r4.y};
+	const Material m = B.mats[__float_as_int(r6.x)];
+	s.normal = normalize(bary(t + 9, t + 12, t + 15, u, v));
+	s.origin = bary(t, t + 3, t + 6, u, v); // :138
+	s.emissive = v3(m.er, m.eg, m.eb);
+	s.specular = v3(m.sr, m.sg, m.sb);
+	if (B.texels != nullptr && m.dtex != -1) { // :87-98 / primaryray.glsl:59-71
+		const float4 r5 = __ldg(rec + 5);
+		const float w = 1.0f - u - v;
+		const float ss = r4.z * u + r5.x * v + r5.z * w, tt = r4.w * u + r5.y * v + r5.w * w;
+		s.diffuse = sample_texture(B.texels, B.tex_table[m.dtex], ss, tt);
+	} else
+		s.diffuse = v3(m.dr, m.dg, m.db);
+	s.illum = m.illum;
+	s.shininess = m.shininess;
+	s.ior = m.ior;
+}
+
+// The material switch of Render (pathtracer.glsl:141-201) for a segment that hit surface s coming along `dir` with
+// throughput `color`: true = the path goes on along the new dir with the new color, false = it ends here.
+__device__ __forceinline__ bool scatter(const PTArgs &A, int b, const Surface &s, float rx, float ry, float xi, V3 &dir, V3 &color)
+{
+	V3 normal = s.normal;
+	if (s.illum < 6 && dot(dir, normal) > 0.0f) normal = -normal; // :141-142
 
 	bool do_diffuse = false;
-	switch (m.illum) { // :144-201
+	switch (s.illum) { // :144-201
 	case 2: {
-		const float e = m.shininess * 0.01f;
+		const float e = s.shininess * 0.01f;
 		if (e > 0.3f) {
-			const V3 r = reflect(dir, normal), s = sample_hemisphere(rx, ry, e);
-			dir = align_direction(s, r);
-			if (dot(dir, normal) < 0.0f) return kEnded;
-			color = color * (diffuse + specular * detmath::pow(dot(dir, r), e));
+			const V3 r = reflect(dir, normal), h = sample_hemisphere(rx, ry, e);
+			dir = align_direction(h, r);
+			if (dot(dir, normal) < 0.0f) return false;
+			color = color * (s.diffuse + s.specular * detmath::pow(dot(dir, r), e));
 		} else
 			do_diffuse = true;
 		break;
@@ -247,11 +252,11 @@ __device__ __forceinline__ SegmentResult shade_segment(const ShadeBuffers &B, co
 		do_diffuse = true;
 		break;
 	case 3: case 4: case 5:
-		color = color * specular;
+		color = color * s.specular;
 		dir = reflect(dir, normal);
 		break;
 	case 6: case 7: {
-		float eta = m.ior;
+		float eta = s.ior;
 		float cosi = dot(dir, normal);
 		float fresnel, etai, etat;
 		if (cosi > 0.0f) { etai = eta; etat = 1.0f; }
@@ -277,17 +282,21 @@ __device__ __forceinline__ SegmentResult shade_segment(const ShadeBuffers &B, co
 	}
 	if (do_diffuse) { // :156-159
 		dir = align_direction(sample_hemisphere(rx, ry, 0.0f), normal);
-		color = color * diffuse;
+		color = color * s.diffuse;
 	}
 	// Russian roulette (BASELINE.json configs[2]; not in the reference, off unless adypt_tracer_set_russian_roulette
 	// asked for it): survive with probability p = min(1, max(color)), then weight by 1/p. xi = this bounce's draw.
 	if (A.rr_start >= 0 && b >= A.rr_start) {
 		const float p = glsl_min(1.0f, glsl_max(color.x, glsl_max(color.y, color.z)));
-		if (!(xi < p)) return kEnded;
+		if (!(xi < p)) return false;
 		color = v3(__fdiv_rn(color.x, p), __fdiv_rn(color.y, p), __fdiv_rn(color.z, p));
 	}
-	return kContinues;
+	return true;
 }
+
+// x + a == x bit for bit when every component of a is +-0 (x is never -0 here: radiance sums start at +0 and (+0) + (-0) = +0),
+// so such an addition -- a non-emissive hit, the common case -- needs no read-modify-write of the path's radiance. NaN compares unequal.
+__device__ __forceinline__ bool adds_nothing(V3 a) { return a.x == 0.0f && a.y == 0.0f && a.z == 0.0f; }
 
 // warp-aggregated append: returns this lane's slot in the output queue (valid when `keep`)
 __device__ __forceinline__ unsigned long long queue_append(bool keep, unsigned long long *counter)
@@ -301,122 +310,243 @@ __device__ __forceinline__ unsigned long long queue_append(bool keep, unsigned l
 	return base + (unsigned long long)__popc(m & ((1u << lane) - 1u));
 }
 
-// bounce 0 for every (sample, pixel) of the batch: reads the cached primary hit
-__global__ void __launch_bounds__(256, 4) k_shade_primary(ShadeBuffers B, PTArgs A, CameraArgs cam)
+// Bounce 0 of the batch's S samples. All samples of a tmpLifetime block share the primary hit and the camera ray
+// (pathtracer.glsl:113-127, 206-211), so a thread takes one pixel and a GROUP of its samples: FetchInfo, the normal and the
+// emission term are evaluated once per group and only the material switch -- the part that consumes the sample's Sobol pair --
+// runs per sample. The queue slot of sample k is requested (one atomic per warp) before sample k+1 is shaded and used after,
+// so the atomic's latency hides behind that work. Path id = s * npix + pixel.
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(256, MIN_CTAS) k_shade_primary(ShadeBuffers B, PTArgs A, CameraArgs cam, int group)
 {
-	const unsigned long long npix = (unsigned long long)A.width * (unsigned long long)A.height;
-	const unsigned long long total = npix * (unsigned long long)A.n_samples;
+	const unsigned npix = (unsigned)A.width * (unsigned)A.height;
+	const unsigned n_groups = ((unsigned)A.n_samples + (unsigned)group - 1u) / (unsigned)group;
+	const unsigned long long items = (unsigned long long)npix * n_groups;
 	const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-	const unsigned long long rounds = (total + stride - 1) / stride;
+	const unsigned long long rounds = (items + stride - 1u) / stride;
+	const unsigned lane = threadIdx.x & 31u;
 	float bx, by;
 	subpixel_bias(A.subpixel, A.tmp_lifetime, A.first_spp, &bx, &by);
 	const int dims = A.dims;
+	const V3 sun = v3(A.sun[0], A.sun[1], A.sun[2]);
+	const bool last = A.max_bounce == 1; // the loop of Render ends after this segment
 	for (unsigned long long r = 0; r < rounds; ++r) {
-		const unsigned long long id = r * stride + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-		bool keep = false, conn = false;
-		V3 origin = v3(cam.origin[0], cam.origin[1], cam.origin[2]), dir = v3(0, 0, 0), color = v3(1.f, 1.f, 1.f), ret = v3(0.f, 0.f, 0.f);
-		if (id < total) {
-			const unsigned pix = (unsigned)(id % npix), s = (unsigned)(id / npix);
-			dir = camera_dir(cam, A.width, A.height, (int)(pix % (unsigned)A.width), (int)(pix / (unsigned)A.width), bx, by);
+		const unsigned long long item = r * stride + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+		const bool live = item < items;
+		const unsigned pix = live ? (unsigned)(item % npix) : 0u;
+		const int s_first = live ? (int)(item / npix) * group : 0;
+		V3 dir0 = v3(0, 0, 0), ret0 = v3(0.f, 0.f, 0.f);
+		Surface sf;
+		sf.illum = 0;
+		sf.origin = v3(0, 0, 0);
+		bool hit = false;
+		float fbx = 0.f, fby = 0.f;
+		unsigned bias_bits = 0u;
+		if (live) {
+			dir0 = camera_dir(cam, A.width, A.height, (int)(pix % (unsigned)A.width), (int)(pix / (unsigned)A.width), bx, by);
 			const uchar2 bb = B.bias[pix];
-			const float rx = fract(B.sobol[s * dims + 0] + (float)bb.x / 255.0f);
-			const float ry = fract(B.sobol[s * dims + 1] + (float)bb.y / 255.0f);
-			const float xi = A.rr_start >= 0 ? fract(B.sobol[s * dims + 2 * A.max_bounce] + (float)bb.x / 255.0f) : 0.0f;
-			const float2 uv = B.prim_uv[pix];
-			const SegmentResult res = shade_segment(B, A, 0, B.prim_tri[pix], uv.x, uv.y, rx, ry, xi, origin, dir, color, ret);
-			keep = res == kContinues;
-			conn = res == kConnects; // origin is still the camera position
-			B.ret[id] = make_float4(ret.x, ret.y, ret.z, 0.0f);
-			if (keep || conn) B.color[id] = make_float4(color.x, color.y, color.z, 0.0f);
+			fbx = (float)bb.x / 255.0f;
+			fby = (float)bb.y / 255.0f;
+			bias_bits = (unsigned)bb.x | ((unsigned)bb.y << 8);
+			const int32_t tri = B.prim_tri[pix];
+			hit = tri != -1;
+			if (hit) {
+				const float2 uv = B.prim_uv[pix];
+				fetch_surface(B, tri, uv.x, uv.y, sf);
+				ret0 = ret0 + v3(1.f, 1.f, 1.f) * sf.emissive; // :139 with color = 1, ret = 0
+			} else if (B.conn_rays == nullptr)
+				ret0 = ret0 + v3(1.f, 1.f, 1.f) * sun; // :130-135
 		}
-		const unsigned long long slot = queue_append(keep, B.out_count);
-		if (keep) {
-			B.out_rays[2 * slot] = make_float4(origin.x, origin.y, origin.z, cam.tmin);
-			B.out_rays[2 * slot + 1] = make_float4(dir.x, dir.y, dir.z, __uint_as_float((unsigned)id));
-		}
-		if (B.conn_rays != nullptr) {
-			const unsigned long long cs = queue_append(conn, B.conn_count);
-			if (conn) {
-				B.conn_rays[2 * cs] = make_float4(origin.x, origin.y, origin.z, cam.tmin);
-				B.conn_rays[2 * cs + 1] = make_float4(B.sun_dir[0], B.sun_dir[1], B.sun_dir[2], __uint_as_float((unsigned)id));
+		// software pipeline over the group's samples: [request the slot of sample k-1] [shade sample k] [store sample k-1]
+		bool p_keep = false;
+		V3 p_dir = v3(0, 0, 0), p_color = v3(0, 0, 0);
+		unsigned p_id = 0u;
+		for (int k = 0; k <= group; ++k) {
+			const unsigned m = __ballot_sync(kFullMask, p_keep);
+			const unsigned leader = m ? (unsigned)__ffs((int)m) - 1u : 0u;
+			unsigned long long base = 0;
+			if (m != 0u && lane == leader) base = atomicAdd(B.out_count, (unsigned long long)__popc(m));
+
+			const int sidx = s_first + k;
+			const bool have = live && k < group && sidx < A.n_samples;
+			bool keep = false, conn = false;
+			V3 dir = dir0, color = v3(1.f, 1.f, 1.f);
+			const unsigned id = (unsigned)sidx * npix + pix;
+			if (have) {
+				B.ret[id] = make_float4(ret0.x, ret0.y, ret0.z, 0.0f);
+				if (!hit) {
+					conn = B.conn_rays != nullptr; // the shadow ray starts at the camera
+					color = color * sun;
+				} else if (!last) {
+					const float rx = fract(B.sobol[sidx * dims + 0] + fbx);
+					const float ry = fract(B.sobol[sidx * dims + 1] + fby);
+					const float xi = A.rr_start >= 0 ? fract(B.sobol[sidx * dims + 2 * A.max_bounce] + fbx) : 0.0f;
+					keep = scatter(A, 0, sf, rx, ry, xi, dir, color);
+				}
 			}
+			if (B.conn_rays != nullptr) {
+				const unsigned long long cs = queue_append(conn, B.conn_count);
+				if (conn) {
+					B.conn_rays[2 * cs] = make_float4(cam.origin[0], cam.origin[1], cam.origin[2], cam.tmin);
+					B.conn_rays[2 * cs + 1] = make_float4(B.sun_dir[0], B.sun_dir[1], B.sun_dir[2], __uint_as_float(id));
+					B.conn_color[cs] = make_float4(color.x, color.y, color.z, 0.0f);
+				}
+			}
+
+			if (m != 0u) {
+				base = __shfl_sync(kFullMask, base, (int)leader);
+				if (p_keep) {
+					const unsigned long long slot = base + (unsigned long long)__popc(m & ((1u << lane) - 1u));
+					B.out_org[slot] = make_float4(sf.origin.x, sf.origin.y, sf.origin.z, cam.tmin);
+					B.out_dir[slot] = make_float4(p_dir.x, p_dir.y, p_dir.z, __uint_as_float(p_id));
+					B.out_state[slot] = make_float4(p_color.x, p_color.y, p_color.z, __uint_as_float(bias_bits));
+				}
+			}
+			p_keep = keep; p_dir = dir; p_color = color; p_id = id;
 		}
 	}
 }
 
+enum { kClassMiss = 0, kClassDiffuse = 1, kClassGlossy = 2, kClassMirror = 3, kClassGlass = 4, kClassOther = 5, kClassNone = 7 };
+
 // bounce b >= 1 over the current queue
-__global__ void __launch_bounds__(256, 4) k_shade_bounce(ShadeBuffers B, PTArgs A, int b, float tmin)
+template <int MIN_CTAS, int BLOCK>
+__global__ void __launch_bounds__(BLOCK, MIN_CTAS) k_shade_bounce(ShadeBuffers B, PTArgs A, int b, float tmin)
 {
-	const unsigned long long npix = (unsigned long long)A.width * (unsigned long long)A.height;
+	const unsigned npix = (unsigned)A.width * (unsigned)A.height;
 	const unsigned long long total = *B.in_count;
 	const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
 	const unsigned long long rounds = (total + stride - 1) / stride;
 	const int dims = A.dims;
+	const bool last = b == A.max_bounce - 1; // the loop of Render ends after this segment: only the emission / sun terms are left
 	if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(B.segments, total);
-	// Each block regroups its 256 queue entries by shading branch before shading them, so that a warp mostly runs ONE
-	// of miss / diffuse / glossy / mirror / glass instead of all of them one after the other (measured 13.4 of 32
-	// lanes active without this). Which lane shades which entry never reaches the image: every path writes its own
-	// slots, and the next queue's order is free.
-	__shared__ unsigned s_class_count[8];
-	__shared__ unsigned short s_order[256];
-	for (unsigned long long r = 0; r < rounds; ++r) {
-		const unsigned long long q0 = r * stride + (unsigned long long)blockIdx.x * blockDim.x;
-		if (threadIdx.x < 8) s_class_count[threadIdx.x] = 0u;
-		__syncthreads();
-		unsigned cls = 7u, rank = 0u; // 7 = past the end of the queue
-		if (q0 + threadIdx.x < total) {
-			const int32_t tri_idx = B.in_tri[q0 + threadIdx.x];
-			if (tri_idx == -1) cls = 0u;
-			else {
-				const int32_t matid = *(const int32_t *)(B.tris + (size_t)tri_idx * 100u + 96u);
-				const int32_t illum = B.mats[matid].illum;
-				cls = illum == 1 ? 1u : illum == 2 ? (B.mats[matid].shininess * 0.01f > 0.3f ? 2u : 1u) : (illum >= 3 && illum <= 5) ? 3u
-				      : (illum == 6 || illum == 7) ? 4u : 5u;
-			}
+	// Each block regroups its BLOCK (256) queue entries by shading branch before shading them, so that a warp mostly runs ONE of
+	// miss / diffuse / glossy / mirror / glass instead of all of them one after the other (13.4 of 32 lanes active without
+	// this). Which lane shades which entry never reaches the image: every path owns its slots and the next queue's order is
+	// free. The branch comes from a one-byte-per-triangle table, the hit index of the NEXT round is already in flight while
+	// this one is shaded, and ranks come from one match.any per warp: two barriers per round, no shared-memory atomics.
+	constexpr unsigned kWarps = BLOCK / 32;
+	static_assert(BLOCK == 256 || BLOCK == 128, "eight or four warps");
+	__shared__ __align__(16) unsigned s_count[2][8][kWarps]; // [round parity][class][warp]; the other parity is zeroed for the next round
+	__shared__ unsigned short s_order[BLOCK];             // regrouped position -> entry of the round
+	__shared__ int32_t s_tri[BLOCK];                    // regrouped position -> hit triangle
+	const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+	const unsigned lt_mask = (1u << lane) - 1u;
+	unsigned long long q0 = (unsigned long long)blockIdx.x * blockDim.x;
+	// two rounds of look-ahead: the hit index of round r+2 and the class byte of round r+1 are in flight while round r is shaded
+	int32_t tri_cur = -2, tri_n1 = -2;       // -2 = past the end of the queue
+	unsigned cls_cur = (unsigned)kClassNone;
+	if (rounds > 0) {
+		if (q0 + threadIdx.x < total) tri_cur = B.in_tri[q0 + threadIdx.x];
+		if (rounds > 1 && q0 + stride + threadIdx.x < total) tri_n1 = B.in_tri[q0 + stride + threadIdx.x];
+		cls_cur = tri_cur == -2 ? (unsigned)kClassNone : tri_cur == -1 ? (unsigned)kClassMiss : (unsigned)B.tri_class[tri_cur];
+	}
+	if (threadIdx.x < 16u * kWarps) (&s_count[0][0][0])[threadIdx.x] = 0u;
+	__syncthreads();
+	for (unsigned long long r = 0; r < rounds; ++r, q0 += stride) {
+		const int32_t tri_mine = tri_cur;
+		const unsigned cls = cls_cur;
+		{
+			const unsigned long long q2 = q0 + 2u * stride + threadIdx.x;
+			const int32_t tri_n2 = (r + 2 < rounds && q2 < total) ? B.in_tri[q2] : -2;
+			cls_cur = tri_n1 == -2 ? (unsigned)kClassNone : tri_n1 == -1 ? (unsigned)kClassMiss : (unsigned)B.tri_class[tri_n1];
+			tri_cur = tri_n1;
+			tri_n1 = tri_n2;
 		}
-		rank = atomicAdd(&s_class_count[cls], 1u);
+		const unsigned par = (unsigned)(r & 1u);
+		// rank among the warp's lanes of the same class, and the warp's count per class
+		const unsigned same = __match_any_sync(kFullMask, cls);
+		const unsigned rank = (unsigned)__popc(same & lt_mask);
+		if (rank == 0u) s_count[par][cls][warp] = (unsigned)__popc(same);
+		if (threadIdx.x < 8u * kWarps) (&s_count[par ^ 1u][0][0])[threadIdx.x] = 0u; // next round's counters
 		__syncthreads();
-		unsigned before = 0u;
-		for (unsigned c = 0; c < cls; ++c) before += s_class_count[c];
-		s_order[before + rank] = (unsigned short)threadIdx.x;
+		{
+			// position = (entries of lower classes) + (entries of my class in lower warps) + rank. Lane c < 8 sums class c's eight
+			// warp counts (two 16-byte loads), an 8-lane exclusive scan turns the totals into class offsets, and every lane
+			// picks its class's number with one shuffle.
+			unsigned total_c = 0u, before_c = 0u;
+			if (lane < 8u) {
+				unsigned v[kWarps];
+				const uint4 a = *reinterpret_cast<const uint4 *>(&s_count[par][lane][0]);
+				v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+				if (kWarps == 8) {
+					const uint4 b4 = *reinterpret_cast<const uint4 *>(&s_count[par][lane][kWarps - 4]);
+					v[kWarps - 4] = b4.x; v[kWarps - 3] = b4.y; v[kWarps - 2] = b4.z; v[kWarps - 1] = b4.w;
+				}
+#pragma unroll
+				for (unsigned w = 0; w < kWarps; ++w) {
+					total_c += v[w];
+					if (w < warp) before_c += v[w];
+				}
+			}
+			unsigned incl = total_c;
+#pragma unroll
+			for (unsigned d = 1; d < 8u; d <<= 1) {
+				const unsigned t0 = __shfl_up_sync(kFullMask, incl, d);
+				if (lane >= d) incl += t0;
+			}
+			const unsigned base_c = incl - total_c + before_c;
+			const unsigned pos = __shfl_sync(kFullMask, base_c, (int)cls) + rank;
+			s_order[pos] = (unsigned short)threadIdx.x;
+			s_tri[pos] = tri_mine;
+		}
 		__syncthreads();
 		const unsigned long long q = q0 + s_order[threadIdx.x];
+		const int32_t tri_idx = s_tri[threadIdx.x];
 		bool keep = false, conn = false;
-		V3 origin = v3(0, 0, 0), dir = v3(0, 0, 0), color = v3(0, 0, 0), ret = v3(0, 0, 0);
-		unsigned id = 0;
-		if (q < total) {
-			const float4 r1 = B.in_rays[2 * q + 1];
+		V3 origin = v3(0, 0, 0), dir = v3(0, 0, 0), color = v3(0, 0, 0);
+		unsigned id = 0, bias_bits = 0;
+		if (tri_idx != -2) {
+			const float4 r1 = B.in_dir[q];
+			const float4 st = B.in_state[q];
 			dir = v3(r1.x, r1.y, r1.z);
 			id = __float_as_uint(r1.w);
-			const unsigned pix = (unsigned)(id % npix), s = (unsigned)(id / npix);
-			const uchar2 bb = B.bias[pix];
-			const float rx = fract(B.sobol[s * dims + 2 * b] + (float)bb.x / 255.0f);
-			const float ry = fract(B.sobol[s * dims + 2 * b + 1] + (float)bb.y / 255.0f);
-			const float xi = A.rr_start >= 0 ? fract(B.sobol[s * dims + 2 * A.max_bounce + b] + (float)bb.x / 255.0f) : 0.0f;
-			const float4 c4 = B.color[id], r4 = B.ret[id];
-			color = v3(c4.x, c4.y, c4.z);
-			ret = v3(r4.x, r4.y, r4.z);
-			const float2 uv = B.in_uv[q];
-			const SegmentResult res = shade_segment(B, A, b, B.in_tri[q], uv.x, uv.y, rx, ry, xi, origin, dir, color, ret);
-			keep = res == kContinues;
-			conn = res == kConnects;
-			if (conn) { // the shadow ray starts where this segment started: the previous hit point
-				const float4 r0 = B.in_rays[2 * q];
-				origin = v3(r0.x, r0.y, r0.z);
+			color = v3(st.x, st.y, st.z);
+			bias_bits = __float_as_uint(st.w);
+			V3 add;
+			if (tri_idx == -1) { // :130-135
+				add = color * v3(A.sun[0], A.sun[1], A.sun[2]);
+				if (B.conn_rays != nullptr) {
+					conn = true; // the shadow ray starts where this segment started: the previous hit point
+					color = add;
+					const float4 r0 = B.in_org[q];
+					origin = v3(r0.x, r0.y, r0.z);
+					add = v3(0.f, 0.f, 0.f);
+				}
+			} else {
+				const float2 uv = B.in_uv[q];
+				Surface sf;
+				fetch_surface(B, tri_idx, uv.x, uv.y, sf);
+				origin = sf.origin;
+				add = color * sf.emissive; // :139
+				if (!last) {
+					const unsigned s = id / npix;
+					const float fbx = (float)(bias_bits & 0xffu) / 255.0f, fby = (float)((bias_bits >> 8) & 0xffu) / 255.0f;
+					const float rx = fract(B.sobol[s * dims + 2 * b] + fbx);
+					const float ry = fract(B.sobol[s * dims + 2 * b + 1] + fby);
+					const float xi = A.rr_start >= 0 ? fract(B.sobol[s * dims + 2 * A.max_bounce + b] + fbx) : 0.0f;
+					keep = scatter(A, b, sf, rx, ry, xi, dir, color);
+				}
 			}
-			B.ret[id] = make_float4(ret.x, ret.y, ret.z, 0.0f);
-			if (keep || conn) B.color[id] = make_float4(color.x, color.y, color.z, 0.0f);
+			if (!adds_nothing(add)) {
+				float4 r4 = B.ret[id];
+				r4.x = r4.x + add.x;
+				r4.y = r4.y + add.y;
+				r4.z = r4.z + add.z;
+				B.ret[id] = r4;
+			}
 		}
 		const unsigned long long slot = queue_append(keep, B.out_count);
 		if (keep) {
-			B.out_rays[2 * slot] = make_float4(origin.x, origin.y, origin.z, tmin);
-			B.out_rays[2 * slot + 1] = make_float4(dir.x, dir.y, dir.z, __uint_as_float(id));
+			B.out_org[slot] = make_float4(origin.x, origin.y, origin.z, tmin);
+			B.out_dir[slot] = make_float4(dir.x, dir.y, dir.z, __uint_as_float(id));
+			B.out_state[slot] = make_float4(color.x, color.y, color.z, __uint_as_float(bias_bits));
 		}
 		if (B.conn_rays != nullptr) {
 			const unsigned long long cs = queue_append(conn, B.conn_count);
 			if (conn) {
 				B.conn_rays[2 * cs] = make_float4(origin.x, origin.y, origin.z, tmin);
 				B.conn_rays[2 * cs + 1] = make_float4(B.sun_dir[0], B.sun_dir[1], B.sun_dir[2], __uint_as_float(id));
+				B.conn_color[cs] = make_float4(color.x, color.y, color.z, 0.0f);
 			}
 		}
 	}
@@ -424,13 +554,13 @@ __global__ void __launch_bounds__(256, 4) k_shade_bounce(ShadeBuffers B, PTArgs 
 
 // connect: ret += colour * sun for every escaped path whose shadow ray reached the sun (occ == 0)
 __global__ void k_connect_apply(const float4 *__restrict__ conn_rays, const uint8_t *__restrict__ occ, const unsigned long long *count,
-                                const float4 *__restrict__ color, float4 *__restrict__ ret)
+                                const float4 *__restrict__ conn_color, float4 *__restrict__ ret)
 {
 	const unsigned long long total = *count;
 	for (unsigned long long q = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; q < total; q += (unsigned long long)gridDim.x * blockDim.x) {
 		if (occ[q]) continue;
 		const unsigned id = __float_as_uint(conn_rays[2 * q + 1].w);
-		const float4 c = color[id];
+		const float4 c = conn_color[q];
 		float4 r = ret[id];
 		r.x = r.x + c.x;
 		r.y = r.y + c.y;
@@ -480,7 +610,18 @@ __global__ void k_resolve_sum(const float4 *__restrict__ sum, float4 *__restrict
 	}
 }
 
-// primaryray.glsl main() :46-94 after the intersection (TEXTURE_COUNT == 0)
+// diffuse colour of primaryray.glsl:59-71 from the 100-byte Triangle record
+__device__ __forceinline__ V3 diffuse_of(const uchar4 *__restrict__ texels, const int4 *__restrict__ tex_table, const Material &m, const float *t, float u, float v)
+{
+	if (texels != nullptr && m.dtex != -1) {
+		const float w = 1.0f - u - v;
+		const float s = t[18] * u + t[20] * v + t[22] * w, tt = t[19] * u + t[21] * v + t[23] * w;
+		return sample_texture(texels, tex_table[m.dtex], s, tt);
+	}
+	return v3(m.dr, m.dg, m.db);
+}
+
+// primaryray.glsl main() :46-94 after the intersection
 __global__ void k_view(const uint8_t *__restrict__ tris, const Material *__restrict__ mats, const uchar4 *__restrict__ texels,
                        const int4 *__restrict__ tex_table, const int32_t *__restrict__ hit_tri, const float2 *__restrict__ hit_uv, int type,
                        unsigned npix, float4 *__restrict__ out)
@@ -543,10 +684,11 @@ struct adypt_tracer {
 	// wavefront
 	int batch_samples = 0;       // S
 	unsigned long long capacity = 0; // paths per batch = S * npix
-	float4 *d_rays[2] = {nullptr, nullptr};
+	float4 *d_rays[2] = {nullptr, nullptr};  // ray queues: [0, capacity) origins + tmin, [capacity, 2 capacity) directions + path id
 	int32_t *d_hit_tri = nullptr;
 	float2 *d_hit_uv = nullptr;
-	float4 *d_color = nullptr, *d_ret = nullptr;
+	float4 *d_state[2] = {nullptr, nullptr}; // per queue entry: throughput + bias bytes
+	float4 *d_ret = nullptr;                 // per path: radiance
 	// device counters, sized from maxBounce: [0, max_bounce] queue lengths, [conn_base + b] connect queues, [seg_slot] segments
 	// statistic, [work_slot] the work counter of this tracer's traversal launches (all on t->stream, so one is enough; scene.h)
 	unsigned long long *d_counts = nullptr;
@@ -557,13 +699,16 @@ struct adypt_tracer {
 	bool sun_visibility = false;
 	float sun_dir[3] = {0.f, 0.f, 0.f};
 	int rr_start = -1; // Russian roulette (opt-in extension): first bounce it applies to, -1 = off
-	float4 *d_conn_rays = nullptr;
+	float4 *d_conn_rays = nullptr, *d_conn_color = nullptr;
 	uint8_t *d_conn_occ = nullptr;
 	unsigned long long conn_capacity = 0;
 	uint64_t launches_at_create = 0;
 	uint64_t host_segments = 0;  // primary segments (known on the host)
 	// measurement hooks (adypt_tracer_set_profiling): CUDA events around every stage launch, and / or the instrumented
 	// traversal kernel that counts the nodes and triangles the wavefront's rays touch. Off by default.
+	int bounce_ctas = 0;   // tuning (ADYPT_BOUNCE_CTAS): 4 = 256-thread blocks, four per SM (default); 8 = 128-thread blocks, eight per SM
+	int primary_ctas = 0;  // tuning (ADYPT_PRIMARY_CTAS): CTAs per SM the bounce-0 kernel is compiled for (2, 3, 4); 0 = default
+	int primary_group = 0; // tuning (ADYPT_PRIMARY_GROUP): samples of one pixel a thread of the bounce-0 stage shades; 0 = default
 	int profiling = 0;
 	std::vector<cudaEvent_t> ev_pool;
 	size_t ev_used = 0;
@@ -629,7 +774,7 @@ void free_tracer(adypt_tracer *t)
 	cudaFree(t->d_trace_stats);
 	cudaFree(t->d_result); cudaFree(t->d_sum); cudaFree(t->d_prim_tri); cudaFree(t->d_prim_uv); cudaFree(t->d_bias);
 	cudaFree(t->d_dirs); cudaFree(t->d_sobol); cudaFree(t->d_rays[0]); cudaFree(t->d_rays[1]); cudaFree(t->d_hit_tri);
-	cudaFree(t->d_hit_uv); cudaFree(t->d_color); cudaFree(t->d_ret); cudaFree(t->d_counts); cudaFree(t->d_conn_rays); cudaFree(t->d_conn_occ);
+	cudaFree(t->d_hit_uv); cudaFree(t->d_state[0]); cudaFree(t->d_state[1]); cudaFree(t->d_ret); cudaFree(t->d_counts); cudaFree(t->d_conn_rays); cudaFree(t->d_conn_color); cudaFree(t->d_conn_occ);
 	if (t->stream) cudaStreamDestroy(t->stream);
 	delete t;
 }
@@ -698,14 +843,15 @@ int alloc_wavefront(adypt_tracer *t)
 		t->sobol_cap = sobol_need;
 	}
 	if (cap == t->capacity && S == t->batch_samples) return ADYPT_OK;
-	cudaFree(t->d_rays[0]); cudaFree(t->d_rays[1]); cudaFree(t->d_hit_tri); cudaFree(t->d_hit_uv); cudaFree(t->d_color); cudaFree(t->d_ret);
-	t->d_rays[0] = t->d_rays[1] = nullptr; t->d_hit_tri = nullptr; t->d_hit_uv = nullptr; t->d_color = t->d_ret = nullptr;
+	cudaFree(t->d_rays[0]); cudaFree(t->d_rays[1]); cudaFree(t->d_hit_tri); cudaFree(t->d_hit_uv); cudaFree(t->d_state[0]); cudaFree(t->d_state[1]); cudaFree(t->d_ret);
+	t->d_rays[0] = t->d_rays[1] = nullptr; t->d_hit_tri = nullptr; t->d_hit_uv = nullptr; t->d_state[0] = t->d_state[1] = nullptr; t->d_ret = nullptr;
 	t->capacity = 0;
 	ADYPT_CUDA(cudaMalloc((void **)&t->d_rays[0], cap * 32u));
 	ADYPT_CUDA(cudaMalloc((void **)&t->d_rays[1], cap * 32u));
 	ADYPT_CUDA(cudaMalloc((void **)&t->d_hit_tri, cap * 4u));
 	ADYPT_CUDA(cudaMalloc((void **)&t->d_hit_uv, cap * 8u));
-	ADYPT_CUDA(cudaMalloc((void **)&t->d_color, cap * 16u));
+	ADYPT_CUDA(cudaMalloc((void **)&t->d_state[0], cap * 16u));
+	ADYPT_CUDA(cudaMalloc((void **)&t->d_state[1], cap * 16u));
 	ADYPT_CUDA(cudaMalloc((void **)&t->d_ret, cap * 16u));
 	t->capacity = cap;
 	t->batch_samples = S;
@@ -760,23 +906,25 @@ int run_batch(adypt_tracer *t, int first, int n, bool sum_mode)
 	ts.end();
 	unsigned long long *trace_stats = (t->profiling & 2) ? t->d_trace_stats : nullptr;
 	ShadeBuffers B;
-	B.tris = s->d_tris; B.mats = s->d_mats; B.texels = s->d_texels; B.tex_table = s->d_tex_table; B.bias = t->d_bias; B.sobol = t->d_sobol;
+	B.shade = s->d_shade; B.tri_class = s->d_tri_class; B.mats = s->d_mats; B.texels = s->d_texels; B.tex_table = s->d_tex_table; B.bias = t->d_bias; B.sobol = t->d_sobol;
 	B.prim_tri = t->d_prim_tri; B.prim_uv = t->d_prim_uv;
-	B.in_rays = nullptr; B.in_tri = t->d_hit_tri; B.in_uv = t->d_hit_uv; B.in_count = nullptr;
-	B.out_rays = t->d_rays[1]; B.out_count = t->d_counts + 1;
-	B.color = t->d_color; B.ret = t->d_ret; B.segments = t->d_counts + t->seg_slot;
+	B.in_org = B.in_dir = nullptr; B.in_tri = t->d_hit_tri; B.in_uv = t->d_hit_uv; B.in_state = nullptr; B.in_count = nullptr;
+	B.out_org = t->d_rays[1]; B.out_dir = t->d_rays[1] + t->capacity; B.out_state = t->d_state[1]; B.out_count = t->d_counts + 1;
+	B.ret = t->d_ret; B.segments = t->d_counts + t->seg_slot;
 	const unsigned long long total = (unsigned long long)n * t->npix;
-	B.conn_rays = nullptr; B.conn_count = nullptr;
+	B.conn_rays = nullptr; B.conn_color = nullptr; B.conn_count = nullptr;
 	B.sun_dir[0] = t->sun_dir[0]; B.sun_dir[1] = t->sun_dir[1]; B.sun_dir[2] = t->sun_dir[2];
 	if (t->sun_visibility) {
 		if (t->conn_capacity < total) {
-			cudaFree(t->d_conn_rays); cudaFree(t->d_conn_occ);
-			t->d_conn_rays = nullptr; t->d_conn_occ = nullptr; t->conn_capacity = 0;
+			cudaFree(t->d_conn_rays); cudaFree(t->d_conn_color); cudaFree(t->d_conn_occ);
+			t->d_conn_rays = t->d_conn_color = nullptr; t->d_conn_occ = nullptr; t->conn_capacity = 0;
 			ADYPT_CUDA(cudaMalloc((void **)&t->d_conn_rays, total * 32u));
+			ADYPT_CUDA(cudaMalloc((void **)&t->d_conn_color, total * 16u));
 			ADYPT_CUDA(cudaMalloc((void **)&t->d_conn_occ, total));
 			t->conn_capacity = total;
 		}
 		B.conn_rays = t->d_conn_rays;
+		B.conn_color = t->d_conn_color;
 		B.conn_count = t->d_counts + t->conn_base;
 	}
 	// connect stage of bounce b: any-hit over the shadow rays queued by the shade kernel, then add the sun term
@@ -784,7 +932,7 @@ int run_batch(adypt_tracer *t, int first, int n, bool sum_mode)
 		if (!t->sun_visibility) return ADYPT_OK;
 		StageTimer tc(t, ADYPT_STAGE_CONNECT);
 		ADYPT_TRY(launch_trace(s, t->d_conn_rays, total, nullptr, nullptr, nullptr, t->d_conn_occ, t->stream, t->d_counts + t->conn_base + b, t->d_counts + t->work_slot));
-		k_connect_apply<<<grid_for(total, 256, s->sm_count), 256, 0, t->stream>>>(t->d_conn_rays, t->d_conn_occ, t->d_counts + t->conn_base + b, t->d_color, t->d_ret);
+		k_connect_apply<<<grid_for(total, 256, s->sm_count), 256, 0, t->stream>>>(t->d_conn_rays, t->d_conn_occ, t->d_counts + t->conn_base + b, t->d_conn_color, t->d_ret);
 		count_launch();
 		ADYPT_CUDA(cudaGetLastError());
 		tc.end();
@@ -792,7 +940,14 @@ int run_batch(adypt_tracer *t, int first, int n, bool sum_mode)
 	};
 	{
 		StageTimer tp(t, ADYPT_STAGE_SHADE_PRIMARY);
-		k_shade_primary<<<grid_for(total, 256, s->sm_count), 256, 0, t->stream>>>(B, A, t->cam);
+		const int group = t->primary_group > 0 ? t->primary_group : 4; // samples of a pixel per thread
+		const unsigned long long items = (unsigned long long)t->npix * (unsigned long long)((n + group - 1) / group);
+		const int g = grid_for(items, 256, s->sm_count);
+		switch (t->primary_ctas) { // registers per thread: 64 / 80 / 116 (tuning; same results)
+		case 4: k_shade_primary<4><<<g, 256, 0, t->stream>>>(B, A, t->cam, group); break;
+		case 2: k_shade_primary<2><<<g, 256, 0, t->stream>>>(B, A, t->cam, group); break;
+		default: k_shade_primary<3><<<g, 256, 0, t->stream>>>(B, A, t->cam, group); break;
+		}
 		count_launch();
 		ADYPT_CUDA(cudaGetLastError());
 		tp.end();
@@ -802,15 +957,21 @@ int run_batch(adypt_tracer *t, int first, int n, bool sum_mode)
 	for (int b = 1; b < c.max_bounce; ++b) {
 		// extend: queue length is read on the device
 		StageTimer te(t, ADYPT_STAGE_TRACE_BOUNCE);
-		ADYPT_TRY(launch_trace(s, t->d_rays[cur], total, t->d_hit_tri, nullptr, t->d_hit_uv, nullptr, t->stream, t->d_counts + b, t->d_counts + t->work_slot, trace_stats));
+		ADYPT_TRY(launch_trace(s, t->d_rays[cur], total, t->d_hit_tri, nullptr, t->d_hit_uv, nullptr, t->stream, t->d_counts + b, t->d_counts + t->work_slot, trace_stats,
+		                       t->d_rays[cur] + t->capacity));
 		te.end();
-		B.in_rays = t->d_rays[cur];
+		B.in_org = t->d_rays[cur];
+		B.in_dir = t->d_rays[cur] + t->capacity;
+		B.in_state = t->d_state[cur];
 		B.in_count = t->d_counts + b;
-		B.out_rays = t->d_rays[cur ^ 1];
+		B.out_org = t->d_rays[cur ^ 1];
+		B.out_dir = t->d_rays[cur ^ 1] + t->capacity;
+		B.out_state = t->d_state[cur ^ 1];
 		B.out_count = t->d_counts + b + 1;
 		if (t->sun_visibility) B.conn_count = t->d_counts + t->conn_base + b;
 		StageTimer tb(t, ADYPT_STAGE_SHADE_BOUNCE);
-		k_shade_bounce<<<grid_for(total, 256, s->sm_count), 256, 0, t->stream>>>(B, A, b, c.ray_tmin);
+		if (t->bounce_ctas == 8) k_shade_bounce<8, 128><<<2 * grid_for(total, 256, s->sm_count), 128, 0, t->stream>>>(B, A, b, c.ray_tmin); // regroups 128 entries
+		else k_shade_bounce<4, 256><<<grid_for(total, 256, s->sm_count), 256, 0, t->stream>>>(B, A, b, c.ray_tmin);
 		count_launch();
 		ADYPT_CUDA(cudaGetLastError());
 		tb.end();
@@ -854,7 +1015,7 @@ int adypt_tracer_create(adypt_scene *scene, const adypt_pt_config *config, int32
 	if (!scene || !config || !out) return fail(ADYPT_EINVAL, "scene/config/out is NULL");
 	*out = nullptr;
 	if (width <= 0 || height <= 0 || (uint64_t)width * (uint64_t)height >= (1ull << 31)) return fail(ADYPT_EINVAL, "bad image size");
-	if (!scene->d_tris || !scene->d_mats) return fail(ADYPT_EINVAL, "scene has no triangles/materials: traversal-only scenes cannot shade");
+	if (!scene->d_tris || !scene->d_mats || !scene->d_shade) return fail(ADYPT_EINVAL, "scene has no triangles/materials: traversal-only scenes cannot shade");
 	if (scene->bad_matid_tri >= 0)
 		return fail(ADYPT_EINVAL, "triangle " + std::to_string(scene->bad_matid_tri) + " has a material id outside [0, n_materials) (an OBJ face without a usemtl, or an unknown material): the scene can be traversed but not shaded");
 	ADYPT_TRY(check_config(config, false));
@@ -900,6 +1061,9 @@ int adypt_tracer_create(adypt_scene *scene, const adypt_pt_config *config, int32
 	const float ident[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
 	memcpy(t->cam.inv_proj, ident, 64);
 	memcpy(t->cam.inv_view, ident, 64);
+	if (const char *e = getenv("ADYPT_PRIMARY_GROUP")) t->primary_group = atoi(e);
+	if (const char *e = getenv("ADYPT_PRIMARY_CTAS")) t->primary_ctas = atoi(e);
+	if (const char *e = getenv("ADYPT_BOUNCE_CTAS")) t->bounce_ctas = atoi(e);
 	t->launches_at_create = g_launches.load();
 	*out = t;
 	return ADYPT_OK;

@@ -25,7 +25,9 @@ struct TraceParams {
 	const uint4 *__restrict__ nodes;        // 5 per node
 	const float4 *__restrict__ woop;        // 3 per leaf reference
 	const int32_t *__restrict__ tri_indices;
-	const float4 *__restrict__ rays;        // 2 per ray
+	const float4 *__restrict__ rays;        // origin + tmin of ray r at rays[r * ray_stride]
+	const float4 *__restrict__ dirs;        // direction (+ pad) of ray r at dirs[r * ray_stride]; batch ABI (32-byte rays): dirs = rays + 1, stride 2;
+	uint32_t ray_stride;                    // the wavefront's queues keep origins and directions in two arrays: stride 1
 	unsigned long long n;
 	const unsigned long long *n_ptr;        // when non-null the ray count is read from device memory (wavefront queues)
 	int32_t *__restrict__ out_tri;          // closest
@@ -232,7 +234,7 @@ __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const Trac
 					if (lane < stage_cnt) {
 						// ray setup, traversal.glsl:16-35
 						const unsigned long long r = stage_base + lane;
-						const float4 r0 = __ldg(p.rays + 2 * r), r1 = __ldg(p.rays + 2 * r + 1);
+						const float4 r0 = __ldg(p.rays + r * p.ray_stride), r1 = __ldg(p.dirs + r * p.ray_stride);
 						const float ooeps = 5.42101086242752217e-20f; // exp2(-64)
 						float sx = fabsf(r1.x) > ooeps ? r1.x : (r1.x >= 0.0f ? ooeps : -ooeps);
 						float sy = fabsf(r1.y) > ooeps ? r1.y : (r1.y >= 0.0f ? ooeps : -ooeps);
@@ -282,7 +284,7 @@ __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const Trac
 			if (take) {
 				// ray setup, traversal.glsl:16-35
 				ray_idx = cand;
-				const float4 r0 = __ldg(p.rays + 2 * cand), r1 = __ldg(p.rays + 2 * cand + 1);
+				const float4 r0 = __ldg(p.rays + cand * p.ray_stride), r1 = __ldg(p.dirs + cand * p.ray_stride);
 				ox = r0.x; oy = r0.y; oz = r0.z; tmin = r0.w;
 				const float ooeps = 5.42101086242752217e-20f; // exp2(-64)
 				dx = fabsf(r1.x) > ooeps ? r1.x : (r1.x >= 0.0f ? ooeps : -ooeps);

@@ -338,7 +338,7 @@ def run_native(args, rank, world, local_rank):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # the collectives of this run (barriers + the C5 all-reduce) are listed on stderr by NCCL itself
         os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "COLL")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "COLL,TUNING")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         ctx.dist = dist
     torch.cuda.set_device(local_rank)
@@ -388,10 +388,36 @@ def run_native(args, rank, world, local_rank):
     e2e_s = max_over_ranks(ctx, (time.perf_counter() - t0) / steps)
     clocks = sampler.stop()
     assert torch.equal(h_tri.to(dev), d_tri), "host-path results differ from device-path results"
+    # what the host interface of this box allows for the same bytes with all ranks copying at once, no kernels: the 256 MB up and
+    # 128 MB down of one step on two streams (tools/pcie_probe_multi.py measures the same outside the bench)
+    up_s, down_s = torch.cuda.Stream(), torch.cuda.Stream()
+    d_in = torch.empty(n * 8, dtype=torch.float32, device=dev)
+    d_out = torch.empty(n * 4, dtype=torch.float32, device=dev)
+    h_out = torch.empty(n * 4, dtype=torch.float32).pin_memory()
+
+    def copies():
+        with torch.cuda.stream(up_s):
+            d_in.copy_(h_rays.view(-1), non_blocking=True)
+        with torch.cuda.stream(down_s):
+            h_out.copy_(d_out, non_blocking=True)
+
+    for _ in range(2):
+        copies()
+    barrier(ctx)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        copies()
+    torch.cuda.synchronize()
+    copy_s = max_over_ranks(ctx, (time.perf_counter() - t0) / steps)
+    barrier(ctx)
+    del d_in, d_out, h_out
     chunk = int(os.environ.get("ADYPT_HOST_CHUNK", "0")) or (1 << 19)
     e2e = {"value": world * n / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(n * 32), "d2h_bytes_per_step": int(n * 16),
            "how": f"adypt_trace_closest(ADYPT_MEM_HOST) on pinned host arrays ({chunk}-ray chunks pipelined over 3 streams: H2D, traversal, D2H overlap), "
-                  "wall clock around K blocking calls, max over ranks"}
+                  "wall clock around K blocking calls, max over ranks",
+           "copy_only": {"value": world * n / copy_s / 1e6, "unit": UNIT, "GBps_aggregate": world * n * 48 / copy_s / 1e9,
+                         "how": "the same 256 MB up + 128 MB down per rank and step as plain pinned cudaMemcpyAsync on two streams, all ranks at once, no kernels: "
+                                "what this box's host interface allows for the call's bytes"}}
 
     # ---- roofline of the dominant (only) kernel in the step
     st = scene.trace_stats(d_rays)
@@ -607,9 +633,8 @@ def leg_c5(ctx):
     tr.accumulate(0, L)  # warm-up: allocations, clocks
     tr.sync()
     if ctx.world > 1:
-        warm = torch.zeros_like(acc)  # one warm-up collective of the same size: NCCL sets up its channels and buffers
-        dist.all_reduce(warm, op=dist.ReduceOp.SUM)
-        del warm
+        dist.all_reduce(acc, op=dist.ReduceOp.SUM)  # one warm-up collective on the same buffer (NCCL sets up its channels; the render clears it)
+        torch.cuda.synchronize()
     barrier(ctx)
     l0 = tr.stats()["launches"]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -20,6 +20,10 @@ def main():
     for _ in range(int(os.environ.get('REPS', '4'))):
         t.trace(False, 0)
         t0 = time.perf_counter(); t.sample(64); t.sync(); ts.append(time.perf_counter() - t0)
+    t.set_profiling(stage_times=True); t.profile()
+    t.trace(False, 0); t.sample(64); t.sync()
+    pr = t.profile(); t.set_profiling()
+    print('   stage ms per 64 spp:', {k: round(v, 3) for k, v in pr['stage_ms'].items() if v > 0})
     img = t.read(3)
     print(f"{os.environ.get('TUNE_LIB', 'in-tree')}: C3 64 spp min {min(ts)*1e3:.1f} ms  med {np.median(ts)*1e3:.1f} ms  {1920*1080*64/min(ts)/1e9:.3f} Gsamples/s  mean {float(img.mean()):.9f}")
 
