@@ -131,6 +131,7 @@ TraceKernel trace_kernel_for(bool any, bool stats, int variant)
 	case 2: return trace_kernel<true, false, 2, 8, 2>;
 	case 5: return trace_kernel<true, false, 4, 8, 2>;
 	case 8: return trace_kernel<true, false, 4, 8, 12, false>;
+	case 9: return trace_kernel<true, false, 4, 8, 12, true, true>;
 	default: return trace_kernel<true>;
 	}
 	switch (variant) {
@@ -142,6 +143,9 @@ TraceKernel trace_kernel_for(bool any, bool stats, int variant)
 	case 6: return trace_kernel<false, false, 5, 8, 12>;
 	case 7: return trace_kernel<false, false, 4, 8, 1>;
 	case 8: return trace_kernel<false, false, 4, 8, 12, false>; // ray set-up at refill time
+	case 9: return trace_kernel<false, false, 4, 8, 12, true, true>; // hit-mask contributions from a shared-memory table
+	case 10: return trace_kernel<false, false, 3, 8, 12, true, true>;
+	case 11: return trace_kernel<false, false, 5, 8, 12, true, true>;
 	default: return trace_kernel<false>;
 	}
 }
@@ -435,7 +439,7 @@ int adypt_trace_configure(adypt_scene *s, int ctas_per_sm, int refill_threshold,
 {
 	return guarded([&]() -> int {
 	if (!s) return fail(ADYPT_EINVAL, "scene is NULL");
-	if (ctas_per_sm < 0 || refill_threshold < 0 || refill_threshold > 32 || variant < 0 || variant > 8) return fail(ADYPT_EINVAL, "bad tuning value");
+	if (ctas_per_sm < 0 || refill_threshold < 0 || refill_threshold > 32 || variant < 0 || variant > 15) return fail(ADYPT_EINVAL, "bad tuning value");
 	s->ctas_per_sm = ctas_per_sm;
 	s->refill_threshold = refill_threshold;
 	s->variant = variant;

@@ -706,7 +706,7 @@ struct adypt_tracer {
 	uint64_t host_segments = 0;  // primary segments (known on the host)
 	// measurement hooks (adypt_tracer_set_profiling): CUDA events around every stage launch, and / or the instrumented
 	// traversal kernel that counts the nodes and triangles the wavefront's rays touch. Off by default.
-	int bounce_ctas = 0;   // tuning (ADYPT_BOUNCE_CTAS): 4 = 256-thread blocks, four per SM (default); 8 = 128-thread blocks, eight per SM
+	int bounce_ctas = 0;   // tuning (ADYPT_BOUNCE_CTAS): 4 = 256-thread blocks, four per SM; otherwise 128-thread blocks, eight per SM (default)
 	int primary_ctas = 0;  // tuning (ADYPT_PRIMARY_CTAS): CTAs per SM the bounce-0 kernel is compiled for (2, 3, 4); 0 = default
 	int primary_group = 0; // tuning (ADYPT_PRIMARY_GROUP): samples of one pixel a thread of the bounce-0 stage shades; 0 = default
 	int profiling = 0;
@@ -940,7 +940,7 @@ int run_batch(adypt_tracer *t, int first, int n, bool sum_mode)
 	};
 	{
 		StageTimer tp(t, ADYPT_STAGE_SHADE_PRIMARY);
-		const int group = t->primary_group > 0 ? t->primary_group : 4; // samples of a pixel per thread
+		const int group = t->primary_group > 0 ? t->primary_group : 16; // samples of a pixel per thread (1 .. 16 measured: profiles/r2d_primary_sweep.log)
 		const unsigned long long items = (unsigned long long)t->npix * (unsigned long long)((n + group - 1) / group);
 		const int g = grid_for(items, 256, s->sm_count);
 		switch (t->primary_ctas) { // registers per thread: 64 / 80 / 116 (tuning; same results)
@@ -970,8 +970,10 @@ int run_batch(adypt_tracer *t, int first, int n, bool sum_mode)
 		B.out_count = t->d_counts + b + 1;
 		if (t->sun_visibility) B.conn_count = t->d_counts + t->conn_base + b;
 		StageTimer tb(t, ADYPT_STAGE_SHADE_BOUNCE);
-		if (t->bounce_ctas == 8) k_shade_bounce<8, 128><<<2 * grid_for(total, 256, s->sm_count), 128, 0, t->stream>>>(B, A, b, c.ray_tmin); // regroups 128 entries
-		else k_shade_bounce<4, 256><<<grid_for(total, 256, s->sm_count), 256, 0, t->stream>>>(B, A, b, c.ray_tmin);
+		// 128-thread blocks, eight per SM: smaller groups wait less on each other at the two barriers of a round (13.70 vs 14.17 ms per
+		// 64 spp of C3, profiles/r2g_bounce_block_sweep.log)
+		if (t->bounce_ctas == 4) k_shade_bounce<4, 256><<<grid_for(total, 256, s->sm_count), 256, 0, t->stream>>>(B, A, b, c.ray_tmin);
+		else k_shade_bounce<8, 128><<<2 * grid_for(total, 256, s->sm_count), 128, 0, t->stream>>>(B, A, b, c.ray_tmin);
 		count_launch();
 		ADYPT_CUDA(cudaGetLastError());
 		tb.end();

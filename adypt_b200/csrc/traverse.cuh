@@ -104,10 +104,10 @@ __device__ __forceinline__ float byte_to_float(uint32_t word, uint32_t magic)
 }
 
 // one group of four children (one 32-bit lane of each quantised plane), traversal.glsl:86-143 / :145-202
-template <int K, int CVT_PLANES>
+template <int K, int CVT_PLANES, bool HM_LUT>
 __device__ __forceinline__ uint32_t test_child(uint32_t meta_oct4, uint32_t s_lox, uint32_t s_loy, uint32_t s_loz,
                                                uint32_t s_hix, uint32_t s_hiy, uint32_t s_hiz, float aix, float aiy, float aiz,
-                                               float aox, float aoy, float aoz, float tmin, float hit_t, uint32_t magic)
+                                               float aox, float aoy, float aoz, float tmin, float hit_t, uint32_t magic, const uint32_t *lut)
 {
 	const float txmin = __fmaf_rn(byte_to_float<K, (CVT_PLANES > 0)>(s_lox, magic), aix, aox);
 	const float tymin = __fmaf_rn(byte_to_float<K, (CVT_PLANES > 2)>(s_loy, magic), aiy, aoy);
@@ -121,20 +121,25 @@ __device__ __forceinline__ uint32_t test_child(uint32_t meta_oct4, uint32_t s_lo
 		// the child's meta byte (count bits 7..5, bit index 4..0, already XOR-ed with the octant for inner children),
 		// zero-extended by one PRMT; the funnel shift takes its amount modulo 32, so the index needs no mask
 		const uint32_t b = __byte_perm(meta_oct4, 0u, 0x4440u | K);
+		if (HM_LUT) {
+			// the same value from a 256-entry table in shared memory: one LDS (and an address IMAD on the fma pipe) instead of
+			// two shifts on the alu pipe, which is the busiest pipe of the node step
+			return lut[b];
+		}
 		return __funnelshift_l(0u, b >> 5, b);
 	}
 	return 0u;
 }
 
-template <int CVT_PLANES>
+template <int CVT_PLANES, bool HM_LUT>
 __device__ __forceinline__ uint32_t test_children4(uint32_t meta4, uint32_t octinv4, uint32_t s_lox, uint32_t s_loy,
                                                    uint32_t s_loz, uint32_t s_hix, uint32_t s_hiy, uint32_t s_hiz,
                                                    float aix, float aiy, float aiz, float aox, float aoy, float aoz,
-                                                   float tmin, float hit_t, uint32_t magic)
+                                                   float tmin, float hit_t, uint32_t magic, const uint32_t *lut)
 {
 	const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
 	const uint32_t meta_oct4 = meta4 ^ (octinv4 & ((is_inner4 >> 4) * 0xffu)); // octinv only touches index bits 2..0 of inner children
-#define ADYPT_CHILD(K) test_child<K, CVT_PLANES>(meta_oct4, s_lox, s_loy, s_loz, s_hix, s_hiy, s_hiz, aix, aiy, aiz, aox, aoy, aoz, tmin, hit_t, magic)
+#define ADYPT_CHILD(K) test_child<K, CVT_PLANES, HM_LUT>(meta_oct4, s_lox, s_loy, s_loz, s_hix, s_hiy, s_hiz, aix, aiy, aiz, aox, aoy, aoz, tmin, hit_t, magic, lut)
 	return ADYPT_CHILD(0) | ADYPT_CHILD(1) | ADYPT_CHILD(2) | ADYPT_CHILD(3);
 #undef ADYPT_CHILD
 }
@@ -149,7 +154,7 @@ __device__ __forceinline__ uint32_t test_children4(uint32_t meta4, uint32_t octi
 // whole warp for the next 32 rays of its pool at once and parked in shared memory (48 B per ray); an idle lane then picks
 // its ray up with three LDS.128. Unstaged, the same code runs at every refill for the ~6 lanes that happen to be idle, and
 // the warp waits on the (cold, HBM) ray loads five times as often. Same arithmetic per ray, so same results.
-template <bool ANY, bool STATS = false, int CVT_PLANES = 4, int MIN_CTAS = 8, int TRI_BATCH = 12, bool STAGED = true>
+template <bool ANY, bool STATS = false, int CVT_PLANES = 4, int MIN_CTAS = 8, int TRI_BATCH = 12, bool STAGED = true, bool HM_LUT = false>
 __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const TraceParams p)
 {
 	const uint32_t magic = p.magic;
@@ -162,6 +167,11 @@ __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const Trac
 	static_assert(kWarpRegion % 256u == 0u, "lane bits are taken from the low byte of the address");
 	__shared__ __align__(256) unsigned char s_mem[(kTraceBlock / 32) * kWarpRegion];
 	uint2 l_stack[kLocalStack];
+	__shared__ uint32_t s_hm_lut[HM_LUT ? 256 : 1]; // meta byte -> (count bits) << (bit index), see test_child
+	if (HM_LUT) {
+		for (unsigned i = threadIdx.x; i < 256u; i += kTraceBlock) s_hm_lut[i] = (i >> 5) << (i & 31u);
+		__syncthreads();
+	}
 
 	uint32_t lane_addr = (uint32_t)__cvta_generic_to_shared(s_mem) + (threadIdx.x >> 5) * kWarpRegion + (threadIdx.x & 31u) * 8u;
 	asm volatile("mov.u32 %0, %0;" : "+r"(lane_addr)); // opaque, so that it is held in a register (-3.6 % time)
@@ -350,14 +360,14 @@ __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const Trac
 					const bool nx = idx < 0.0f, ny = idy < 0.0f, nz = idz < 0.0f;
 					// planes: n2 = (lox.lo, lox.hi, loy.lo, loy.hi) n3 = (loz.lo, loz.hi, hix.lo, hix.hi)
 					//         n4 = (hiy.lo, hiy.hi, hiz.lo, hiz.hi)
-					uint32_t hitmask = test_children4<CVT_PLANES>(n1.z, octinv4,
+					uint32_t hitmask = test_children4<CVT_PLANES, HM_LUT>(n1.z, octinv4,
 						nx ? n3.z : n2.x, ny ? n4.x : n2.z, nz ? n4.z : n3.x,
 						nx ? n2.x : n3.z, ny ? n2.z : n4.x, nz ? n3.x : n4.z,
-						aix, aiy, aiz, aox, aoy, aoz, tmin, hit_t, magic);
-					hitmask |= test_children4<CVT_PLANES>(n1.w, octinv4,
+						aix, aiy, aiz, aox, aoy, aoz, tmin, hit_t, magic, s_hm_lut);
+					hitmask |= test_children4<CVT_PLANES, HM_LUT>(n1.w, octinv4,
 						nx ? n3.w : n2.y, ny ? n4.y : n2.w, nz ? n4.w : n3.y,
 						nx ? n2.y : n3.w, ny ? n2.w : n4.y, nz ? n3.y : n4.w,
-						aix, aiy, aiz, aox, aoy, aoz, tmin, hit_t, magic);
+						aix, aiy, aiz, aox, aoy, aoz, tmin, hit_t, magic, s_hm_lut);
 					ng.y = (hitmask & 0xff000000u) | (n0.w >> 24);
 					tg.y = hitmask & 0x00ffffffu;
 				}
