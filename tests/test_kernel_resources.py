@@ -23,7 +23,7 @@ def test_traversal_kernels_fit_eight_ctas_per_sm():
     out = subprocess.run([_cuobjdump(), "-res-usage", adypt_b200.LIB_PATH], capture_output=True, text=True, check=True).stdout
     usage = dict(re.findall(r"Function (\S+):\s*\n\s*(REG:.*)", out))
     # the product kernels: closest-hit and any-hit with the default tuning (CVT planes 4, 8 CTAs/SM, triangle batch 12, staged)
-    names = [n for n in usage if re.match(r"_ZN5adypt12trace_kernelILb[01]ELb0ELi4ELi8ELi12ELb1EEE", n)]
+    names = [n for n in usage if re.match(r"_ZN5adypt12trace_kernelILb[01]ELb0ELi4ELi8ELi12ELb1ELb0EEE", n)]
     assert len(names) == 2, sorted(usage)
     for n in names:
         f = {k: int(v) for k, v in re.findall(r"([A-Z]+):(\d+)", usage[n])}
@@ -31,6 +31,8 @@ def test_traversal_kernels_fit_eight_ctas_per_sm():
         assert f["SHARED"] <= 14336 + 1024, (n, f)    # 4 warps x 3.5 KB (+ 1 KB the system reserves per CTA)
         assert f["STACK"] == 56 * 8, (n, f)           # the local stack overflow and nothing else: no spills
     for n, u in usage.items():
-        if "k_shade" in n:
-            f = {k: int(v) for k, v in re.findall(r"([A-Z]+):(\d+)", u)}
-            assert f["REG"] <= 64 and f["STACK"] == 0, (n, f)  # 256 threads x 4 CTAs per SM
+        f = {k: int(v) for k, v in re.findall(r"([A-Z]+):(\d+)", u)}
+        if "k_shade_bounce" in n:  # 128 threads x 8 CTAs (or 256 x 4) per SM; a handful of spilled values at most
+            assert f["REG"] <= 64 and f["STACK"] <= 64, (n, f)
+        if "k_shade_primaryILi3E" in n:  # the default bounce-0 build: 256 threads x 3 CTAs per SM
+            assert f["REG"] <= 80 and f["STACK"] <= 64, (n, f)
