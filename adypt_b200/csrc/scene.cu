@@ -1,6 +1,7 @@
 // Scene upload, GPU Woop construction and the batch traversal entry points of the C-ABI.
 #include "scene.h"
 #include "traverse.cuh"
+#include "traverse_pool.cuh"
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -192,6 +193,18 @@ int launch_trace(adypt_scene *s, const float4 *d_rays, uint64_t n, int32_t *d_tr
 	}
 	ADYPT_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned long long), stream));
 	p.stats = d_stats;
+	if (s->variant == 12 && d_stats == nullptr) {
+		// EXPERIMENT (traverse_pool.cuh): rays held in shared memory and bound to lanes one round at a time
+		const unsigned pool_grid = (unsigned)s->sm_count * 3u;
+		const unsigned long long warps = (unsigned long long)pool_grid * (kPoolBlock / 32);
+		unsigned long long chunk = n / (warps * 6ull);
+		chunk = (chunk / 32ull) * 32ull;
+		p.pool_chunk = (uint32_t)(chunk < 32ull ? 32ull : chunk > kPoolChunk ? kPoolChunk : chunk);
+		p.guided_shift = 0;
+		while ((1ull << p.guided_shift) < warps * 4ull) ++p.guided_shift;
+		if (any) trace_pool_kernel<true><<<pool_grid, kPoolBlock, sizeof(PoolShared), stream>>>(p);
+		else trace_pool_kernel<false><<<pool_grid, kPoolBlock, sizeof(PoolShared), stream>>>(p);
+	} else
 	trace_kernel_for(any, d_stats != nullptr, s->variant)<<<grid, kTraceBlock, 0, stream>>>(p);
 	count_launch();
 	ADYPT_CUDA(cudaGetLastError());
@@ -359,6 +372,8 @@ int adypt_scene_create(const adypt_scene_desc *d, adypt_scene **out)
 		if (e != cudaSuccess) { free_scene(s); return fail(ADYPT_ECUDA, std::string("build_shade_records: ") + cudaGetErrorString(e)); }
 	}
 	if (cudaMalloc((void **)&s->d_counters, kCounterSlots * sizeof(unsigned long long)) != cudaSuccess) { free_scene(s); return fail(ADYPT_ENOMEM, "cudaMalloc counters"); }
+	cudaFuncSetAttribute(trace_pool_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PoolShared));
+	cudaFuncSetAttribute(trace_pool_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PoolShared));
 	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->occ_closest, trace_kernel<false>, kTraceBlock, 0);
 	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->occ_any, trace_kernel<true>, kTraceBlock, 0);
 	*out = s;
