@@ -409,7 +409,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) k_shade_primary(ShadeBuffers B,
 enum { kClassMiss = 0, kClassDiffuse = 1, kClassGlossy = 2, kClassMirror = 3, kClassGlass = 4, kClassOther = 5, kClassNone = 7 };
 
 // bounce b >= 1 over the current queue
-template <int MIN_CTAS, int BLOCK>
+template <int MIN_CTAS, int BLOCK, bool REGROUP = true>
 __global__ void __launch_bounds__(BLOCK, MIN_CTAS) k_shade_bounce(ShadeBuffers B, PTArgs A, int b, float tmin)
 {
 	const unsigned npix = (unsigned)A.width * (unsigned)A.height;
@@ -435,6 +435,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_CTAS) k_shade_bounce(ShadeBuffers B
 	// two rounds of look-ahead: the hit index of round r+2 and the class byte of round r+1 are in flight while round r is shaded
 	int32_t tri_cur = -2, tri_n1 = -2;       // -2 = past the end of the queue
 	unsigned cls_cur = (unsigned)kClassNone;
+	if (REGROUP) {
 	if (rounds > 0) {
 		if (q0 + threadIdx.x < total) tri_cur = B.in_tri[q0 + threadIdx.x];
 		if (rounds > 1 && q0 + stride + threadIdx.x < total) tri_n1 = B.in_tri[q0 + stride + threadIdx.x];
@@ -442,7 +443,11 @@ __global__ void __launch_bounds__(BLOCK, MIN_CTAS) k_shade_bounce(ShadeBuffers B
 	}
 	if (threadIdx.x < 16u * kWarps) (&s_count[0][0][0])[threadIdx.x] = 0u;
 	__syncthreads();
+	}
 	for (unsigned long long r = 0; r < rounds; ++r, q0 += stride) {
+		unsigned long long q;
+		int32_t tri_idx;
+		if (REGROUP) {
 		const int32_t tri_mine = tri_cur;
 		const unsigned cls = cls_cur;
 		{
@@ -490,8 +495,12 @@ __global__ void __launch_bounds__(BLOCK, MIN_CTAS) k_shade_bounce(ShadeBuffers B
 			s_tri[pos] = tri_mine;
 		}
 		__syncthreads();
-		const unsigned long long q = q0 + s_order[threadIdx.x];
-		const int32_t tri_idx = s_tri[threadIdx.x];
+		q = q0 + s_order[threadIdx.x];
+		tri_idx = s_tri[threadIdx.x];
+		} else { // TUNING VARIANT: every lane shades its own entry, no regrouping, no barriers
+			q = q0 + threadIdx.x;
+			tri_idx = q < total ? B.in_tri[q] : -2;
+		}
 		bool keep = false, conn = false;
 		V3 origin = v3(0, 0, 0), dir = v3(0, 0, 0), color = v3(0, 0, 0);
 		unsigned id = 0, bias_bits = 0;
@@ -972,7 +981,8 @@ int run_batch(adypt_tracer *t, int first, int n, bool sum_mode)
 		StageTimer tb(t, ADYPT_STAGE_SHADE_BOUNCE);
 		// 128-thread blocks, eight per SM: smaller groups wait less on each other at the two barriers of a round (13.70 vs 14.17 ms per
 		// 64 spp of C3, profiles/r2g_bounce_block_sweep.log)
-		if (t->bounce_ctas == 4) k_shade_bounce<4, 256><<<grid_for(total, 256, s->sm_count), 256, 0, t->stream>>>(B, A, b, c.ray_tmin);
+		if (t->bounce_ctas == 1) k_shade_bounce<8, 128, false><<<2 * grid_for(total, 256, s->sm_count), 128, 0, t->stream>>>(B, A, b, c.ray_tmin); // no regrouping
+		else if (t->bounce_ctas == 4) k_shade_bounce<4, 256><<<grid_for(total, 256, s->sm_count), 256, 0, t->stream>>>(B, A, b, c.ray_tmin);
 		else k_shade_bounce<8, 128><<<2 * grid_for(total, 256, s->sm_count), 128, 0, t->stream>>>(B, A, b, c.ray_tmin);
 		count_launch();
 		ADYPT_CUDA(cudaGetLastError());

@@ -114,7 +114,8 @@ int adypt_trace_stats(adypt_scene *scene, const float *rays, uint64_t n, int mem
 /* number of kernel launches adypt_* calls have issued so far on this scene's device (bench accounting) */
 int adypt_launch_count(uint64_t *launches);
 /* tuning knobs of the persistent traversal kernel (0 = default): CTAs per SM, the refill threshold, and a
- * code-generation variant of the traversal kernels (0..8, see launch_trace in csrc/scene.cu; same algorithm, identical results) */
+ * variant of the traversal kernels (0..15, see trace_kernel_for / launch_trace in csrc/scene.cu: 0 = the product kernel, the rest are the
+ * measured alternatives kept for A/B runs, e.g. 9-11 the shared-memory hit-mask table, 12 the shared-memory ray pool; identical results) */
 int adypt_trace_configure(adypt_scene *scene, int ctas_per_sm, int refill_threshold, int variant);
 
 /* ------------------------------------------------------------------------------------------------
