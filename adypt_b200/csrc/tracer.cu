@@ -42,6 +42,7 @@ struct PTArgs { // uuPT (pathtracer.glsl:34-38) + batch bookkeeping
 	int32_t n_samples; // S
 	int32_t dims;      // Sobol dimensions per sample: 2*max_bounce, +max_bounce roulette draws when rr_start >= 0
 	int32_t rr_start;  // >= 0: Russian roulette from this bounce on (opt-in extension, -1 = the reference's behaviour)
+	uint32_t zero;     // always 0, but only known at run time: lets a kernel tie an instruction's operand to a value it must wait for
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -298,14 +299,24 @@ __device__ __forceinline__ bool scatter(const PTArgs &A, int b, const Surface &s
 // so such an addition -- a non-emissive hit, the common case -- needs no read-modify-write of the path's radiance. NaN compares unequal.
 __device__ __forceinline__ bool adds_nothing(V3 a) { return a.x == 0.0f && a.y == 0.0f && a.z == 0.0f; }
 
+// atomicAdd by ONE lane of a warp, as written. Left alone, ptxas wraps an atomic whose address is warp-uniform in its own
+// aggregation (VOTEU / UPOPC / FLO, then a pair of SHFL that consume the result right behind the atomic) -- for inline PTX as
+// well. That duplicates the aggregation done by hand here and, worse, ends the overlap of the atomic's latency with the work
+// that follows it. `lane_zero` is (lane & a run-time zero): it makes the address formally lane-dependent, so the atomic stays one
+// plain ATOMG.
+__device__ __forceinline__ unsigned long long atom_add_u64(unsigned long long *p, unsigned long long v, unsigned lane_zero)
+{
+	return atomicAdd(p + lane_zero, v);
+}
+
 // warp-aggregated append: returns this lane's slot in the output queue (valid when `keep`)
-__device__ __forceinline__ unsigned long long queue_append(bool keep, unsigned long long *counter)
+__device__ __forceinline__ unsigned long long queue_append(bool keep, unsigned long long *counter, unsigned zero)
 {
 	const unsigned m = __ballot_sync(kFullMask, keep);
 	if (m == 0u) return 0ull;
 	const unsigned lane = threadIdx.x & 31u, leader = (unsigned)__ffs((int)m) - 1u;
 	unsigned long long base = 0;
-	if (lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(m));
+	if (lane == leader) base = atom_add_u64(counter, (unsigned long long)__popc(m), lane & zero);
 	base = __shfl_sync(kFullMask, base, (int)leader);
 	return base + (unsigned long long)__popc(m & ((1u << lane) - 1u));
 }
@@ -364,7 +375,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) k_shade_primary(ShadeBuffers B,
 			const unsigned m = __ballot_sync(kFullMask, p_keep);
 			const unsigned leader = m ? (unsigned)__ffs((int)m) - 1u : 0u;
 			unsigned long long base = 0;
-			if (m != 0u && lane == leader) base = atomicAdd(B.out_count, (unsigned long long)__popc(m));
+			if (m != 0u && lane == leader) base = atom_add_u64(B.out_count, (unsigned long long)__popc(m), lane & A.zero);
 
 			const int sidx = s_first + k;
 			const bool have = live && k < group && sidx < A.n_samples;
@@ -384,7 +395,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) k_shade_primary(ShadeBuffers B,
 				}
 			}
 			if (B.conn_rays != nullptr) {
-				const unsigned long long cs = queue_append(conn, B.conn_count);
+				const unsigned long long cs = queue_append(conn, B.conn_count, A.zero);
 				if (conn) {
 					B.conn_rays[2 * cs] = make_float4(cam.origin[0], cam.origin[1], cam.origin[2], cam.tmin);
 					B.conn_rays[2 * cs + 1] = make_float4(B.sun_dir[0], B.sun_dir[1], B.sun_dir[2], __uint_as_float(id));
@@ -393,7 +404,12 @@ __global__ void __launch_bounds__(256, MIN_CTAS) k_shade_primary(ShadeBuffers B,
 			}
 
 			if (m != 0u) {
-				base = __shfl_sync(kFullMask, base, (int)leader);
+				// The slot request above must stay in flight while this sample is shaded: its first use is this shuffle, and
+				// left alone the compiler moves the shuffle up to right behind the atomic (47 % of the kernel's stall samples
+				// sat there, profiles/r2l_shade_primary_*). The source-lane operand is therefore made to depend on the
+				// shading result through a run-time zero.
+				const unsigned dep = (__float_as_uint(dir.x) ^ __float_as_uint(color.y)) & A.zero;
+				base = __shfl_sync(kFullMask, base, (int)(leader + dep));
 				if (p_keep) {
 					const unsigned long long slot = base + (unsigned long long)__popc(m & ((1u << lane) - 1u));
 					B.out_org[slot] = make_float4(sf.origin.x, sf.origin.y, sf.origin.z, cam.tmin);
@@ -544,14 +560,14 @@ __global__ void __launch_bounds__(BLOCK, MIN_CTAS) k_shade_bounce(ShadeBuffers B
 				B.ret[id] = r4;
 			}
 		}
-		const unsigned long long slot = queue_append(keep, B.out_count);
+		const unsigned long long slot = queue_append(keep, B.out_count, A.zero);
 		if (keep) {
 			B.out_org[slot] = make_float4(origin.x, origin.y, origin.z, tmin);
 			B.out_dir[slot] = make_float4(dir.x, dir.y, dir.z, __uint_as_float(id));
 			B.out_state[slot] = make_float4(color.x, color.y, color.z, __uint_as_float(bias_bits));
 		}
 		if (B.conn_rays != nullptr) {
-			const unsigned long long cs = queue_append(conn, B.conn_count);
+			const unsigned long long cs = queue_append(conn, B.conn_count, A.zero);
 			if (conn) {
 				B.conn_rays[2 * cs] = make_float4(origin.x, origin.y, origin.z, tmin);
 				B.conn_rays[2 * cs + 1] = make_float4(B.sun_dir[0], B.sun_dir[1], B.sun_dir[2], __uint_as_float(id));
@@ -693,6 +709,8 @@ struct adypt_tracer {
 	// wavefront
 	int batch_samples = 0;       // S
 	unsigned long long capacity = 0; // paths per batch = S * npix
+	uint8_t *d_slab = nullptr;               // one allocation behind all wavefront buffers below
+	size_t slab_skew = 0;                    // tuning (ADYPT_WAVEFRONT_SKEW): extra bytes (multiple of 256) between the buffers
 	float4 *d_rays[2] = {nullptr, nullptr};  // ray queues: [0, capacity) origins + tmin, [capacity, 2 capacity) directions + path id
 	int32_t *d_hit_tri = nullptr;
 	float2 *d_hit_uv = nullptr;
@@ -782,8 +800,8 @@ void free_tracer(adypt_tracer *t)
 	for (cudaEvent_t e : t->ev_pool) cudaEventDestroy(e);
 	cudaFree(t->d_trace_stats);
 	cudaFree(t->d_result); cudaFree(t->d_sum); cudaFree(t->d_prim_tri); cudaFree(t->d_prim_uv); cudaFree(t->d_bias);
-	cudaFree(t->d_dirs); cudaFree(t->d_sobol); cudaFree(t->d_rays[0]); cudaFree(t->d_rays[1]); cudaFree(t->d_hit_tri);
-	cudaFree(t->d_hit_uv); cudaFree(t->d_state[0]); cudaFree(t->d_state[1]); cudaFree(t->d_ret); cudaFree(t->d_counts); cudaFree(t->d_conn_rays); cudaFree(t->d_conn_color); cudaFree(t->d_conn_occ);
+	cudaFree(t->d_dirs); cudaFree(t->d_sobol); cudaFree(t->d_slab);
+	cudaFree(t->d_counts); cudaFree(t->d_conn_rays); cudaFree(t->d_conn_color); cudaFree(t->d_conn_occ);
 	if (t->stream) cudaStreamDestroy(t->stream);
 	delete t;
 }
@@ -852,16 +870,32 @@ int alloc_wavefront(adypt_tracer *t)
 		t->sobol_cap = sobol_need;
 	}
 	if (cap == t->capacity && S == t->batch_samples) return ADYPT_OK;
-	cudaFree(t->d_rays[0]); cudaFree(t->d_rays[1]); cudaFree(t->d_hit_tri); cudaFree(t->d_hit_uv); cudaFree(t->d_state[0]); cudaFree(t->d_state[1]); cudaFree(t->d_ret);
+	// One slab for all wavefront buffers, carved at fixed offsets: how the arrays lie relative to each other (DRAM channel /
+	// TLB aliasing between the 16 sample planes of `ret` and the queues the bounce-0 kernel writes side by side) then no
+	// longer depends on what the process allocated before -- the same kernel measured 0.96 ms in one process and 1.25 ms in
+	// another with separately allocated buffers.
+	if (t->d_slab) {
+		ADYPT_CUDA(cudaStreamSynchronize(t->stream));
+		cudaFree(t->d_slab);
+	}
+	t->d_slab = nullptr;
 	t->d_rays[0] = t->d_rays[1] = nullptr; t->d_hit_tri = nullptr; t->d_hit_uv = nullptr; t->d_state[0] = t->d_state[1] = nullptr; t->d_ret = nullptr;
 	t->capacity = 0;
-	ADYPT_CUDA(cudaMalloc((void **)&t->d_rays[0], cap * 32u));
-	ADYPT_CUDA(cudaMalloc((void **)&t->d_rays[1], cap * 32u));
-	ADYPT_CUDA(cudaMalloc((void **)&t->d_hit_tri, cap * 4u));
-	ADYPT_CUDA(cudaMalloc((void **)&t->d_hit_uv, cap * 8u));
-	ADYPT_CUDA(cudaMalloc((void **)&t->d_state[0], cap * 16u));
-	ADYPT_CUDA(cudaMalloc((void **)&t->d_state[1], cap * 16u));
-	ADYPT_CUDA(cudaMalloc((void **)&t->d_ret, cap * 16u));
+	const size_t sizes[7] = {(size_t)cap * 32u, (size_t)cap * 32u, (size_t)cap * 4u, (size_t)cap * 8u, (size_t)cap * 16u, (size_t)cap * 16u, (size_t)cap * 16u};
+	size_t offs[7], total = 0;
+	const size_t skew = t->slab_skew;
+	for (int k = 0; k < 7; ++k) {
+		offs[k] = total;
+		total += ((sizes[k] + 255u) & ~(size_t)255u) + skew;
+	}
+	ADYPT_CUDA(cudaMalloc((void **)&t->d_slab, total));
+	t->d_rays[0] = (float4 *)(t->d_slab + offs[0]);
+	t->d_rays[1] = (float4 *)(t->d_slab + offs[1]);
+	t->d_hit_tri = (int32_t *)(t->d_slab + offs[2]);
+	t->d_hit_uv = (float2 *)(t->d_slab + offs[3]);
+	t->d_state[0] = (float4 *)(t->d_slab + offs[4]);
+	t->d_state[1] = (float4 *)(t->d_slab + offs[5]);
+	t->d_ret = (float4 *)(t->d_slab + offs[6]);
 	t->capacity = cap;
 	t->batch_samples = S;
 	return ADYPT_OK;
@@ -895,6 +929,7 @@ int run_batch(adypt_tracer *t, int first, int n, bool sum_mode)
 	A.clamp = c.clamp; A.sun[0] = c.sun[0]; A.sun[1] = c.sun[1]; A.sun[2] = c.sun[2];
 	A.width = t->width; A.height = t->height; A.first_spp = first; A.n_samples = n;
 	A.rr_start = t->rr_start;
+	A.zero = 0u;
 	A.dims = (t->rr_start >= 0 ? 3 : 2) * c.max_bounce;
 	// uSpp % uTmpLife == 0 -> trace and store the primary hit; otherwise reuse it (pathtracer.glsl:113-127)
 	if (first % c.tmp_lifetime == 0 || !t->prim_valid || t->prim_block != block) {
@@ -1076,6 +1111,7 @@ int adypt_tracer_create(adypt_scene *scene, const adypt_pt_config *config, int32
 	if (const char *e = getenv("ADYPT_PRIMARY_GROUP")) t->primary_group = atoi(e);
 	if (const char *e = getenv("ADYPT_PRIMARY_CTAS")) t->primary_ctas = atoi(e);
 	if (const char *e = getenv("ADYPT_BOUNCE_CTAS")) t->bounce_ctas = atoi(e);
+	if (const char *e = getenv("ADYPT_WAVEFRONT_SKEW")) t->slab_skew = ((size_t)atol(e) + 255u) & ~(size_t)255u;
 	t->launches_at_create = g_launches.load();
 	*out = t;
 	return ADYPT_OK;

@@ -149,7 +149,9 @@ class ClockSampler(threading.Thread):
         mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+        pw = [float(r[3]) for r in self.rows if len(r) >= 9 and r[3].replace(".", "").isdigit()]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm),
+                "sm_mhz_min": min(sm) if sm else None, "power_w_max": max(pw) if pw else None}
 
 
 def bytes_per_ray(nodes, tris, hits, n):
@@ -515,6 +517,9 @@ def leg_c3(ctx):
     tr.set_profiling(stage_times=True)
     tr.profile()
     step_ms, launches = [], 0
+    sampler = ClockSampler(ctx.local_rank)
+    sampler.start()
+    time.sleep(0.25)
     for _ in range(reps):
         tr.primary(0)  # Trace(false): spp back to 0, as the viewer does before "Start"
         tr.sync()
@@ -529,6 +534,7 @@ def leg_c3(ctx):
         launches = tr.stats()["launches"] - l0
     prof = tr.profile()
     tr.set_profiling()
+    clocks = sampler.stop()
     ms = max_over_ranks(ctx, sum(step_ms)) / reps
     samples = w * h * spp
     value = ctx.world * samples / (ms * 1e-3)
@@ -578,7 +584,7 @@ def leg_c3(ctx):
     out = {"metric": "path samples/s (1080p)", "value": value, "unit": "path samples/s", "ms_per_step": ms, "steps": reps, "higher_is_better": True,
            "scaling": "weak", "config": {"workload": C3_WORKLOAD, "triangles": int(mesh.n_tris)}, "path_samples_per_s": value,
            "path_segments_per_s": ctx.world * seg / (ms * 1e-3), "segments_per_sample": seg / samples, "seconds": ms * 1e-3, "gpu_launches": int(launches),
-           "roofline": roofline, "e2e": e2e, "dtype": "f32"}
+           "roofline": roofline, "e2e": e2e, "dtype": "f32", "clocks": clocks}
     if ctx.rank == 0 and ctx.world == 1 and not ctx.args.no_cpu_baseline:
         from oracle import cpu
         hs.woop = cpu.build_woop(hs.tris, hs.tri_indices)
@@ -636,6 +642,9 @@ def leg_c5(ctx):
         dist.all_reduce(acc, op=dist.ReduceOp.SUM)  # one warm-up collective on the same buffer (NCCL sets up its channels; the render clears it)
         torch.cuda.synchronize()
     barrier(ctx)
+    sampler = ClockSampler(ctx.local_rank)
+    sampler.start()
+    time.sleep(0.25)
     l0 = tr.stats()["launches"]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
@@ -643,6 +652,7 @@ def leg_c5(ctx):
     mine = sharding.render_sharded(tr, spp, ctx.rank, ctx.world, all_reduce)
     e1.record(st)
     tr.sync()
+    clocks = sampler.stop()
     wall = max_over_ranks(ctx, time.perf_counter() - t0)
     seconds = max_over_ranks(ctx, e0.elapsed_time(e1) * 1e-3)
     launches = tr.stats()["launches"] - l0
@@ -652,7 +662,7 @@ def leg_c5(ctx):
            "samples_this_rank": int(mine), "blocks_total": (spp + L - 1) // L, "gpu_launches": int(launches),
            "reduce_ms": max_over_ranks(ctx, reduce_ev[0]) if reduce_ev else 0.0, "reduce_bytes": int(nfl * 4),
            "reduce": (f"torch.distributed.all_reduce(SUM) over NCCL of the {nfl * 4 / 1e6:.1f} MB sum buffer, inside the timed region" if ctx.world > 1 else "none (one GPU)"),
-           "timing": "cuda events on the tracer's stream around clear + blocks + all-reduce + resolve, max over ranks"}
+           "timing": "cuda events on the tracer's stream around clear + blocks + all-reduce + resolve, max over ranks", "clocks": clocks}
     # the N-GPU image against the 1-GPU running mean (the reference's accumulation order): rank 0 renders every sample alone
     if ctx.rank == 0:
         rp, rn = tr.result_buffer()
