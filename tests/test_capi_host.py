@@ -39,7 +39,8 @@ def test_exports_every_declared_symbol():
 
 def test_header_compiles_as_c(tmp_path):
     src = tmp_path / "t.c"
-    src.write_text('#include "adypt_b200.h"\nint main(void){ adypt_pt_config c; return sizeof(c) == 40 ? 0 : 1; }\n')
+    src.write_text('#include "adypt_b200.h"\nint main(void){ adypt_pt_config c; return sizeof(c) == 40 && sizeof(adypt_tracer_profile) == %d ? 0 : 1; }\n'
+                   % C.sizeof(A.TracerProfile))  # the ctypes mirror of the profile block has the C layout
     exe = tmp_path / "t"
     import subprocess
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])

@@ -156,6 +156,31 @@ def test_connect_stage_sun_visibility(A, cpu):
     assert np.array_equal(bits(tr.read(4).reshape(-1, 4)), bits(plain))  # switching it off restores the reference image
 
 
+def test_profiling_hooks_count_the_oracles_work(A, cpu):
+    """adypt_tracer_set_profiling: the instrumented traversal kernel run on the wavefront's own queues counts exactly the nodes
+    and triangles the oracle's megakernel restatement touches for the same samples (these counts are the C3 roofline's
+    algorithmic bytes in bench.py), the image is unchanged by the hooks, and the stage timer returns a time for every stage."""
+    g = load_golden("city12")
+    sc, tr = make(A, g)
+    origin, m = oracle_cam(cpu, g)
+    tr.set_profiling(stage_times=True, trace_counters=True)
+    tr.sample(40)
+    pr = tr.profile()
+    exp, _, cnt = cpu.pt_render(g, origin, m["inv_proj"], m["inv_view"], W_, H_, OCFG, tr.get_bias(), 0, 40)
+    assert np.array_equal(bits(tr.read(4).reshape(-1, 4)), bits(exp))
+    assert pr["trace"]["nodes"] + pr["primary"]["nodes"] == cnt["nodes"]
+    assert pr["trace"]["tris"] + pr["primary"]["tris"] == cnt["tris"]
+    assert pr["primary"]["rays"] == 3 * W_ * H_  # one primary traversal per tmpLifetime block (pathtracer.glsl:113-127)
+    assert pr["primary"]["rays"] + pr["trace"]["rays"] == cnt["segments"] == tr.stats()["segments"]  # traced segments; cached primary hits are not
+    assert max(pr["trace"]["max_stack"], 0) <= cnt["max_stack"]
+    for stage in ("generate", "trace_primary", "shade_primary", "trace_bounce", "shade_bounce", "accumulate"):
+        assert pr["stage_ms"][stage] > 0.0 and pr["stage_launches"][stage] > 0, stage
+    assert pr["stage_launches"]["trace_bounce"] == 3 * (OCFG["max_bounce"] - 1)
+    tr.set_profiling()
+    assert tr.profile()["stage_ms"]["trace_bounce"] == 0.0  # reset by the previous read
+    assert "trace_kernel" in sc.kernel_name(False) and "trace_kernel" in sc.kernel_name(True)
+
+
 def test_config_limits(A):
     g = load_golden("city12")
     sc = A.Scene(g.nodes, g.tri_indices, g.woop, g.tris, g.mats)
