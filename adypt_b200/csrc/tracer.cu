@@ -324,10 +324,11 @@ __device__ __forceinline__ unsigned long long queue_append(bool keep, unsigned l
 // Bounce 0 of the batch's S samples. All samples of a tmpLifetime block share the primary hit and the camera ray
 // (pathtracer.glsl:113-127, 206-211), so a thread takes one pixel and a GROUP of its samples: FetchInfo, the normal and the
 // emission term are evaluated once per group and only the material switch -- the part that consumes the sample's Sobol pair --
-// runs per sample. The queue slot of sample k is requested (one atomic per warp) before sample k+1 is shaded and used after,
-// so the atomic's latency hides behind that work. Path id = s * npix + pixel.
+// runs per sample, and the queue slots of several samples are requested with one atomic per warp. Path id = s * npix + pixel.
+constexpr int kMaxPrimaryChunk = 8;
+
 template <int MIN_CTAS>
-__global__ void __launch_bounds__(256, MIN_CTAS) k_shade_primary(ShadeBuffers B, PTArgs A, CameraArgs cam, int group)
+__global__ void __launch_bounds__(256, MIN_CTAS) k_shade_primary(ShadeBuffers B, PTArgs A, CameraArgs cam, int group, int chunk)
 {
 	const unsigned npix = (unsigned)A.width * (unsigned)A.height;
 	const unsigned n_groups = ((unsigned)A.n_samples + (unsigned)group - 1u) / (unsigned)group;
@@ -367,57 +368,60 @@ __global__ void __launch_bounds__(256, MIN_CTAS) k_shade_primary(ShadeBuffers B,
 			} else if (B.conn_rays == nullptr)
 				ret0 = ret0 + v3(1.f, 1.f, 1.f) * sun; // :130-135
 		}
-		// software pipeline over the group's samples: [request the slot of sample k-1] [shade sample k] [store sample k-1]
-		bool p_keep = false;
-		V3 p_dir = v3(0, 0, 0), p_color = v3(0, 0, 0);
-		unsigned p_id = 0u;
-		for (int k = 0; k <= group; ++k) {
-			const unsigned m = __ballot_sync(kFullMask, p_keep);
-			const unsigned leader = m ? (unsigned)__ffs((int)m) - 1u : 0u;
-			unsigned long long base = 0;
-			if (m != 0u && lane == leader) base = atom_add_u64(B.out_count, (unsigned long long)__popc(m), lane & A.zero);
-
-			const int sidx = s_first + k;
-			const bool have = live && k < group && sidx < A.n_samples;
-			bool keep = false, conn = false;
-			V3 dir = dir0, color = v3(1.f, 1.f, 1.f);
-			const unsigned id = (unsigned)sidx * npix + pix;
-			if (have) {
-				B.ret[id] = make_float4(ret0.x, ret0.y, ret0.z, 0.0f);
-				if (!hit) {
-					conn = B.conn_rays != nullptr; // the shadow ray starts at the camera
-					color = color * sun;
-				} else if (!last) {
-					const float rx = fract(B.sobol[sidx * dims + 0] + fbx);
-					const float ry = fract(B.sobol[sidx * dims + 1] + fby);
-					const float xi = A.rr_start >= 0 ? fract(B.sobol[sidx * dims + 2 * A.max_bounce] + fbx) : 0.0f;
-					keep = scatter(A, 0, sf, rx, ry, xi, dir, color);
+		// The group's samples in chunks: every sample of a chunk is shaded first and parked (two float4 per sample in local
+		// memory), then the warp asks for the chunk's queue slots with ONE atomic and writes the survivors out. One atomic per
+		// warp and SAMPLE put a million same-address atomics into every launch -- about what the L2 retires in the kernel's
+		// whole run time (the kernel sat at its slot requests: 47 % of the stall samples, profiles/r2l_shade_primary_*).
+		for (int k0 = 0; k0 < group; k0 += chunk) {
+			float4 c_dir[kMaxPrimaryChunk], c_col[kMaxPrimaryChunk]; // dir + path id; colour + slot offset inside the warp's claim
+			unsigned kept = 0u, total = 0u;
+			for (int j = 0; j < chunk; ++j) {
+				const int sidx = s_first + k0 + j;
+				const bool have = live && k0 + j < group && sidx < A.n_samples;
+				bool keep = false, conn = false;
+				V3 dir = dir0, color = v3(1.f, 1.f, 1.f);
+				const unsigned id = (unsigned)sidx * npix + pix;
+				if (have) {
+					B.ret[id] = make_float4(ret0.x, ret0.y, ret0.z, 0.0f);
+					if (!hit) {
+						conn = B.conn_rays != nullptr; // the shadow ray starts at the camera
+						color = color * sun;
+					} else if (!last) {
+						const float rx = fract(B.sobol[sidx * dims + 0] + fbx);
+						const float ry = fract(B.sobol[sidx * dims + 1] + fby);
+						const float xi = A.rr_start >= 0 ? fract(B.sobol[sidx * dims + 2 * A.max_bounce] + fbx) : 0.0f;
+						keep = scatter(A, 0, sf, rx, ry, xi, dir, color);
+					}
 				}
-			}
-			if (B.conn_rays != nullptr) {
-				const unsigned long long cs = queue_append(conn, B.conn_count, A.zero);
-				if (conn) {
-					B.conn_rays[2 * cs] = make_float4(cam.origin[0], cam.origin[1], cam.origin[2], cam.tmin);
-					B.conn_rays[2 * cs + 1] = make_float4(B.sun_dir[0], B.sun_dir[1], B.sun_dir[2], __uint_as_float(id));
-					B.conn_color[cs] = make_float4(color.x, color.y, color.z, 0.0f);
+				if (B.conn_rays != nullptr) {
+					const unsigned long long cs = queue_append(conn, B.conn_count, A.zero);
+					if (conn) {
+						B.conn_rays[2 * cs] = make_float4(cam.origin[0], cam.origin[1], cam.origin[2], cam.tmin);
+						B.conn_rays[2 * cs + 1] = make_float4(B.sun_dir[0], B.sun_dir[1], B.sun_dir[2], __uint_as_float(id));
+						B.conn_color[cs] = make_float4(color.x, color.y, color.z, 0.0f);
+					}
 				}
-			}
-
-			if (m != 0u) {
-				// The slot request above must stay in flight while this sample is shaded: its first use is this shuffle, and
-				// left alone the compiler moves the shuffle up to right behind the atomic (47 % of the kernel's stall samples
-				// sat there, profiles/r2l_shade_primary_*). The source-lane operand is therefore made to depend on the
-				// shading result through a run-time zero.
-				const unsigned dep = (__float_as_uint(dir.x) ^ __float_as_uint(color.y)) & A.zero;
-				base = __shfl_sync(kFullMask, base, (int)(leader + dep));
-				if (p_keep) {
-					const unsigned long long slot = base + (unsigned long long)__popc(m & ((1u << lane) - 1u));
-					B.out_org[slot] = make_float4(sf.origin.x, sf.origin.y, sf.origin.z, cam.tmin);
-					B.out_dir[slot] = make_float4(p_dir.x, p_dir.y, p_dir.z, __uint_as_float(p_id));
-					B.out_state[slot] = make_float4(p_color.x, p_color.y, p_color.z, __uint_as_float(bias_bits));
+				const unsigned m = __ballot_sync(kFullMask, keep);
+				if (keep) {
+					kept |= 1u << j;
+					c_dir[j] = make_float4(dir.x, dir.y, dir.z, __uint_as_float(id));
+					c_col[j] = make_float4(color.x, color.y, color.z, __uint_as_float(total + (unsigned)__popc(m & ((1u << lane) - 1u))));
 				}
+				total += (unsigned)__popc(m);
 			}
-			p_keep = keep; p_dir = dir; p_color = color; p_id = id;
+			if (total != 0u) { // warp-uniform
+				unsigned long long base = 0;
+				if (lane == 0u) base = atom_add_u64(B.out_count, (unsigned long long)total, lane & A.zero);
+				base = __shfl_sync(kFullMask, base, 0);
+				for (int j = 0; j < chunk; ++j)
+					if ((kept >> j) & 1u) {
+						const float4 d4 = c_dir[j], c4 = c_col[j];
+						const unsigned long long slot = base + (unsigned long long)__float_as_uint(c4.w);
+						B.out_org[slot] = make_float4(sf.origin.x, sf.origin.y, sf.origin.z, cam.tmin);
+						B.out_dir[slot] = d4;
+						B.out_state[slot] = make_float4(c4.x, c4.y, c4.z, __uint_as_float(bias_bits));
+					}
+			}
 		}
 	}
 }
@@ -441,7 +445,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_CTAS) k_shade_bounce(ShadeBuffers B
 	// free. The branch comes from a one-byte-per-triangle table, the hit index of the NEXT round is already in flight while
 	// this one is shaded, and ranks come from one match.any per warp: two barriers per round, no shared-memory atomics.
 	constexpr unsigned kWarps = BLOCK / 32;
-	static_assert(BLOCK == 256 || BLOCK == 128, "eight or four warps");
+	static_assert(BLOCK == 256 || BLOCK == 128 || BLOCK == 64, "eight, four or two warps");
 	__shared__ __align__(16) unsigned s_count[2][8][kWarps]; // [round parity][class][warp]; the other parity is zeroed for the next round
 	__shared__ unsigned short s_order[BLOCK];             // regrouped position -> entry of the round
 	__shared__ int32_t s_tri[BLOCK];                    // regrouped position -> hit triangle
@@ -486,9 +490,14 @@ __global__ void __launch_bounds__(BLOCK, MIN_CTAS) k_shade_bounce(ShadeBuffers B
 			// picks its class's number with one shuffle.
 			unsigned total_c = 0u, before_c = 0u;
 			if (lane < 8u) {
-				unsigned v[kWarps];
-				const uint4 a = *reinterpret_cast<const uint4 *>(&s_count[par][lane][0]);
-				v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+				unsigned v[kWarps < 4 ? 4 : kWarps];
+				if (kWarps == 2) {
+					const uint2 a = *reinterpret_cast<const uint2 *>(&s_count[par][lane][0]);
+					v[0] = a.x; v[1] = a.y;
+				} else {
+					const uint4 a = *reinterpret_cast<const uint4 *>(&s_count[par][lane][0]);
+					v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+				}
 				if (kWarps == 8) {
 					const uint4 b4 = *reinterpret_cast<const uint4 *>(&s_count[par][lane][kWarps - 4]);
 					v[kWarps - 4] = b4.x; v[kWarps - 3] = b4.y; v[kWarps - 2] = b4.z; v[kWarps - 1] = b4.w;
@@ -735,6 +744,7 @@ struct adypt_tracer {
 	// traversal kernel that counts the nodes and triangles the wavefront's rays touch. Off by default.
 	int bounce_ctas = 0;   // tuning (ADYPT_BOUNCE_CTAS): 4 = 256-thread blocks, four per SM; otherwise 128-thread blocks, eight per SM (default)
 	int primary_ctas = 0;  // tuning (ADYPT_PRIMARY_CTAS): CTAs per SM the bounce-0 kernel is compiled for (2, 3, 4); 0 = default
+	int primary_chunk = 0; // tuning (ADYPT_PRIMARY_CHUNK): samples of a group shaded per queue-slot request (1..8); 0 = default
 	int primary_group = 0; // tuning (ADYPT_PRIMARY_GROUP): samples of one pixel a thread of the bounce-0 stage shades; 0 = default
 	int profiling = 0;
 	std::vector<cudaEvent_t> ev_pool;
@@ -987,10 +997,11 @@ int run_batch(adypt_tracer *t, int first, int n, bool sum_mode)
 		const int group = t->primary_group > 0 ? t->primary_group : 16; // samples of a pixel per thread (1 .. 16 measured: profiles/r2d_primary_sweep.log)
 		const unsigned long long items = (unsigned long long)t->npix * (unsigned long long)((n + group - 1) / group);
 		const int g = grid_for(items, 256, s->sm_count);
-		switch (t->primary_ctas) { // registers per thread: 64 / 80 / 116 (tuning; same results)
-		case 4: k_shade_primary<4><<<g, 256, 0, t->stream>>>(B, A, t->cam, group); break;
-		case 2: k_shade_primary<2><<<g, 256, 0, t->stream>>>(B, A, t->cam, group); break;
-		default: k_shade_primary<3><<<g, 256, 0, t->stream>>>(B, A, t->cam, group); break;
+		const int chunk = t->primary_chunk > 0 && t->primary_chunk <= kMaxPrimaryChunk ? t->primary_chunk : 4; // samples per queue-slot request
+		switch (t->primary_ctas) { // registers per thread: 64 / 80 / 120 (tuning; same results; profiles/r2u_primary_chunk_sweep.log)
+		case 3: k_shade_primary<3><<<g, 256, 0, t->stream>>>(B, A, t->cam, group, chunk); break;
+		case 2: k_shade_primary<2><<<g, 256, 0, t->stream>>>(B, A, t->cam, group, chunk); break;
+		default: k_shade_primary<4><<<g, 256, 0, t->stream>>>(B, A, t->cam, group, chunk); break;
 		}
 		count_launch();
 		ADYPT_CUDA(cudaGetLastError());
@@ -1017,6 +1028,7 @@ int run_batch(adypt_tracer *t, int first, int n, bool sum_mode)
 		// 128-thread blocks, eight per SM: smaller groups wait less on each other at the two barriers of a round (13.70 vs 14.17 ms per
 		// 64 spp of C3, profiles/r2g_bounce_block_sweep.log)
 		if (t->bounce_ctas == 1) k_shade_bounce<8, 128, false><<<2 * grid_for(total, 256, s->sm_count), 128, 0, t->stream>>>(B, A, b, c.ray_tmin); // no regrouping
+		else if (t->bounce_ctas == 16) k_shade_bounce<16, 64><<<4 * grid_for(total, 256, s->sm_count), 64, 0, t->stream>>>(B, A, b, c.ray_tmin); // regroups 64 entries
 		else if (t->bounce_ctas == 4) k_shade_bounce<4, 256><<<grid_for(total, 256, s->sm_count), 256, 0, t->stream>>>(B, A, b, c.ray_tmin);
 		else k_shade_bounce<8, 128><<<2 * grid_for(total, 256, s->sm_count), 128, 0, t->stream>>>(B, A, b, c.ray_tmin);
 		count_launch();
@@ -1110,6 +1122,7 @@ int adypt_tracer_create(adypt_scene *scene, const adypt_pt_config *config, int32
 	memcpy(t->cam.inv_view, ident, 64);
 	if (const char *e = getenv("ADYPT_PRIMARY_GROUP")) t->primary_group = atoi(e);
 	if (const char *e = getenv("ADYPT_PRIMARY_CTAS")) t->primary_ctas = atoi(e);
+	if (const char *e = getenv("ADYPT_PRIMARY_CHUNK")) t->primary_chunk = atoi(e);
 	if (const char *e = getenv("ADYPT_BOUNCE_CTAS")) t->bounce_ctas = atoi(e);
 	if (const char *e = getenv("ADYPT_WAVEFRONT_SKEW")) t->slab_skew = ((size_t)atol(e) + 255u) & ~(size_t)255u;
 	t->launches_at_create = g_launches.load();
