@@ -455,6 +455,8 @@ int adypt_trace_configure(adypt_scene *s, int ctas_per_sm, int refill_threshold,
 	return guarded([&]() -> int {
 	if (!s) return fail(ADYPT_EINVAL, "scene is NULL");
 	if (ctas_per_sm < 0 || refill_threshold < 0 || refill_threshold > 32 || variant < 0 || variant > 15) return fail(ADYPT_EINVAL, "bad tuning value");
+	if (variant == 12 && !getenv("ADYPT_EXPERIMENTAL"))
+		return fail(ADYPT_EINVAL, "variant 12 (shared-memory ray pool) is an experiment without a deep-stack path: set ADYPT_EXPERIMENTAL=1 to select it");
 	s->ctas_per_sm = ctas_per_sm;
 	s->refill_threshold = refill_threshold;
 	s->variant = variant;

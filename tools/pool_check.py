@@ -4,6 +4,7 @@ kernel on the committed fixture scenes: ids, t, uv and any-hit bits must be iden
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ.setdefault('ADYPT_EXPERIMENTAL', '1')
 import adypt_b200 as A
 ok = True
 for name in ("tiny_two_triangles", "tiny_shared_edge", "tiny_strip", "tiny_deep", "city12"):
