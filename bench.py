@@ -338,9 +338,6 @@ def run_native(args, rank, world, local_rank):
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # the collectives of this run (barriers + the C5 all-reduce) are listed on stderr by NCCL itself
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "COLL,TUNING")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         ctx.dist = dist
     torch.cuda.set_device(local_rank)
@@ -781,6 +778,12 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and args.impl == "native":
+        # the collectives of this run (barriers + the C5 all-reduce) are listed on stderr by NCCL itself; set before torch is imported
+        # (the image pre-sets NCCL_DEBUG=VERSION, so this is an override, limited to the two subsystems that describe collectives)
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+            os.environ["NCCL_DEBUG"] = "INFO"
+            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "COLL,TUNING")
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:
