@@ -96,6 +96,11 @@ __global__ void k_generate(CameraArgs cam, int w, int h, float bx, float by, flo
 	}
 }
 
+__global__ void k_unorm8_table(float *__restrict__ out)
+{
+	out[threadIdx.x] = (float)threadIdx.x / 255.0f; // the same IEEE division the shading code would do per segment
+}
+
 // ---------------------------------------------------------------------------------------------
 // Sobol: uSobol for every sample of the batch, computed on the device from the direction numbers
 // (Sobol.cpp:16-21 in closed form: state after n calls = XOR of columns selected by gray(n)).
@@ -121,13 +126,14 @@ struct ShadeBuffers {
 	const uchar4 *__restrict__ texels;       // diffuse textures, RGBX8 (nullptr when TEXTURE_COUNT == 0)
 	const int4 *__restrict__ tex_table;      // (first texel, width, height, -)
 	const uchar2 *__restrict__ bias;         // uSobolBiasImg
+	const float *__restrict__ unorm8;        // the 256 values (float)b / 255.0f an RG8 UNORM texel can take, made by that very division on the device
 	const float *__restrict__ sobol;         // [S][dims]
 	// primary hit cache (uPrimaryTmpImg): x = tri id bits, zw = uv
 	const int32_t *__restrict__ prim_tri;
 	const float2 *__restrict__ prim_uv;
 	// current queue (bounce >= 1), structure of arrays: ray origins (+ tmin) and directions (.w = path id bits) as the traversal
-	// kernel takes them, the hits it wrote, and per entry the path's throughput + its pixel's bias bytes (xyz = colour,
-	// w = bias.x | bias.y << 8). Shading reads the direction but not the origin, so the two are kept apart.
+	// kernel takes them, the hits it wrote, and per entry the path's throughput + its pixel's bias bytes and sample number
+	// (xyz = colour, w = bias.x | bias.y << 8 | sample in the batch << 16). Shading reads the direction but not the origin, so the two are kept apart.
 	const float4 *__restrict__ in_org;
 	const float4 *__restrict__ in_dir;
 	const int32_t *__restrict__ in_tri;
@@ -419,7 +425,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) k_shade_primary(ShadeBuffers B,
 						const unsigned long long slot = base + (unsigned long long)__float_as_uint(c4.w);
 						B.out_org[slot] = make_float4(sf.origin.x, sf.origin.y, sf.origin.z, cam.tmin);
 						B.out_dir[slot] = d4;
-						B.out_state[slot] = make_float4(c4.x, c4.y, c4.z, __uint_as_float(bias_bits));
+						B.out_state[slot] = make_float4(c4.x, c4.y, c4.z, __uint_as_float(bias_bits | ((unsigned)(s_first + k0 + j) << 16)));
 					}
 			}
 		}
@@ -432,13 +438,13 @@ enum { kClassMiss = 0, kClassDiffuse = 1, kClassGlossy = 2, kClassMirror = 3, kC
 template <int MIN_CTAS, int BLOCK, bool REGROUP = true>
 __global__ void __launch_bounds__(BLOCK, MIN_CTAS) k_shade_bounce(ShadeBuffers B, PTArgs A, int b, float tmin)
 {
-	const unsigned npix = (unsigned)A.width * (unsigned)A.height;
-	const unsigned long long total = *B.in_count;
-	const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-	const unsigned long long rounds = (total + stride - 1) / stride;
+	// queue positions fit 32 bits (a batch holds fewer than 2^31 + a grid's worth of paths, alloc_wavefront)
+	const unsigned total = (unsigned)*B.in_count;
+	const unsigned stride = gridDim.x * blockDim.x;
+	const unsigned rounds = total / stride + (total % stride != 0u ? 1u : 0u);
 	const int dims = A.dims;
 	const bool last = b == A.max_bounce - 1; // the loop of Render ends after this segment: only the emission / sun terms are left
-	if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(B.segments, total);
+	if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(B.segments, (unsigned long long)total);
 	// Each block regroups its BLOCK (256) queue entries by shading branch before shading them, so that a warp mostly runs ONE of
 	// miss / diffuse / glossy / mirror / glass instead of all of them one after the other (13.4 of 32 lanes active without
 	// this). Which lane shades which entry never reaches the image: every path owns its slots and the next queue's order is
@@ -451,7 +457,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_CTAS) k_shade_bounce(ShadeBuffers B
 	__shared__ int32_t s_tri[BLOCK];                    // regrouped position -> hit triangle
 	const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 	const unsigned lt_mask = (1u << lane) - 1u;
-	unsigned long long q0 = (unsigned long long)blockIdx.x * blockDim.x;
+	unsigned q0 = blockIdx.x * blockDim.x;
 	// two rounds of look-ahead: the hit index of round r+2 and the class byte of round r+1 are in flight while round r is shaded
 	int32_t tri_cur = -2, tri_n1 = -2;       // -2 = past the end of the queue
 	unsigned cls_cur = (unsigned)kClassNone;
@@ -464,14 +470,14 @@ __global__ void __launch_bounds__(BLOCK, MIN_CTAS) k_shade_bounce(ShadeBuffers B
 	if (threadIdx.x < 16u * kWarps) (&s_count[0][0][0])[threadIdx.x] = 0u;
 	__syncthreads();
 	}
-	for (unsigned long long r = 0; r < rounds; ++r, q0 += stride) {
-		unsigned long long q;
+	for (unsigned r = 0; r < rounds; ++r, q0 += stride) {
+		unsigned q;
 		int32_t tri_idx;
 		if (REGROUP) {
 		const int32_t tri_mine = tri_cur;
 		const unsigned cls = cls_cur;
 		{
-			const unsigned long long q2 = q0 + 2u * stride + threadIdx.x;
+			const unsigned q2 = q0 + 2u * stride + threadIdx.x;
 			const int32_t tri_n2 = (r + 2 < rounds && q2 < total) ? B.in_tri[q2] : -2;
 			cls_cur = tri_n1 == -2 ? (unsigned)kClassNone : tri_n1 == -1 ? (unsigned)kClassMiss : (unsigned)B.tri_class[tri_n1];
 			tri_cur = tri_n1;
@@ -553,8 +559,8 @@ __global__ void __launch_bounds__(BLOCK, MIN_CTAS) k_shade_bounce(ShadeBuffers B
 				origin = sf.origin;
 				add = color * sf.emissive; // :139
 				if (!last) {
-					const unsigned s = id / npix;
-					const float fbx = (float)(bias_bits & 0xffu) / 255.0f, fby = (float)((bias_bits >> 8) & 0xffu) / 255.0f;
+					const unsigned s = bias_bits >> 16; // the path's sample within the batch travels with its bias bytes (= id / npix)
+					const float fbx = __ldg(B.unorm8 + (bias_bits & 0xffu)), fby = __ldg(B.unorm8 + ((bias_bits >> 8) & 0xffu)); // byte / 255.0f
 					const float rx = fract(B.sobol[s * dims + 2 * b] + fbx);
 					const float ry = fract(B.sobol[s * dims + 2 * b + 1] + fby);
 					const float xi = A.rr_start >= 0 ? fract(B.sobol[s * dims + 2 * A.max_bounce + b] + fbx) : 0.0f;
@@ -711,6 +717,7 @@ struct adypt_tracer {
 	int32_t *d_prim_tri = nullptr;
 	float2 *d_prim_uv = nullptr;
 	uchar2 *d_bias = nullptr;
+	float *d_unorm8 = nullptr;  // 256 floats, see ShadeBuffers::unorm8
 	std::vector<uint8_t> h_bias;
 	// Sobol
 	uint32_t *d_dirs = nullptr;
@@ -809,7 +816,7 @@ void free_tracer(adypt_tracer *t)
 	if (t->stream) cudaStreamSynchronize(t->stream);
 	for (cudaEvent_t e : t->ev_pool) cudaEventDestroy(e);
 	cudaFree(t->d_trace_stats);
-	cudaFree(t->d_result); cudaFree(t->d_sum); cudaFree(t->d_prim_tri); cudaFree(t->d_prim_uv); cudaFree(t->d_bias);
+	cudaFree(t->d_result); cudaFree(t->d_sum); cudaFree(t->d_prim_tri); cudaFree(t->d_prim_uv); cudaFree(t->d_bias); cudaFree(t->d_unorm8);
 	cudaFree(t->d_dirs); cudaFree(t->d_sobol); cudaFree(t->d_slab);
 	cudaFree(t->d_counts); cudaFree(t->d_conn_rays); cudaFree(t->d_conn_color); cudaFree(t->d_conn_occ);
 	if (t->stream) cudaStreamDestroy(t->stream);
@@ -871,6 +878,7 @@ int alloc_wavefront(adypt_tracer *t)
 	int S = t->cfg.tmp_lifetime;
 	const unsigned long long by_mem = std::max(1ull, kDefaultMaxPaths / (unsigned long long)t->npix);
 	if ((unsigned long long)S > by_mem) S = (int)by_mem;
+	if (S > 65535) S = 65535; // a path's sample number shares a word with its bias bytes in the state queue
 	const unsigned long long cap = (unsigned long long)S * t->npix;
 	if (cap >= (1ull << 32)) return fail(ADYPT_ERANGE, "batch too large for 32-bit path ids");
 	const size_t sobol_need = (size_t)t->dims_cap * (size_t)S;
@@ -960,7 +968,7 @@ int run_batch(adypt_tracer *t, int first, int n, bool sum_mode)
 	ts.end();
 	unsigned long long *trace_stats = (t->profiling & 2) ? t->d_trace_stats : nullptr;
 	ShadeBuffers B;
-	B.shade = s->d_shade; B.tri_class = s->d_tri_class; B.mats = s->d_mats; B.texels = s->d_texels; B.tex_table = s->d_tex_table; B.bias = t->d_bias; B.sobol = t->d_sobol;
+	B.shade = s->d_shade; B.tri_class = s->d_tri_class; B.mats = s->d_mats; B.texels = s->d_texels; B.tex_table = s->d_tex_table; B.bias = t->d_bias; B.unorm8 = t->d_unorm8; B.sobol = t->d_sobol;
 	B.prim_tri = t->d_prim_tri; B.prim_uv = t->d_prim_uv;
 	B.in_org = B.in_dir = nullptr; B.in_tri = t->d_hit_tri; B.in_uv = t->d_hit_uv; B.in_state = nullptr; B.in_count = nullptr;
 	B.out_org = t->d_rays[1]; B.out_dir = t->d_rays[1] + t->capacity; B.out_state = t->d_state[1]; B.out_count = t->d_counts + 1;
@@ -1093,6 +1101,12 @@ int adypt_tracer_create(adypt_scene *scene, const adypt_pt_config *config, int32
 	if (e == cudaSuccess) e = cudaMalloc((void **)&t->d_prim_tri, np * 4u);
 	if (e == cudaSuccess) e = cudaMalloc((void **)&t->d_prim_uv, np * 8u);
 	if (e == cudaSuccess) e = cudaMalloc((void **)&t->d_bias, np * 2u);
+	if (e == cudaSuccess) e = cudaMalloc((void **)&t->d_unorm8, 256u * 4u);
+	if (e == cudaSuccess) {
+		k_unorm8_table<<<1, 256>>>(t->d_unorm8);
+		count_launch();
+		e = cudaDeviceSynchronize();
+	}
 	if (e == cudaSuccess) e = cudaMemset(t->d_result, 0, np * 16u);
 	if (e == cudaSuccess) e = cudaMemset(t->d_sum, 0, np * 16u);
 	if (e == cudaSuccess) {
