@@ -94,11 +94,11 @@ __global__ void build_woop_kernel(const uint8_t *__restrict__ tris, const int32_
 // Shading records: the wavefront's shading stage gathers one Triangle per segment. The reference's record is
 // 100 bytes at a 100-byte stride (Shape.hpp:70-88) -- 25 scalar loads over 4 or 5 sectors; here it is copied, unchanged, to
 // the start of a 128-byte line (7 vector loads, exactly one L2 line). The shading branch its material selects
-// (pathtracer.glsl:144-201) is also kept as one byte per triangle, so that the stage can regroup a block's segments by
-// branch without touching the record or the material. 1 diffuse (illum 1, and illum 2 with shininess*0.01 <= 0.3), 2 glossy,
+// (pathtracer.glsl:144-201) is also kept in a word per triangle (class << 24 | material id), so that the stage can regroup a block's
+// segments by branch -- and request the material -- without touching the record. 1 diffuse (illum 1, and illum 2 with shininess*0.01 <= 0.3), 2 glossy,
 // 3 mirror (illum 3-5), 4 dielectric (6, 7), 5 everything else (passes straight through).
 __global__ void build_shade_records(const uint8_t *__restrict__ tris, const Material *__restrict__ mats, uint32_t n_tris, uint32_t n_mats,
-                                    float4 *__restrict__ shade, uint8_t *__restrict__ tri_class)
+                                    float4 *__restrict__ shade, uint32_t *__restrict__ tri_class)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n_tris) return;
@@ -117,7 +117,9 @@ __global__ void build_shade_records(const uint8_t *__restrict__ tris, const Mate
 	for (int k = 26; k < 32; ++k) f[k] = 0.0f;
 #pragma unroll
 	for (int k = 0; k < 8; ++k) shade[(size_t)i * 8u + k] = make_float4(f[4 * k], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]);
-	tri_class[i] = (uint8_t)cls;
+	// class in the top byte, material id below it: the shading stage learns both one round ahead of the record itself, so the
+	// material's 64 bytes are requested together with the record instead of after it
+	tri_class[i] = (cls << 24) | ((uint32_t)matid < 0x00ffffffu ? (uint32_t)matid : 0x00ffffffu); // 0xffffff: look in the record
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -361,11 +363,11 @@ int adypt_scene_create(const adypt_scene_desc *d, adypt_scene **out)
 	}
 #undef UP
 	if (d->n_tris && d->n_mats) {
-		if (cudaMalloc((void **)&s->d_shade, (size_t)d->n_tris * 128u) != cudaSuccess || cudaMalloc((void **)&s->d_tri_class, (size_t)d->n_tris) != cudaSuccess) {
+		if (cudaMalloc((void **)&s->d_shade, (size_t)d->n_tris * 128u) != cudaSuccess || cudaMalloc((void **)&s->d_tri_class, (size_t)d->n_tris * 4u) != cudaSuccess) {
 			free_scene(s);
 			return fail(ADYPT_ENOMEM, "cudaMalloc shading records");
 		}
-		s->device_bytes += (size_t)d->n_tris * 129u;
+		s->device_bytes += (size_t)d->n_tris * 132u;
 		build_shade_records<<<(d->n_tris + 127) / 128, 128>>>(s->d_tris, s->d_mats, d->n_tris, d->n_mats, s->d_shade, s->d_tri_class);
 		count_launch();
 		cudaError_t e = cudaDeviceSynchronize();

@@ -24,9 +24,9 @@ struct adypt_scene {
 	uint8_t *d_tris = nullptr;         // n_tris * 100
 	adypt::Material *d_mats = nullptr; // n_mats
 	// derived at upload, like the Woop rows: the Triangle record on its own 128-byte line (8 x float4: floats 0..24 = the
-	// 100-byte record, float 25 = shading class) and the shading class alone, one byte per triangle
+	// 100-byte record, float 25 = shading class) and a word per triangle with the shading class and the material id
 	float4 *d_shade = nullptr;         // n_tris * 8
-	uint8_t *d_tri_class = nullptr;    // n_tris
+	uint32_t *d_tri_class = nullptr;   // n_tris: shading class << 24 | material id
 	uchar4 *d_texels = nullptr;        // all textures back to back, RGBX8
 	int4 *d_tex_table = nullptr;       // per texture: (first texel, width, height, 0)
 	uint32_t n_textures = 0;           // TEXTURE_COUNT

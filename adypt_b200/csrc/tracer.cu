@@ -121,7 +121,7 @@ __global__ void k_sobol(const uint32_t *__restrict__ dirs, int dims, int first_s
 
 struct ShadeBuffers {
 	const float4 *__restrict__ shade;        // 8 x float4 per scene triangle: the Triangle record on a 128-byte line (scene.cu)
-	const uint8_t *__restrict__ tri_class;   // shading branch of a triangle's material (kClass*), for the regrouping pass
+	const uint32_t *__restrict__ tri_class;  // per triangle: shading branch of its material (kClass*) << 24 | material id, for the regrouping pass
 	const Material *__restrict__ mats;
 	const uchar4 *__restrict__ texels;       // diffuse textures, RGBX8 (nullptr when TEXTURE_COUNT == 0)
 	const int4 *__restrict__ tex_table;      // (first texel, width, height, -)
@@ -213,12 +213,15 @@ struct Surface {
 
 // FetchInfo for scene triangle tri_idx at (u, v). The Triangle record is read from its 128-byte line: floats 0..24 are the
 // reference's Triangle (Shape.hpp:70-88: p1 p2 p3, n1 n2 n3, tc1 tc2 tc3, matid), so the arithmetic is unchanged.
-__device__ __forceinline__ void fetch_surface(const ShadeBuffers &B, int32_t tri_idx, float u, float v, Surface &s)
+// matid >= 0: the caller already knows the triangle's material (from the class table), so the material is requested alongside the
+// record; otherwise it is taken from the record (float 24), one dependent load later.
+__device__ __forceinline__ void fetch_surface(const ShadeBuffers &B, int32_t tri_idx, float u, float v, Surface &s, int32_t matid = -1)
 {
 	const float4 *rec = B.shade + (size_t)tri_idx * 8u;
-	const float4 r0 = __ldg(rec), r1 = __ldg(rec + 1), r2 = __ldg(rec + 2), r3 = __ldg(rec + 3), r4 = __ldg(rec + 4), r6 = __ldg(rec + 6);
+	const float4 r0 = __ldg(rec), r1 = __ldg(rec + 1), r2 = __ldg(rec + 2), r3 = __ldg(rec + 3), r4 = __ldg(rec + 4);
 	const float t[18] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, r3.w, r4.x, r4.y};
-	const Material m = B.mats[__float_as_int(r6.x)];
+	if (matid < 0) matid = __float_as_int(__ldg(rec + 6).x);
+	const Material m = B.mats[matid];
 	s.normal = normalize(bary(t + 9, t + 12, t + 15, u, v));
 	s.origin = bary(t, t + 3, t + 6, u, v); // :138
 	s.emissive = v3(m.er, m.eg, m.eb);
@@ -455,31 +458,33 @@ __global__ void __launch_bounds__(BLOCK, MIN_CTAS) k_shade_bounce(ShadeBuffers B
 	__shared__ __align__(16) unsigned s_count[2][8][kWarps]; // [round parity][class][warp]; the other parity is zeroed for the next round
 	__shared__ unsigned short s_order[BLOCK];             // regrouped position -> entry of the round
 	__shared__ int32_t s_tri[BLOCK];                    // regrouped position -> hit triangle
+	__shared__ int32_t s_mat[BLOCK];                    // regrouped position -> its material id
 	const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 	const unsigned lt_mask = (1u << lane) - 1u;
 	unsigned q0 = blockIdx.x * blockDim.x;
 	// two rounds of look-ahead: the hit index of round r+2 and the class byte of round r+1 are in flight while round r is shaded
 	int32_t tri_cur = -2, tri_n1 = -2;       // -2 = past the end of the queue
-	unsigned cls_cur = (unsigned)kClassNone;
+	unsigned cls_cur = (unsigned)kClassNone << 24; // class << 24 | material id, as in the table
 	if (REGROUP) {
 	if (rounds > 0) {
 		if (q0 + threadIdx.x < total) tri_cur = B.in_tri[q0 + threadIdx.x];
 		if (rounds > 1 && q0 + stride + threadIdx.x < total) tri_n1 = B.in_tri[q0 + stride + threadIdx.x];
-		cls_cur = tri_cur == -2 ? (unsigned)kClassNone : tri_cur == -1 ? (unsigned)kClassMiss : (unsigned)B.tri_class[tri_cur];
+		cls_cur = tri_cur == -2 ? (unsigned)kClassNone << 24 : tri_cur == -1 ? (unsigned)kClassMiss << 24 : B.tri_class[tri_cur];
 	}
 	if (threadIdx.x < 16u * kWarps) (&s_count[0][0][0])[threadIdx.x] = 0u;
 	__syncthreads();
 	}
 	for (unsigned r = 0; r < rounds; ++r, q0 += stride) {
 		unsigned q;
-		int32_t tri_idx;
+		int32_t tri_idx, mat_idx = -1;
 		if (REGROUP) {
 		const int32_t tri_mine = tri_cur;
-		const unsigned cls = cls_cur;
+		const unsigned cls = cls_cur >> 24;
+		const int32_t mat_mine = (cls_cur & 0x00ffffffu) != 0x00ffffffu ? (int32_t)(cls_cur & 0x00ffffffu) : -1;
 		{
 			const unsigned q2 = q0 + 2u * stride + threadIdx.x;
 			const int32_t tri_n2 = (r + 2 < rounds && q2 < total) ? B.in_tri[q2] : -2;
-			cls_cur = tri_n1 == -2 ? (unsigned)kClassNone : tri_n1 == -1 ? (unsigned)kClassMiss : (unsigned)B.tri_class[tri_n1];
+			cls_cur = tri_n1 == -2 ? (unsigned)kClassNone << 24 : tri_n1 == -1 ? (unsigned)kClassMiss << 24 : B.tri_class[tri_n1];
 			tri_cur = tri_n1;
 			tri_n1 = tri_n2;
 		}
@@ -524,10 +529,12 @@ __global__ void __launch_bounds__(BLOCK, MIN_CTAS) k_shade_bounce(ShadeBuffers B
 			const unsigned pos = __shfl_sync(kFullMask, base_c, (int)cls) + rank;
 			s_order[pos] = (unsigned short)threadIdx.x;
 			s_tri[pos] = tri_mine;
+			s_mat[pos] = mat_mine;
 		}
 		__syncthreads();
 		q = q0 + s_order[threadIdx.x];
 		tri_idx = s_tri[threadIdx.x];
+		mat_idx = s_mat[threadIdx.x];
 		} else { // TUNING VARIANT: every lane shades its own entry, no regrouping, no barriers
 			q = q0 + threadIdx.x;
 			tri_idx = q < total ? B.in_tri[q] : -2;
@@ -555,7 +562,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_CTAS) k_shade_bounce(ShadeBuffers B
 			} else {
 				const float2 uv = B.in_uv[q];
 				Surface sf;
-				fetch_surface(B, tri_idx, uv.x, uv.y, sf);
+				fetch_surface(B, tri_idx, uv.x, uv.y, sf, mat_idx);
 				origin = sf.origin;
 				add = color * sf.emissive; // :139
 				if (!last) {
