@@ -217,6 +217,22 @@ def test_c2_incoherent_rays(A, cpu, c2):
     assert torch.equal(again, d_tri)
     host = sc.trace_closest(rays[:500_000])
     assert np.array_equal(host["tri"], tri[:500_000]) and np.array_equal(bits(host["t"]), bits(t[:500_000]))
+    # a ray's result does not depend on its neighbours: all 8M rays in a random order give the same results, permuted (which
+    # warp and lane a ray lands in, who refills when, is scheduling only)
+    perm = torch.randperm(n, device="cuda", generator=torch.Generator(device="cuda").manual_seed(7))
+    p_rays = d_rays[perm].contiguous()
+    p_tri, p_t, p_uv = torch.empty_like(d_tri), torch.empty_like(d_t), torch.empty_like(d_uv)
+    sc.trace_closest(p_rays, p_tri, p_t, p_uv, stream=st)
+    torch.cuda.synchronize()
+    assert torch.equal(p_tri, d_tri[perm]) and torch.equal(p_t.view(torch.int32), d_t[perm].view(torch.int32))
+    assert torch.equal(p_uv.view(torch.int32), d_uv[perm].view(torch.int32))
+    # the structure-of-arrays entry the wavefront uses (origins and directions as two arrays) is the same kernel with another stride
+    for variant in (0, 9):  # product kernel; hit-mask table variant
+        sc.configure(0, 0, variant)
+        sc.trace_closest(d_rays[:1_000_000], again[:1_000_000], None, None, stream=st)
+        torch.cuda.synchronize()
+        assert torch.equal(again[:1_000_000], d_tri[:1_000_000]), variant
+    sc.configure(0, 0, 0)
 
 
 @pytest.mark.parametrize("seed", [1, 2, 3])
