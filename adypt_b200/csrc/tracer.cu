@@ -437,6 +437,70 @@ __global__ void __launch_bounds__(256, MIN_CTAS) k_shade_primary(ShadeBuffers B,
 
 enum { kClassMiss = 0, kClassDiffuse = 1, kClassGlossy = 2, kClassMirror = 3, kClassGlass = 4, kClassOther = 5, kClassNone = 7 };
 
+// One queue entry of bounce b: everything of Render's loop body after the intersection (pathtracer.glsl:130-201) and the hand-over
+// to the next queue. Called by all 32 lanes of a warp together (the queue appends are warp-collective); tri_idx == -2 = no entry.
+__device__ __forceinline__ void shade_queue_entry(const ShadeBuffers &B, const PTArgs &A, int b, float tmin, bool last, int dims, unsigned q,
+                                                  int32_t tri_idx, int32_t mat_idx)
+{
+	bool keep = false, conn = false;
+	V3 origin = v3(0, 0, 0), dir = v3(0, 0, 0), color = v3(0, 0, 0);
+	unsigned id = 0, bias_bits = 0;
+	if (tri_idx != -2) {
+		const float4 r1 = B.in_dir[q];
+		const float4 st = B.in_state[q];
+		dir = v3(r1.x, r1.y, r1.z);
+		id = __float_as_uint(r1.w);
+		color = v3(st.x, st.y, st.z);
+		bias_bits = __float_as_uint(st.w);
+		V3 add;
+		if (tri_idx == -1) { // :130-135
+			add = color * v3(A.sun[0], A.sun[1], A.sun[2]);
+			if (B.conn_rays != nullptr) {
+				conn = true; // the shadow ray starts where this segment started: the previous hit point
+				color = add;
+				const float4 r0 = B.in_org[q];
+				origin = v3(r0.x, r0.y, r0.z);
+				add = v3(0.f, 0.f, 0.f);
+			}
+		} else {
+			const float2 uv = B.in_uv[q];
+			Surface sf;
+			fetch_surface(B, tri_idx, uv.x, uv.y, sf, mat_idx);
+			origin = sf.origin;
+			add = color * sf.emissive; // :139
+			if (!last) {
+				const unsigned s = bias_bits >> 16; // the path's sample within the batch travels with its bias bytes (= id / npix)
+				const float fbx = __ldg(B.unorm8 + (bias_bits & 0xffu)), fby = __ldg(B.unorm8 + ((bias_bits >> 8) & 0xffu)); // byte / 255.0f
+				const float rx = fract(B.sobol[s * dims + 2 * b] + fbx);
+				const float ry = fract(B.sobol[s * dims + 2 * b + 1] + fby);
+				const float xi = A.rr_start >= 0 ? fract(B.sobol[s * dims + 2 * A.max_bounce + b] + fbx) : 0.0f;
+				keep = scatter(A, b, sf, rx, ry, xi, dir, color);
+			}
+		}
+		if (!adds_nothing(add)) {
+			float4 r4 = B.ret[id];
+			r4.x = r4.x + add.x;
+			r4.y = r4.y + add.y;
+			r4.z = r4.z + add.z;
+			B.ret[id] = r4;
+		}
+	}
+	const unsigned long long slot = queue_append(keep, B.out_count, A.zero);
+	if (keep) {
+		B.out_org[slot] = make_float4(origin.x, origin.y, origin.z, tmin);
+		B.out_dir[slot] = make_float4(dir.x, dir.y, dir.z, __uint_as_float(id));
+		B.out_state[slot] = make_float4(color.x, color.y, color.z, __uint_as_float(bias_bits));
+	}
+	if (B.conn_rays != nullptr) {
+		const unsigned long long cs = queue_append(conn, B.conn_count, A.zero);
+		if (conn) {
+			B.conn_rays[2 * cs] = make_float4(origin.x, origin.y, origin.z, tmin);
+			B.conn_rays[2 * cs + 1] = make_float4(B.sun_dir[0], B.sun_dir[1], B.sun_dir[2], __uint_as_float(id));
+			B.conn_color[cs] = make_float4(color.x, color.y, color.z, 0.0f);
+		}
+	}
+}
+
 // bounce b >= 1 over the current queue
 template <int MIN_CTAS, int BLOCK, bool REGROUP = true>
 __global__ void __launch_bounds__(BLOCK, MIN_CTAS) k_shade_bounce(ShadeBuffers B, PTArgs A, int b, float tmin)
@@ -539,62 +603,89 @@ __global__ void __launch_bounds__(BLOCK, MIN_CTAS) k_shade_bounce(ShadeBuffers B
 			q = q0 + threadIdx.x;
 			tri_idx = q < total ? B.in_tri[q] : -2;
 		}
-		bool keep = false, conn = false;
-		V3 origin = v3(0, 0, 0), dir = v3(0, 0, 0), color = v3(0, 0, 0);
-		unsigned id = 0, bias_bits = 0;
-		if (tri_idx != -2) {
-			const float4 r1 = B.in_dir[q];
-			const float4 st = B.in_state[q];
-			dir = v3(r1.x, r1.y, r1.z);
-			id = __float_as_uint(r1.w);
-			color = v3(st.x, st.y, st.z);
-			bias_bits = __float_as_uint(st.w);
-			V3 add;
-			if (tri_idx == -1) { // :130-135
-				add = color * v3(A.sun[0], A.sun[1], A.sun[2]);
-				if (B.conn_rays != nullptr) {
-					conn = true; // the shadow ray starts where this segment started: the previous hit point
-					color = add;
-					const float4 r0 = B.in_org[q];
-					origin = v3(r0.x, r0.y, r0.z);
-					add = v3(0.f, 0.f, 0.f);
-				}
-			} else {
-				const float2 uv = B.in_uv[q];
-				Surface sf;
-				fetch_surface(B, tri_idx, uv.x, uv.y, sf, mat_idx);
-				origin = sf.origin;
-				add = color * sf.emissive; // :139
-				if (!last) {
-					const unsigned s = bias_bits >> 16; // the path's sample within the batch travels with its bias bytes (= id / npix)
-					const float fbx = __ldg(B.unorm8 + (bias_bits & 0xffu)), fby = __ldg(B.unorm8 + ((bias_bits >> 8) & 0xffu)); // byte / 255.0f
-					const float rx = fract(B.sobol[s * dims + 2 * b] + fbx);
-					const float ry = fract(B.sobol[s * dims + 2 * b + 1] + fby);
-					const float xi = A.rr_start >= 0 ? fract(B.sobol[s * dims + 2 * A.max_bounce + b] + fbx) : 0.0f;
-					keep = scatter(A, b, sf, rx, ry, xi, dir, color);
-				}
-			}
-			if (!adds_nothing(add)) {
-				float4 r4 = B.ret[id];
-				r4.x = r4.x + add.x;
-				r4.y = r4.y + add.y;
-				r4.z = r4.z + add.z;
-				B.ret[id] = r4;
-			}
+		shade_queue_entry(B, A, b, tmin, last, dims, q, tri_idx, mat_idx);
+	}
+}
+
+// The same stage with EPT queue entries per thread and the warps of a block taking 32-entry chunks of the regrouped round
+// dynamically. With one entry per thread a block's warps end up with one class each -- a warp of misses is done long before a warp
+// of diffuse hits -- and a quarter of the stall samples sat at the round's first barrier (profiles/r2aa). Here a round is 128 * EPT
+// entries: per class a contiguous region (class totals by shared-memory atomics, then one reservation per warp-level group), 4 * EPT
+// chunks for 4 warps to share, and two barriers per 128 * EPT entries instead of per 128.
+template <int EPT, int BLOCK = 128>
+__global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) k_shade_bounce_multi(ShadeBuffers B, PTArgs A, int b, float tmin)
+{
+	constexpr unsigned kN = (unsigned)BLOCK * EPT;
+	const unsigned total = (unsigned)*B.in_count; // queue positions fit 32 bits (alloc_wavefront)
+	const unsigned stride = gridDim.x * kN;
+	const unsigned rounds = total / stride + (total % stride != 0u ? 1u : 0u);
+	const int dims = A.dims;
+	const bool last = b == A.max_bounce - 1;
+	if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(B.segments, (unsigned long long)total);
+	__shared__ unsigned s_total[2][8], s_fill[2][8], s_next[2];
+	__shared__ unsigned short s_order[2][kN];
+	__shared__ int32_t s_tri[2][kN], s_mat[2][kN];
+	const unsigned lane = threadIdx.x & 31u;
+	const unsigned lt_mask = (1u << lane) - 1u;
+	if (threadIdx.x < 16u) (&s_total[0][0])[threadIdx.x] = 0u;
+	else if (threadIdx.x < 32u) (&s_fill[0][0])[threadIdx.x - 16u] = 0u;
+	else if (threadIdx.x < 34u) s_next[threadIdx.x - 32u] = 0u;
+	__syncthreads();
+	unsigned q0 = blockIdx.x * kN;
+	for (unsigned r = 0; r < rounds; ++r, q0 += stride) {
+		const unsigned buf = r & 1u;
+		int32_t tri[EPT];
+		unsigned cw[EPT], rank[EPT];
+#pragma unroll
+		for (int k = 0; k < EPT; ++k) {
+			const unsigned q = q0 + (unsigned)k * (unsigned)BLOCK + threadIdx.x;
+			tri[k] = q < total ? B.in_tri[q] : -2;
 		}
-		const unsigned long long slot = queue_append(keep, B.out_count, A.zero);
-		if (keep) {
-			B.out_org[slot] = make_float4(origin.x, origin.y, origin.z, tmin);
-			B.out_dir[slot] = make_float4(dir.x, dir.y, dir.z, __uint_as_float(id));
-			B.out_state[slot] = make_float4(color.x, color.y, color.z, __uint_as_float(bias_bits));
+#pragma unroll
+		for (int k = 0; k < EPT; ++k)
+			cw[k] = tri[k] == -2 ? (unsigned)kClassNone << 24 : tri[k] == -1 ? (unsigned)kClassMiss << 24 : B.tri_class[tri[k]];
+#pragma unroll
+		for (int k = 0; k < EPT; ++k) {
+			const unsigned cls = cw[k] >> 24;
+			const unsigned same = __match_any_sync(kFullMask, cls);
+			rank[k] = (unsigned)__popc(same & lt_mask);
+			if (rank[k] == 0u) atomicAdd(&s_total[buf][cls], (unsigned)__popc(same));
 		}
-		if (B.conn_rays != nullptr) {
-			const unsigned long long cs = queue_append(conn, B.conn_count, A.zero);
-			if (conn) {
-				B.conn_rays[2 * cs] = make_float4(origin.x, origin.y, origin.z, tmin);
-				B.conn_rays[2 * cs + 1] = make_float4(B.sun_dir[0], B.sun_dir[1], B.sun_dir[2], __uint_as_float(id));
-				B.conn_color[cs] = make_float4(color.x, color.y, color.z, 0.0f);
+		__syncthreads();
+		{
+			const uint4 t0 = *reinterpret_cast<const uint4 *>(&s_total[buf][0]), t1 = *reinterpret_cast<const uint4 *>(&s_total[buf][4]);
+			const unsigned tot[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+#pragma unroll
+			for (int k = 0; k < EPT; ++k) {
+				const unsigned cls = cw[k] >> 24;
+				unsigned base = 0u;
+#pragma unroll
+				for (unsigned c = 0; c < 8u; ++c)
+					if (c < cls) base += tot[c];
+				const unsigned same = __match_any_sync(kFullMask, cls);
+				const unsigned leader = (unsigned)__ffs((int)same) - 1u;
+				unsigned off = 0u;
+				if (lane == leader) off = atomicAdd(&s_fill[buf][cls], (unsigned)__popc(same));
+				off = __shfl_sync(kFullMask, off, (int)leader);
+				const unsigned pos = base + off + rank[k];
+				s_order[buf][pos] = (unsigned short)((unsigned)k * (unsigned)BLOCK + threadIdx.x);
+				s_tri[buf][pos] = tri[k];
+				s_mat[buf][pos] = (cw[k] & 0x00ffffffu) != 0x00ffffffu ? (int32_t)(cw[k] & 0x00ffffffu) : -1;
 			}
+			// the other buffer's counters for the next round (everybody has left the previous round: they are all past the barrier above)
+			if (threadIdx.x < 8u) { s_total[buf ^ 1u][threadIdx.x] = 0u; s_fill[buf ^ 1u][threadIdx.x] = 0u; }
+			if (threadIdx.x == 8u) s_next[buf ^ 1u] = 0u;
+		}
+		__syncthreads();
+		const unsigned n_valid = q0 >= total ? 0u : (total - q0 < kN ? total - q0 : kN);
+		const unsigned n_chunks = (n_valid + 31u) / 32u;
+		for (;;) {
+			unsigned c = 0u;
+			if (lane == 0u) c = atomicAdd(&s_next[buf], 1u);
+			c = __shfl_sync(kFullMask, c, 0);
+			if (c >= n_chunks) break;
+			const unsigned p = c * 32u + lane;
+			shade_queue_entry(B, A, b, tmin, last, dims, q0 + s_order[buf][p], s_tri[buf][p], s_mat[buf][p]);
 		}
 	}
 }
@@ -756,7 +847,7 @@ struct adypt_tracer {
 	uint64_t host_segments = 0;  // primary segments (known on the host)
 	// measurement hooks (adypt_tracer_set_profiling): CUDA events around every stage launch, and / or the instrumented
 	// traversal kernel that counts the nodes and triangles the wavefront's rays touch. Off by default.
-	int bounce_ctas = 0;   // tuning (ADYPT_BOUNCE_CTAS): 4 = 256-thread blocks, four per SM; otherwise 128-thread blocks, eight per SM (default)
+	int bounce_ctas = 0;   // tuning (ADYPT_BOUNCE_CTAS): see the switch in run_batch; 0 = default (four entries per thread, dynamic chunks)
 	int primary_ctas = 0;  // tuning (ADYPT_PRIMARY_CTAS): CTAs per SM the bounce-0 kernel is compiled for (2, 3, 4); 0 = default
 	int primary_chunk = 0; // tuning (ADYPT_PRIMARY_CHUNK): samples of a group shaded per queue-slot request (1..8); 0 = default
 	int primary_group = 0; // tuning (ADYPT_PRIMARY_GROUP): samples of one pixel a thread of the bounce-0 stage shades; 0 = default
@@ -1040,12 +1131,22 @@ int run_batch(adypt_tracer *t, int first, int n, bool sum_mode)
 		B.out_count = t->d_counts + b + 1;
 		if (t->sun_visibility) B.conn_count = t->d_counts + t->conn_base + b;
 		StageTimer tb(t, ADYPT_STAGE_SHADE_BOUNCE);
-		// 128-thread blocks, eight per SM: smaller groups wait less on each other at the two barriers of a round (13.70 vs 14.17 ms per
-		// 64 spp of C3, profiles/r2g_bounce_block_sweep.log)
-		if (t->bounce_ctas == 1) k_shade_bounce<8, 128, false><<<2 * grid_for(total, 256, s->sm_count), 128, 0, t->stream>>>(B, A, b, c.ray_tmin); // no regrouping
-		else if (t->bounce_ctas == 16) k_shade_bounce<16, 64><<<4 * grid_for(total, 256, s->sm_count), 64, 0, t->stream>>>(B, A, b, c.ray_tmin); // regroups 64 entries
-		else if (t->bounce_ctas == 4) k_shade_bounce<4, 256><<<grid_for(total, 256, s->sm_count), 256, 0, t->stream>>>(B, A, b, c.ray_tmin);
-		else k_shade_bounce<8, 128><<<2 * grid_for(total, 256, s->sm_count), 128, 0, t->stream>>>(B, A, b, c.ray_tmin);
+		// Default: 128-thread blocks, eight per SM, FOUR queue entries per thread with the block's warps taking the regrouped round's
+		// 32-entry chunks dynamically (k_shade_bounce_multi): 10.2 ms per 64 spp of C3. One entry per thread (k_shade_bounce): 12.1 ms with
+		// 128-thread blocks, 14.2 with 256, 14.5 with 64, 14.7 without regrouping (profiles/r2g, r2k, r2t, r2ad logs). The alternatives stay
+		// selectable for A/B runs (ADYPT_BOUNCE_CTAS).
+		switch (t->bounce_ctas) {
+		case 1: k_shade_bounce<8, 128, false><<<2 * grid_for(total, 256, s->sm_count), 128, 0, t->stream>>>(B, A, b, c.ray_tmin); break; // no regrouping
+		case 4: k_shade_bounce<4, 256><<<grid_for(total, 256, s->sm_count), 256, 0, t->stream>>>(B, A, b, c.ray_tmin); break;
+		case 8: k_shade_bounce<8, 128><<<2 * grid_for(total, 256, s->sm_count), 128, 0, t->stream>>>(B, A, b, c.ray_tmin); break;
+		case 16: k_shade_bounce<16, 64><<<4 * grid_for(total, 256, s->sm_count), 64, 0, t->stream>>>(B, A, b, c.ray_tmin); break;
+		case 22: k_shade_bounce_multi<2><<<grid_for(total, 256, s->sm_count), 128, 0, t->stream>>>(B, A, b, c.ray_tmin); break;
+		case 26: k_shade_bounce_multi<6><<<grid_for(total, 768, s->sm_count), 128, 0, t->stream>>>(B, A, b, c.ray_tmin); break;
+		case 32: k_shade_bounce_multi<2, 256><<<grid_for(total, 512, s->sm_count), 256, 0, t->stream>>>(B, A, b, c.ray_tmin); break;
+		case 34: k_shade_bounce_multi<4, 256><<<grid_for(total, 1024, s->sm_count), 256, 0, t->stream>>>(B, A, b, c.ray_tmin); break;
+		case 28: k_shade_bounce_multi<8><<<grid_for(total, 1024, s->sm_count), 128, 0, t->stream>>>(B, A, b, c.ray_tmin); break;
+		default: k_shade_bounce_multi<4><<<grid_for(total, 512, s->sm_count), 128, 0, t->stream>>>(B, A, b, c.ray_tmin); break;
+		}
 		count_launch();
 		ADYPT_CUDA(cudaGetLastError());
 		tb.end();
