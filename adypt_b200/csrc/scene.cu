@@ -486,9 +486,22 @@ static int trace_host(adypt_scene *s, const float *rays, uint64_t n, int32_t *tr
 		const long v = e ? atol(e) : 0;
 		return v >= 1024 ? (uint64_t)v : (uint64_t)(1u << 19);
 	}();
+	// The call's time is the upload's plus what cannot overlap it: the first chunk's upload (nothing to trace or download yet) and
+	// the last chunk's traversal and download (nothing left to upload). So the first and last chunks are short -- 1/8, 1/4, 1/2 of a
+	// full chunk on the way in, the same on the way out -- when the batch is long enough to have a steady state in between.
+	static const bool ramp = []() { const char *e = getenv("ADYPT_HOST_RAMP"); return !e || atoi(e) != 0; }();
+	const uint64_t ramp_rays = ramp ? ((chunk >> 3) + (chunk >> 2) + (chunk >> 1)) : 0; // one side
+	const bool ramped = ramp && (chunk >> 3) >= 1024 && n >= 2 * ramp_rays + 2 * chunk;
 	int k = 0;
-	for (uint64_t b = 0; b < n; b += chunk, ++k) {
-		const uint64_t m = (n - b < chunk) ? n - b : chunk;
+	for (uint64_t b = 0; b < n; ++k) {
+		uint64_t m = chunk;
+		if (ramped) {
+			const uint64_t left = n - b;
+			if (k < 3) m = chunk >> (3 - k);
+			else if (left <= ramp_rays) m = left > (chunk >> 1) + (chunk >> 3) ? chunk >> 1 : left > (chunk >> 3) ? chunk >> 2 : left;
+			else if (left - ramp_rays < chunk) m = left - ramp_rays; // the steady state's short last chunk
+		}
+		if (m > n - b) m = n - b;
 		cudaStream_t st = s->pipe[k % 3];
 		unsigned long long *ctr = s->d_counters + kCounterPipe + (k % 3); // owned by that stream
 		float4 *d_in = s->stage_in.as<float4>() + 2 * b;
@@ -505,6 +518,7 @@ static int trace_host(adypt_scene *s, const float *rays, uint64_t n, int32_t *tr
 			if (t) ADYPT_CUDA(cudaMemcpyAsync(t + b, d_t, (size_t)m * 4u, cudaMemcpyDeviceToHost, st));
 			if (uv) ADYPT_CUDA(cudaMemcpyAsync(uv + 2 * b, d_uv, (size_t)m * 8u, cudaMemcpyDeviceToHost, st));
 		}
+		b += m;
 	}
 	for (int i = 0; i < 3; ++i) ADYPT_CUDA(cudaStreamSynchronize(s->pipe[i]));
 	return ADYPT_OK;

@@ -336,6 +336,95 @@ __device__ __forceinline__ unsigned long long queue_append(bool keep, unsigned l
 // runs per sample, and the queue slots of several samples are requested with one atomic per warp. Path id = s * npix + pixel.
 constexpr int kMaxPrimaryChunk = 8;
 
+// One item of bounce 0: pixel (item % npix), samples [(item / npix) * group, ... + group) of the batch. Called by all 32 lanes of a warp
+// together (uniform trip counts, warp-collective queue appends). known_tri != -3: the caller has already read the pixel's cached primary
+// hit (and, known_mat >= 0, its material id).
+__device__ __forceinline__ void shade_primary_item(const ShadeBuffers &B, const PTArgs &A, const CameraArgs &cam, int group, int chunk, unsigned npix,
+                                                   unsigned long long items, unsigned long long item, float bx, float by, int dims, V3 sun, bool last,
+                                                   unsigned lane, int32_t known_tri, int32_t known_mat)
+{
+	const bool live = item < items;
+	const unsigned pix = live ? (unsigned)(item % npix) : 0u;
+	const int s_first = live ? (int)(item / npix) * group : 0;
+	V3 dir0 = v3(0, 0, 0), ret0 = v3(0.f, 0.f, 0.f);
+	Surface sf;
+	sf.illum = 0;
+	sf.origin = v3(0, 0, 0);
+	bool hit = false;
+	float fbx = 0.f, fby = 0.f;
+	unsigned bias_bits = 0u;
+	if (live) {
+		dir0 = camera_dir(cam, A.width, A.height, (int)(pix % (unsigned)A.width), (int)(pix / (unsigned)A.width), bx, by);
+		const uchar2 bb = B.bias[pix];
+		fbx = (float)bb.x / 255.0f;
+		fby = (float)bb.y / 255.0f;
+		bias_bits = (unsigned)bb.x | ((unsigned)bb.y << 8);
+		const int32_t tri = known_tri != -3 ? known_tri : B.prim_tri[pix];
+		hit = tri != -1;
+		if (hit) {
+			const float2 uv = B.prim_uv[pix];
+			fetch_surface(B, tri, uv.x, uv.y, sf, known_mat);
+			ret0 = ret0 + v3(1.f, 1.f, 1.f) * sf.emissive; // :139 with color = 1, ret = 0
+		} else if (B.conn_rays == nullptr)
+			ret0 = ret0 + v3(1.f, 1.f, 1.f) * sun; // :130-135
+	}
+	// The group's samples in chunks: every sample of a chunk is shaded first and parked (two float4 per sample in local
+	// memory), then the warp asks for the chunk's queue slots with ONE atomic and writes the survivors out. One atomic per
+	// warp and SAMPLE put a million same-address atomics into every launch -- about what the L2 retires in the kernel's
+	// whole run time (the kernel sat at its slot requests: 47 % of the stall samples, profiles/r2l_shade_primary_*).
+	for (int k0 = 0; k0 < group; k0 += chunk) {
+		float4 c_dir[kMaxPrimaryChunk], c_col[kMaxPrimaryChunk]; // dir + path id; colour + slot offset inside the warp's claim
+		unsigned kept = 0u, total = 0u;
+		for (int j = 0; j < chunk; ++j) {
+			const int sidx = s_first + k0 + j;
+			const bool have = live && k0 + j < group && sidx < A.n_samples;
+			bool keep = false, conn = false;
+			V3 dir = dir0, color = v3(1.f, 1.f, 1.f);
+			const unsigned id = (unsigned)sidx * npix + pix;
+			if (have) {
+				B.ret[id] = make_float4(ret0.x, ret0.y, ret0.z, 0.0f);
+				if (!hit) {
+					conn = B.conn_rays != nullptr; // the shadow ray starts at the camera
+					color = color * sun;
+				} else if (!last) {
+					const float rx = fract(B.sobol[sidx * dims + 0] + fbx);
+					const float ry = fract(B.sobol[sidx * dims + 1] + fby);
+					const float xi = A.rr_start >= 0 ? fract(B.sobol[sidx * dims + 2 * A.max_bounce] + fbx) : 0.0f;
+					keep = scatter(A, 0, sf, rx, ry, xi, dir, color);
+				}
+			}
+			if (B.conn_rays != nullptr) {
+				const unsigned long long cs = queue_append(conn, B.conn_count, A.zero);
+				if (conn) {
+					B.conn_rays[2 * cs] = make_float4(cam.origin[0], cam.origin[1], cam.origin[2], cam.tmin);
+					B.conn_rays[2 * cs + 1] = make_float4(B.sun_dir[0], B.sun_dir[1], B.sun_dir[2], __uint_as_float(id));
+					B.conn_color[cs] = make_float4(color.x, color.y, color.z, 0.0f);
+				}
+			}
+			const unsigned m = __ballot_sync(kFullMask, keep);
+			if (keep) {
+				kept |= 1u << j;
+				c_dir[j] = make_float4(dir.x, dir.y, dir.z, __uint_as_float(id));
+				c_col[j] = make_float4(color.x, color.y, color.z, __uint_as_float(total + (unsigned)__popc(m & ((1u << lane) - 1u))));
+			}
+			total += (unsigned)__popc(m);
+		}
+		if (total != 0u) { // warp-uniform
+			unsigned long long base = 0;
+			if (lane == 0u) base = atom_add_u64(B.out_count, (unsigned long long)total, lane & A.zero);
+			base = __shfl_sync(kFullMask, base, 0);
+			for (int j = 0; j < chunk; ++j)
+				if ((kept >> j) & 1u) {
+					const float4 d4 = c_dir[j], c4 = c_col[j];
+					const unsigned long long slot = base + (unsigned long long)__float_as_uint(c4.w);
+					B.out_org[slot] = make_float4(sf.origin.x, sf.origin.y, sf.origin.z, cam.tmin);
+					B.out_dir[slot] = d4;
+					B.out_state[slot] = make_float4(c4.x, c4.y, c4.z, __uint_as_float(bias_bits | ((unsigned)(s_first + k0 + j) << 16)));
+				}
+		}
+	}
+}
+
 template <int MIN_CTAS>
 __global__ void __launch_bounds__(256, MIN_CTAS) k_shade_primary(ShadeBuffers B, PTArgs A, CameraArgs cam, int group, int chunk)
 {
@@ -352,86 +441,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) k_shade_primary(ShadeBuffers B,
 	const bool last = A.max_bounce == 1; // the loop of Render ends after this segment
 	for (unsigned long long r = 0; r < rounds; ++r) {
 		const unsigned long long item = r * stride + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-		const bool live = item < items;
-		const unsigned pix = live ? (unsigned)(item % npix) : 0u;
-		const int s_first = live ? (int)(item / npix) * group : 0;
-		V3 dir0 = v3(0, 0, 0), ret0 = v3(0.f, 0.f, 0.f);
-		Surface sf;
-		sf.illum = 0;
-		sf.origin = v3(0, 0, 0);
-		bool hit = false;
-		float fbx = 0.f, fby = 0.f;
-		unsigned bias_bits = 0u;
-		if (live) {
-			dir0 = camera_dir(cam, A.width, A.height, (int)(pix % (unsigned)A.width), (int)(pix / (unsigned)A.width), bx, by);
-			const uchar2 bb = B.bias[pix];
-			fbx = (float)bb.x / 255.0f;
-			fby = (float)bb.y / 255.0f;
-			bias_bits = (unsigned)bb.x | ((unsigned)bb.y << 8);
-			const int32_t tri = B.prim_tri[pix];
-			hit = tri != -1;
-			if (hit) {
-				const float2 uv = B.prim_uv[pix];
-				fetch_surface(B, tri, uv.x, uv.y, sf);
-				ret0 = ret0 + v3(1.f, 1.f, 1.f) * sf.emissive; // :139 with color = 1, ret = 0
-			} else if (B.conn_rays == nullptr)
-				ret0 = ret0 + v3(1.f, 1.f, 1.f) * sun; // :130-135
-		}
-		// The group's samples in chunks: every sample of a chunk is shaded first and parked (two float4 per sample in local
-		// memory), then the warp asks for the chunk's queue slots with ONE atomic and writes the survivors out. One atomic per
-		// warp and SAMPLE put a million same-address atomics into every launch -- about what the L2 retires in the kernel's
-		// whole run time (the kernel sat at its slot requests: 47 % of the stall samples, profiles/r2l_shade_primary_*).
-		for (int k0 = 0; k0 < group; k0 += chunk) {
-			float4 c_dir[kMaxPrimaryChunk], c_col[kMaxPrimaryChunk]; // dir + path id; colour + slot offset inside the warp's claim
-			unsigned kept = 0u, total = 0u;
-			for (int j = 0; j < chunk; ++j) {
-				const int sidx = s_first + k0 + j;
-				const bool have = live && k0 + j < group && sidx < A.n_samples;
-				bool keep = false, conn = false;
-				V3 dir = dir0, color = v3(1.f, 1.f, 1.f);
-				const unsigned id = (unsigned)sidx * npix + pix;
-				if (have) {
-					B.ret[id] = make_float4(ret0.x, ret0.y, ret0.z, 0.0f);
-					if (!hit) {
-						conn = B.conn_rays != nullptr; // the shadow ray starts at the camera
-						color = color * sun;
-					} else if (!last) {
-						const float rx = fract(B.sobol[sidx * dims + 0] + fbx);
-						const float ry = fract(B.sobol[sidx * dims + 1] + fby);
-						const float xi = A.rr_start >= 0 ? fract(B.sobol[sidx * dims + 2 * A.max_bounce] + fbx) : 0.0f;
-						keep = scatter(A, 0, sf, rx, ry, xi, dir, color);
-					}
-				}
-				if (B.conn_rays != nullptr) {
-					const unsigned long long cs = queue_append(conn, B.conn_count, A.zero);
-					if (conn) {
-						B.conn_rays[2 * cs] = make_float4(cam.origin[0], cam.origin[1], cam.origin[2], cam.tmin);
-						B.conn_rays[2 * cs + 1] = make_float4(B.sun_dir[0], B.sun_dir[1], B.sun_dir[2], __uint_as_float(id));
-						B.conn_color[cs] = make_float4(color.x, color.y, color.z, 0.0f);
-					}
-				}
-				const unsigned m = __ballot_sync(kFullMask, keep);
-				if (keep) {
-					kept |= 1u << j;
-					c_dir[j] = make_float4(dir.x, dir.y, dir.z, __uint_as_float(id));
-					c_col[j] = make_float4(color.x, color.y, color.z, __uint_as_float(total + (unsigned)__popc(m & ((1u << lane) - 1u))));
-				}
-				total += (unsigned)__popc(m);
-			}
-			if (total != 0u) { // warp-uniform
-				unsigned long long base = 0;
-				if (lane == 0u) base = atom_add_u64(B.out_count, (unsigned long long)total, lane & A.zero);
-				base = __shfl_sync(kFullMask, base, 0);
-				for (int j = 0; j < chunk; ++j)
-					if ((kept >> j) & 1u) {
-						const float4 d4 = c_dir[j], c4 = c_col[j];
-						const unsigned long long slot = base + (unsigned long long)__float_as_uint(c4.w);
-						B.out_org[slot] = make_float4(sf.origin.x, sf.origin.y, sf.origin.z, cam.tmin);
-						B.out_dir[slot] = d4;
-						B.out_state[slot] = make_float4(c4.x, c4.y, c4.z, __uint_as_float(bias_bits | ((unsigned)(s_first + k0 + j) << 16)));
-					}
-			}
-		}
+		shade_primary_item(B, A, cam, group, chunk, npix, items, item, bx, by, dims, sun, last, lane, -3, -1);
 	}
 }
 
@@ -690,6 +700,92 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) k_shade_bounce_multi(Shad
 	}
 }
 
+// Bounce 0 with the block's items regrouped by the class of the cached primary hit, like k_shade_bounce_multi: 128 threads sort 128 * EPT
+// items (pixel, sample group) so that a warp's lanes run the same branch for their 16 samples (21.5 of 32 lanes active unsorted: a
+// warp of neighbouring pixels mixes sky, walls and lamps), and take the sorted 32-item chunks dynamically.
+template <int EPT>
+__global__ void __launch_bounds__(128, 8) k_shade_primary_sorted(ShadeBuffers B, PTArgs A, CameraArgs cam, int group, int chunk)
+{
+	constexpr unsigned kN = 128u * EPT;
+	const unsigned npix = (unsigned)A.width * (unsigned)A.height;
+	const unsigned n_groups = ((unsigned)A.n_samples + (unsigned)group - 1u) / (unsigned)group;
+	const unsigned long long items = (unsigned long long)npix * n_groups;
+	const unsigned long long stride = (unsigned long long)gridDim.x * kN;
+	const unsigned long long rounds = (items + stride - 1u) / stride;
+	const unsigned lane = threadIdx.x & 31u;
+	const unsigned lt_mask = (1u << lane) - 1u;
+	float bx, by;
+	subpixel_bias(A.subpixel, A.tmp_lifetime, A.first_spp, &bx, &by);
+	const int dims = A.dims;
+	const V3 sun = v3(A.sun[0], A.sun[1], A.sun[2]);
+	const bool last = A.max_bounce == 1;
+	__shared__ unsigned s_total[2][8], s_fill[2][8], s_next[2];
+	__shared__ unsigned short s_order[2][kN];
+	__shared__ int32_t s_tri[2][kN], s_mat[2][kN];
+	if (threadIdx.x < 16u) (&s_total[0][0])[threadIdx.x] = 0u;
+	else if (threadIdx.x < 32u) (&s_fill[0][0])[threadIdx.x - 16u] = 0u;
+	else if (threadIdx.x < 34u) s_next[threadIdx.x - 32u] = 0u;
+	__syncthreads();
+	unsigned long long i0 = (unsigned long long)blockIdx.x * kN;
+	for (unsigned long long r = 0; r < rounds; ++r, i0 += stride) {
+		const unsigned buf = (unsigned)(r & 1u);
+		int32_t tri[EPT];
+		unsigned cw[EPT], rank[EPT];
+#pragma unroll
+		for (int k = 0; k < EPT; ++k) {
+			const unsigned long long item = i0 + (unsigned)k * 128u + threadIdx.x;
+			tri[k] = item < items ? B.prim_tri[(unsigned)(item % npix)] : -2;
+		}
+#pragma unroll
+		for (int k = 0; k < EPT; ++k)
+			cw[k] = tri[k] == -2 ? (unsigned)kClassNone << 24 : tri[k] == -1 ? (unsigned)kClassMiss << 24 : B.tri_class[tri[k]];
+#pragma unroll
+		for (int k = 0; k < EPT; ++k) {
+			const unsigned cls = cw[k] >> 24;
+			const unsigned same = __match_any_sync(kFullMask, cls);
+			rank[k] = (unsigned)__popc(same & lt_mask);
+			if (rank[k] == 0u) atomicAdd(&s_total[buf][cls], (unsigned)__popc(same));
+		}
+		__syncthreads();
+		{
+			const uint4 t0 = *reinterpret_cast<const uint4 *>(&s_total[buf][0]), t1 = *reinterpret_cast<const uint4 *>(&s_total[buf][4]);
+			const unsigned tot[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+#pragma unroll
+			for (int k = 0; k < EPT; ++k) {
+				const unsigned cls = cw[k] >> 24;
+				unsigned base = 0u;
+#pragma unroll
+				for (unsigned c = 0; c < 8u; ++c)
+					if (c < cls) base += tot[c];
+				const unsigned same = __match_any_sync(kFullMask, cls);
+				const unsigned leader = (unsigned)__ffs((int)same) - 1u;
+				unsigned off = 0u;
+				if (lane == leader) off = atomicAdd(&s_fill[buf][cls], (unsigned)__popc(same));
+				off = __shfl_sync(kFullMask, off, (int)leader);
+				const unsigned pos = base + off + rank[k];
+				s_order[buf][pos] = (unsigned short)((unsigned)k * 128u + threadIdx.x);
+				s_tri[buf][pos] = tri[k];
+				s_mat[buf][pos] = (cw[k] & 0x00ffffffu) != 0x00ffffffu ? (int32_t)(cw[k] & 0x00ffffffu) : -1;
+			}
+			if (threadIdx.x < 8u) { s_total[buf ^ 1u][threadIdx.x] = 0u; s_fill[buf ^ 1u][threadIdx.x] = 0u; }
+			if (threadIdx.x == 8u) s_next[buf ^ 1u] = 0u;
+		}
+		__syncthreads();
+		const unsigned n_valid = i0 >= items ? 0u : (items - i0 < (unsigned long long)kN ? (unsigned)(items - i0) : kN);
+		const unsigned n_chunks = (n_valid + 31u) / 32u;
+		for (;;) {
+			unsigned c = 0u;
+			if (lane == 0u) c = atomicAdd(&s_next[buf], 1u);
+			c = __shfl_sync(kFullMask, c, 0);
+			if (c >= n_chunks) break;
+			const unsigned p = c * 32u + lane;
+			const int32_t t = s_tri[buf][p];
+			// entries past the end of the item list (t == -2) sit at the end of the sorted round: an item number >= items switches the lane off
+			shade_primary_item(B, A, cam, group, chunk, npix, items, t == -2 ? items : i0 + s_order[buf][p], bx, by, dims, sun, last, lane, t == -2 ? -3 : t, s_mat[buf][p]);
+		}
+	}
+}
+
 // connect: ret += colour * sun for every escaped path whose shadow ray reached the sun (occ == 0)
 __global__ void k_connect_apply(const float4 *__restrict__ conn_rays, const uint8_t *__restrict__ occ, const unsigned long long *count,
                                 const float4 *__restrict__ conn_color, float4 *__restrict__ ret)
@@ -848,7 +944,7 @@ struct adypt_tracer {
 	// measurement hooks (adypt_tracer_set_profiling): CUDA events around every stage launch, and / or the instrumented
 	// traversal kernel that counts the nodes and triangles the wavefront's rays touch. Off by default.
 	int bounce_ctas = 0;   // tuning (ADYPT_BOUNCE_CTAS): see the switch in run_batch; 0 = default (four entries per thread, dynamic chunks)
-	int primary_ctas = 0;  // tuning (ADYPT_PRIMARY_CTAS): CTAs per SM the bounce-0 kernel is compiled for (2, 3, 4); 0 = default
+	int primary_ctas = 0;  // tuning (ADYPT_PRIMARY_CTAS): bounce-0 kernel: 2 / 3 / 4 = unsorted at that many CTAs per SM, 22 = class-sorted 2 items per thread; 0 = default (class-sorted, 4 per thread)
 	int primary_chunk = 0; // tuning (ADYPT_PRIMARY_CHUNK): samples of a group shaded per queue-slot request (1..8); 0 = default
 	int primary_group = 0; // tuning (ADYPT_PRIMARY_GROUP): samples of one pixel a thread of the bounce-0 stage shades; 0 = default
 	int profiling = 0;
@@ -1104,10 +1200,12 @@ int run_batch(adypt_tracer *t, int first, int n, bool sum_mode)
 		const unsigned long long items = (unsigned long long)t->npix * (unsigned long long)((n + group - 1) / group);
 		const int g = grid_for(items, 256, s->sm_count);
 		const int chunk = t->primary_chunk > 0 && t->primary_chunk <= kMaxPrimaryChunk ? t->primary_chunk : 4; // samples per queue-slot request
-		switch (t->primary_ctas) { // registers per thread: 64 / 80 / 120 (tuning; same results; profiles/r2u_primary_chunk_sweep.log)
-		case 3: k_shade_primary<3><<<g, 256, 0, t->stream>>>(B, A, t->cam, group, chunk); break;
-		case 2: k_shade_primary<2><<<g, 256, 0, t->stream>>>(B, A, t->cam, group, chunk); break;
-		default: k_shade_primary<4><<<g, 256, 0, t->stream>>>(B, A, t->cam, group, chunk); break;
+		switch (t->primary_ctas) { // tuning, same results: profiles/r2u_primary_chunk_sweep.log, profiles/r2ah_primary_sorted.log
+		case 2: k_shade_primary<2><<<g, 256, 0, t->stream>>>(B, A, t->cam, group, chunk); break; // unsorted, 120 registers
+		case 3: k_shade_primary<3><<<g, 256, 0, t->stream>>>(B, A, t->cam, group, chunk); break; // unsorted, 80 registers
+		case 4: k_shade_primary<4><<<g, 256, 0, t->stream>>>(B, A, t->cam, group, chunk); break; // unsorted, 64 registers
+		case 22: k_shade_primary_sorted<2><<<grid_for(items, 256, s->sm_count), 128, 0, t->stream>>>(B, A, t->cam, group, chunk); break;
+		default: k_shade_primary_sorted<4><<<grid_for(items, 512, s->sm_count), 128, 0, t->stream>>>(B, A, t->cam, group, chunk); break; // items regrouped by class, 4 per thread
 		}
 		count_launch();
 		ADYPT_CUDA(cudaGetLastError());

@@ -412,7 +412,7 @@ def run_native(args, rank, world, local_rank):
     del d_in, d_out, h_out
     chunk = int(os.environ.get("ADYPT_HOST_CHUNK", "0")) or (1 << 19)
     e2e = {"value": world * n / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(n * 32), "d2h_bytes_per_step": int(n * 16),
-           "how": f"adypt_trace_closest(ADYPT_MEM_HOST) on pinned host arrays ({chunk}-ray chunks pipelined over 3 streams: H2D, traversal, D2H overlap), "
+           "how": f"adypt_trace_closest(ADYPT_MEM_HOST) on pinned host arrays ({chunk}-ray chunks, shorter first and last ones, pipelined over 3 streams: H2D, traversal, D2H overlap), "
                   "wall clock around K blocking calls, max over ranks",
            "copy_only": {"value": world * n / copy_s / 1e6, "unit": UNIT, "GBps_aggregate": world * n * 48 / copy_s / 1e9,
                          "how": "the same 256 MB up + 128 MB down per rank and step as plain pinned cudaMemcpyAsync on two streams, all ranks at once, no kernels: "

@@ -83,6 +83,33 @@ def test_empty_and_ragged_batches(A, cpu):
     assert r["t"] is None and r["uv"] is None and np.array_equal(r["tri"], o["tri"][:100])
 
 
+def test_host_array_call_equals_device_call_across_its_chunk_schedule(A):
+    """The host-array call cuts the batch into chunks with short first and last ones (scene.cu trace_host); sizes around the point
+    where that schedule switches on, and odd ones that put chunk boundaries at odd ray indices, against ONE device launch."""
+    import torch
+    g = load_golden("city12")
+    sc = A.Scene(g.nodes, g.tri_indices, g.woop)
+    base = g.extra["rays"]
+    n_max = 2 * (1 << 21) + 12345
+    rays = np.ascontiguousarray(np.tile(base, ((n_max + base.shape[0] - 1) // base.shape[0], 1))[:n_max])
+    rays[:, 0:3] += (np.arange(n_max, dtype=np.float32)[:, None] % 7.0) * np.float32(1e-3)  # not just copies of the fixture's rays
+    d_rays = torch.from_numpy(rays).cuda()
+    d_tri = torch.empty(n_max, dtype=torch.int32, device="cuda")
+    d_t = torch.empty(n_max, dtype=torch.float32, device="cuda")
+    d_uv = torch.empty((n_max, 2), dtype=torch.float32, device="cuda")
+    sc.trace_closest(d_rays, d_tri, d_t, d_uv)
+    d_occ = torch.empty(n_max, dtype=torch.uint8, device="cuda")
+    sc.trace_any(d_rays, d_occ)
+    torch.cuda.synchronize()
+    ref = {"tri": d_tri.cpu().numpy(), "t": d_t.cpu().numpy(), "uv": d_uv.cpu().numpy()}
+    occ = d_occ.cpu().numpy()
+    for n in (1966079, 1966080, 1966081, (1 << 21) - 1, 3000001, n_max):
+        r = sc.trace_closest(rays[:n])
+        assert np.array_equal(r["tri"], ref["tri"][:n]), n
+        assert np.array_equal(bits(r["t"]), bits(ref["t"][:n])) and np.array_equal(bits(r["uv"]), bits(ref["uv"][:n])), n
+        assert np.array_equal(sc.trace_any(rays[:n]), occ[:n]), n
+
+
 def test_scheduling_knobs_do_not_change_results(A, cpu):
     """Refill threshold / CTAs per SM only change scheduling; per-ray results are invariant, as is any
     permutation of the ray buffer."""

@@ -34,5 +34,6 @@ def test_traversal_kernels_fit_eight_ctas_per_sm():
         f = {k: int(v) for k, v in re.findall(r"([A-Z]+):(\d+)", u)}
         if "k_shade_bounce" in n:  # 128 threads x 8 CTAs (or 256 x 4) per SM; a handful of spilled values at most
             assert f["REG"] <= 64 and f["STACK"] <= 64, (n, f)
-        if "k_shade_primaryILi4E" in n:  # the default bounce-0 build: 256 threads x 4 CTAs per SM; its local memory is the
-            assert f["REG"] <= 64 and f["STACK"] <= 384, (n, f)  # parked chunk (8 x 2 float4) + a few spilled values
+        if "k_shade_primaryILi4E" in n or "k_shade_primary_sorted" in n:  # bounce 0 (default: class-sorted, 128 threads x 8 CTAs per
+            assert f["REG"] <= 64 and f["STACK"] <= 384, (n, f)  # SM): local memory = the parked chunk (8 x 2 float4) + a few spills
+            assert f["SHARED"] <= 12288, (n, f)                   # 8 CTAs x 12 KB of sort buffers fit beside the L1
