@@ -43,6 +43,7 @@ struct PTArgs { // uuPT (pathtracer.glsl:34-38) + batch bookkeeping
 	int32_t dims;      // Sobol dimensions per sample: 2*max_bounce, +max_bounce roulette draws when rr_start >= 0
 	int32_t rr_start;  // >= 0: Russian roulette from this bounce on (opt-in extension, -1 = the reference's behaviour)
 	uint32_t zero;     // always 0, but only known at run time: lets a kernel tie an instruction's operand to a value it must wait for
+	uint32_t early_slots; // tuning (ADYPT_EARLY_SLOTS): entries whose class always goes on ask for their queue slot before the gathers
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -449,9 +450,14 @@ enum { kClassMiss = 0, kClassDiffuse = 1, kClassGlossy = 2, kClassMirror = 3, kC
 
 // One queue entry of bounce b: everything of Render's loop body after the intersection (pathtracer.glsl:130-201) and the hand-over
 // to the next queue. Called by all 32 lanes of a warp together (the queue appends are warp-collective); tri_idx == -2 = no entry.
+// sure_base != nullptr: the caller knows from the entry's class that the path goes on (diffuse, mirror, dielectric, pass-through; not the
+// last bounce, no Russian roulette) and its block has reserved the slots of all such entries of the round with ONE atomic: the entry's slot
+// is *sure_base + sure_idx (*sure_base is kNoBase until the reservation has come back).
+constexpr unsigned kNoBase = 0xffffffffu;
 __device__ __forceinline__ void shade_queue_entry(const ShadeBuffers &B, const PTArgs &A, int b, float tmin, bool last, int dims, unsigned q,
-                                                  int32_t tri_idx, int32_t mat_idx)
+                                                  int32_t tri_idx, int32_t mat_idx, const volatile unsigned *sure_base = nullptr, unsigned sure_idx = 0u)
 {
+	const bool sure = sure_base != nullptr;
 	bool keep = false, conn = false;
 	V3 origin = v3(0, 0, 0), dir = v3(0, 0, 0), color = v3(0, 0, 0);
 	unsigned id = 0, bias_bits = 0;
@@ -495,7 +501,12 @@ __device__ __forceinline__ void shade_queue_entry(const ShadeBuffers &B, const P
 			B.ret[id] = r4;
 		}
 	}
-	const unsigned long long slot = queue_append(keep, B.out_count, A.zero);
+	unsigned long long slot = queue_append(keep && !sure, B.out_count, A.zero);
+	if (sure) {
+		unsigned base;
+		while ((base = *sure_base) == kNoBase) {}
+		slot = base + sure_idx; // queue positions fit 32 bits (alloc_wavefront)
+	}
 	if (keep) {
 		B.out_org[slot] = make_float4(origin.x, origin.y, origin.z, tmin);
 		B.out_dir[slot] = make_float4(dir.x, dir.y, dir.z, __uint_as_float(id));
@@ -631,8 +642,13 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) k_shade_bounce_multi(Shad
 	const unsigned rounds = total / stride + (total % stride != 0u ? 1u : 0u);
 	const int dims = A.dims;
 	const bool last = b == A.max_bounce - 1;
+	// Entries of a class that always goes on get their slots in the next queue from ONE reservation per block and round (their number is
+	// known once the round's class totals are). One request per 32-entry chunk is 0.85 M atomics on one address in a 27 M-segment launch,
+	// about as many as the L2 retires in the kernel's whole run time (the same limit bounce 0 ran into, shade_primary_item).
+	const bool block_slots = !last && A.rr_start < 0 && A.early_slots != 0;
 	if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(B.segments, (unsigned long long)total);
 	__shared__ unsigned s_total[2][8], s_fill[2][8], s_next[2];
+	__shared__ unsigned s_base[2];
 	__shared__ unsigned short s_order[2][kN];
 	__shared__ int32_t s_tri[2][kN], s_mat[2][kN];
 	const unsigned lane = threadIdx.x & 31u;
@@ -640,6 +656,7 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) k_shade_bounce_multi(Shad
 	if (threadIdx.x < 16u) (&s_total[0][0])[threadIdx.x] = 0u;
 	else if (threadIdx.x < 32u) (&s_fill[0][0])[threadIdx.x - 16u] = 0u;
 	else if (threadIdx.x < 34u) s_next[threadIdx.x - 32u] = 0u;
+	else if (threadIdx.x < 36u) s_base[threadIdx.x - 34u] = kNoBase;
 	__syncthreads();
 	unsigned q0 = blockIdx.x * kN;
 	for (unsigned r = 0; r < rounds; ++r, q0 += stride) {
@@ -662,9 +679,14 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) k_shade_bounce_multi(Shad
 			if (rank[k] == 0u) atomicAdd(&s_total[buf][cls], (unsigned)__popc(same));
 		}
 		__syncthreads();
+		unsigned reserved = kNoBase; // thread 0: the round's reservation, on its way while the entries are put in order
 		{
 			const uint4 t0 = *reinterpret_cast<const uint4 *>(&s_total[buf][0]), t1 = *reinterpret_cast<const uint4 *>(&s_total[buf][4]);
 			const unsigned tot[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+			if (block_slots && threadIdx.x == 0u) {
+				const unsigned n_sure = tot[kClassDiffuse] + tot[kClassMirror] + tot[kClassGlass] + tot[kClassOther];
+				reserved = n_sure != 0u ? (unsigned)atom_add_u64(B.out_count, (unsigned long long)n_sure, lane & A.zero) : 0u;
+			}
 #pragma unroll
 			for (int k = 0; k < EPT; ++k) {
 				const unsigned cls = cw[k] >> 24;
@@ -680,22 +702,29 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) k_shade_bounce_multi(Shad
 				const unsigned pos = base + off + rank[k];
 				s_order[buf][pos] = (unsigned short)((unsigned)k * (unsigned)BLOCK + threadIdx.x);
 				s_tri[buf][pos] = tri[k];
-				s_mat[buf][pos] = (cw[k] & 0x00ffffffu) != 0x00ffffffu ? (int32_t)(cw[k] & 0x00ffffffu) : -1;
+				s_mat[buf][pos] = (int32_t)cw[k];
 			}
 			// the other buffer's counters for the next round (everybody has left the previous round: they are all past the barrier above)
 			if (threadIdx.x < 8u) { s_total[buf ^ 1u][threadIdx.x] = 0u; s_fill[buf ^ 1u][threadIdx.x] = 0u; }
 			if (threadIdx.x == 8u) s_next[buf ^ 1u] = 0u;
+			if (threadIdx.x == 9u) s_base[buf ^ 1u] = kNoBase;
 		}
 		__syncthreads();
+		if (block_slots && threadIdx.x == 0u) *(volatile unsigned *)&s_base[buf] = reserved; // whoever needs a slot before this waits for it
 		const unsigned n_valid = q0 >= total ? 0u : (total - q0 < kN ? total - q0 : kN);
 		const unsigned n_chunks = (n_valid + 31u) / 32u;
+		const unsigned n_miss = s_total[buf][kClassMiss], n_glossy = s_total[buf][kClassGlossy]; // the regions in front of the sure ones
 		for (;;) {
 			unsigned c = 0u;
 			if (lane == 0u) c = atomicAdd(&s_next[buf], 1u);
 			c = __shfl_sync(kFullMask, c, 0);
 			if (c >= n_chunks) break;
 			const unsigned p = c * 32u + lane;
-			shade_queue_entry(B, A, b, tmin, last, dims, q0 + s_order[buf][p], s_tri[buf][p], s_mat[buf][p]);
+			const unsigned w = (unsigned)s_mat[buf][p]; // class << 24 | material id
+			const unsigned cls = w >> 24;
+			const bool sure = block_slots && (cls == (unsigned)kClassDiffuse || cls == (unsigned)kClassMirror || cls == (unsigned)kClassGlass || cls == (unsigned)kClassOther);
+			shade_queue_entry(B, A, b, tmin, last, dims, q0 + s_order[buf][p], s_tri[buf][p], (w & 0x00ffffffu) != 0x00ffffffu ? (int32_t)(w & 0x00ffffffu) : -1,
+			                  sure ? (const volatile unsigned *)&s_base[buf] : nullptr, p - n_miss - (cls > (unsigned)kClassGlossy ? n_glossy : 0u));
 		}
 	}
 }
@@ -945,6 +974,7 @@ struct adypt_tracer {
 	// traversal kernel that counts the nodes and triangles the wavefront's rays touch. Off by default.
 	int bounce_ctas = 0;   // tuning (ADYPT_BOUNCE_CTAS): see the switch in run_batch; 0 = default (four entries per thread, dynamic chunks)
 	int primary_ctas = 0;  // tuning (ADYPT_PRIMARY_CTAS): bounce-0 kernel: 2 / 3 / 4 = unsorted at that many CTAs per SM, 22 = class-sorted 2 items per thread; 0 = default (class-sorted, 4 per thread)
+	unsigned early_slots = 1; // tuning (ADYPT_EARLY_SLOTS)
 	int primary_chunk = 0; // tuning (ADYPT_PRIMARY_CHUNK): samples of a group shaded per queue-slot request (1..8); 0 = default
 	int primary_group = 0; // tuning (ADYPT_PRIMARY_GROUP): samples of one pixel a thread of the bounce-0 stage shades; 0 = default
 	int profiling = 0;
@@ -1142,6 +1172,7 @@ int run_batch(adypt_tracer *t, int first, int n, bool sum_mode)
 	A.width = t->width; A.height = t->height; A.first_spp = first; A.n_samples = n;
 	A.rr_start = t->rr_start;
 	A.zero = 0u;
+	A.early_slots = t->early_slots;
 	A.dims = (t->rr_start >= 0 ? 3 : 2) * c.max_bounce;
 	// uSpp % uTmpLife == 0 -> trace and store the primary hit; otherwise reuse it (pathtracer.glsl:113-127)
 	if (first % c.tmp_lifetime == 0 || !t->prim_valid || t->prim_block != block) {
@@ -1343,6 +1374,7 @@ int adypt_tracer_create(adypt_scene *scene, const adypt_pt_config *config, int32
 	if (const char *e = getenv("ADYPT_PRIMARY_GROUP")) t->primary_group = atoi(e);
 	if (const char *e = getenv("ADYPT_PRIMARY_CTAS")) t->primary_ctas = atoi(e);
 	if (const char *e = getenv("ADYPT_PRIMARY_CHUNK")) t->primary_chunk = atoi(e);
+	if (const char *e = getenv("ADYPT_EARLY_SLOTS")) t->early_slots = atoi(e) != 0 ? 1u : 0u;
 	if (const char *e = getenv("ADYPT_BOUNCE_CTAS")) t->bounce_ctas = atoi(e);
 	if (const char *e = getenv("ADYPT_WAVEFRONT_SKEW")) t->slab_skew = ((size_t)atol(e) + 255u) & ~(size_t)255u;
 	t->launches_at_create = g_launches.load();
