@@ -135,6 +135,9 @@ TraceKernel trace_kernel_for(bool any, bool stats, int variant)
 	case 5: return trace_kernel<true, false, 4, 8, 2>;
 	case 8: return trace_kernel<true, false, 4, 8, 12, false>;
 	case 9: return trace_kernel<true, false, 4, 8, 12, true, true>;
+	case 13: return trace_kernel<true, false, 4, 8, 12, true, false, true>;
+	case 14: return trace_kernel<true, false, 3, 8, 12, true, false, true>;
+	case 15: return trace_kernel<true, false, 2, 8, 12, true, false, true>;
 	default: return trace_kernel<true>;
 	}
 	switch (variant) {
@@ -149,6 +152,9 @@ TraceKernel trace_kernel_for(bool any, bool stats, int variant)
 	case 9: return trace_kernel<false, false, 4, 8, 12, true, true>; // hit-mask contributions from a shared-memory table
 	case 10: return trace_kernel<false, false, 3, 8, 12, true, true>;
 	case 11: return trace_kernel<false, false, 5, 8, 12, true, true>;
+	case 13: return trace_kernel<false, false, 4, 8, 12, true, false, true>; // slab evaluations as packed FFMA2 / FADD2
+	case 14: return trace_kernel<false, false, 3, 8, 12, true, false, true>;
+	case 15: return trace_kernel<false, false, 2, 8, 12, true, false, true>;
 	default: return trace_kernel<false>;
 	}
 }

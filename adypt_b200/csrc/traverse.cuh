@@ -144,6 +144,109 @@ __device__ __forceinline__ uint32_t test_children4(uint32_t meta4, uint32_t octi
 #undef ADYPT_CHILD
 }
 
+// The same four children with the slab evaluations issued two at a time: Blackwell's packed fp32 instructions (fma.rn.f32x2 /
+// sub.rn.f32x2 -> FFMA2 / FADD2) take a register PAIR for the two children's quantised coordinates and the ray's scaled inverse
+// direction and origin as scalars that SASS broadcasts (`R4.F32`), so a node step issues 24 FFMA2 + 8 FADD2 where it issued
+// 48 FFMA + 16 FADD. Each half is the IEEE round-to-nearest fused multiply-add / subtraction of the scalar form: same bits.
+__device__ __forceinline__ unsigned long long pack2(float a, float b)
+{
+	unsigned long long r;
+	asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+	return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float &a, float &b)
+{
+	asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+// (o . m.xyz, d . m.xyz) with the two dot products side by side: three packed instructions instead of six, each half evaluated
+// exactly like dot3_fma (fma(z, m.z, fma(y, m.y, x * m.x)))
+__device__ __forceinline__ void dot3_fma_pair(float ox, float dx, float oy, float dy, float oz, float dz, const float4 m, float &dot_o, float &dot_d)
+{
+	unsigned long long r;
+	asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pack2(ox, dx)), "l"(pack2(m.x, m.x)));
+	asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pack2(oy, dy)), "l"(pack2(m.y, m.y)), "l"(r));
+	asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pack2(oz, dz)), "l"(pack2(m.z, m.z)), "l"(r));
+	unpack2(r, dot_o, dot_d);
+}
+// t, u, v of the Woop test (:221-233) for rows M0..M2
+template <bool PACKED>
+__device__ __forceinline__ void woop_eval(float ox, float oy, float oz, float dx, float dy, float dz, const float4 M0, const float4 M1, const float4 M2,
+                                          float &tt, float &tu, float &tv)
+{
+	float o0, d0, o1, d1, o2, d2;
+	if (PACKED) {
+		dot3_fma_pair(ox, dx, oy, dy, oz, dz, M0, o0, d0);
+		dot3_fma_pair(ox, dx, oy, dy, oz, dz, M1, o1, d1);
+		dot3_fma_pair(ox, dx, oy, dy, oz, dz, M2, o2, d2);
+	} else {
+		o0 = dot3_fma(ox, oy, oz, M0); d0 = dot3_fma(dx, dy, dz, M0);
+		o1 = dot3_fma(ox, oy, oz, M1); d1 = dot3_fma(dx, dy, dz, M1);
+		o2 = dot3_fma(ox, oy, oz, M2); d2 = dot3_fma(dx, dy, dz, M2);
+	}
+	const float toz = __fsub_rn(M0.w, o0);
+	const float tidz = __frcp_rn(d0);
+	tt = __fmul_rn(toz, tidz);
+	const float tox = __fadd_rn(M1.w, o1);
+	tu = __fmaf_rn(tt, d1, tox);
+	const float toy = __fadd_rn(M2.w, o2);
+	tv = __fmaf_rn(tt, d2, toy);
+}
+
+// (float)byte K and K + 1 of `word`, times a, plus c
+template <int K, bool CVT>
+__device__ __forceinline__ void plane2(uint32_t word, uint32_t magic, float a, float c, float &t0, float &t1)
+{
+	unsigned long long q;
+	if (CVT)
+		q = pack2(byte_to_float_cvt<K>(word), byte_to_float_cvt<K + 1>(word));
+	else {
+		uint32_t r0, r1;
+		asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r0) : "r"(word), "r"(magic), "n"(0x7540 | K));
+		asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r1) : "r"(word), "r"(magic), "n"(0x7540 | (K + 1)));
+		const float m = __uint_as_float(magic); // 2^23
+		asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(q) : "l"(pack2(__uint_as_float(r0), __uint_as_float(r1))), "l"(pack2(m, m)));
+	}
+	unsigned long long r;
+	asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(q), "l"(pack2(a, a)), "l"(pack2(c, c)));
+	unpack2(r, t0, t1);
+}
+template <int K>
+__device__ __forceinline__ uint32_t finish_child(uint32_t meta_oct4, float txmin, float tymin, float tzmin, float txmax, float tymax, float tzmax,
+                                                 float tmin, float hit_t)
+{
+	const float ctmin = fmaxf(fmaxf(txmin, tymin), fmaxf(tzmin, tmin));
+	const float ctmax = fminf(fminf(txmax, tymax), fminf(tzmax, hit_t));
+	if (ctmin <= ctmax) {
+		const uint32_t b = __byte_perm(meta_oct4, 0u, 0x4440u | K);
+		return __funnelshift_l(0u, b >> 5, b);
+	}
+	return 0u;
+}
+template <int K, int CVT_PLANES>
+__device__ __forceinline__ uint32_t test_child_pair(uint32_t meta_oct4, uint32_t s_lox, uint32_t s_loy, uint32_t s_loz, uint32_t s_hix, uint32_t s_hiy,
+                                                    uint32_t s_hiz, float aix, float aiy, float aiz, float aox, float aoy, float aoz, float tmin, float hit_t,
+                                                    uint32_t magic)
+{
+	float x0, x1, y0, y1, z0, z1, X0, X1, Y0, Y1, Z0, Z1;
+	plane2<K, (CVT_PLANES > 0)>(s_lox, magic, aix, aox, x0, x1);
+	plane2<K, (CVT_PLANES > 2)>(s_loy, magic, aiy, aoy, y0, y1);
+	plane2<K, (CVT_PLANES > 4)>(s_loz, magic, aiz, aoz, z0, z1);
+	plane2<K, (CVT_PLANES > 1)>(s_hix, magic, aix, aox, X0, X1);
+	plane2<K, (CVT_PLANES > 3)>(s_hiy, magic, aiy, aoy, Y0, Y1);
+	plane2<K, (CVT_PLANES > 5)>(s_hiz, magic, aiz, aoz, Z0, Z1);
+	return finish_child<K>(meta_oct4, x0, y0, z0, X0, Y0, Z0, tmin, hit_t) | finish_child<K + 1>(meta_oct4, x1, y1, z1, X1, Y1, Z1, tmin, hit_t);
+}
+template <int CVT_PLANES>
+__device__ __forceinline__ uint32_t test_children4_packed(uint32_t meta4, uint32_t octinv4, uint32_t s_lox, uint32_t s_loy, uint32_t s_loz, uint32_t s_hix,
+                                                          uint32_t s_hiy, uint32_t s_hiz, float aix, float aiy, float aiz, float aox, float aoy, float aoz,
+                                                          float tmin, float hit_t, uint32_t magic)
+{
+	const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+	const uint32_t meta_oct4 = meta4 ^ (octinv4 & ((is_inner4 >> 4) * 0xffu));
+	return test_child_pair<0, CVT_PLANES>(meta_oct4, s_lox, s_loy, s_loz, s_hix, s_hiy, s_hiz, aix, aiy, aiz, aox, aoy, aoz, tmin, hit_t, magic) |
+	       test_child_pair<2, CVT_PLANES>(meta_oct4, s_lox, s_loy, s_loz, s_hix, s_hiy, s_hiz, aix, aiy, aiz, aox, aoy, aoz, tmin, hit_t, magic);
+}
+
 // TRI_BATCH: 0 = a lane tests all triangles of its group before the warp moves on (the GLSL's loop shape);
 // K > 0 = at most K triangle tests per lane and round, lanes with triangles left skip their next node step until
 // the group is empty; 12 = K 2 with both triangles' rows fetched before the first test. Only the warp-level
@@ -154,7 +257,7 @@ __device__ __forceinline__ uint32_t test_children4(uint32_t meta4, uint32_t octi
 // whole warp for the next 32 rays of its pool at once and parked in shared memory (48 B per ray); an idle lane then picks
 // its ray up with three LDS.128. Unstaged, the same code runs at every refill for the ~6 lanes that happen to be idle, and
 // the warp waits on the (cold, HBM) ray loads five times as often. Same arithmetic per ray, so same results.
-template <bool ANY, bool STATS = false, int CVT_PLANES = 4, int MIN_CTAS = 8, int TRI_BATCH = 12, bool STAGED = true, bool HM_LUT = false>
+template <bool ANY, bool STATS = false, int CVT_PLANES = 4, int MIN_CTAS = 8, int TRI_BATCH = 12, bool STAGED = true, bool HM_LUT = false, bool PACKED = false>
 __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const TraceParams p)
 {
 	const uint32_t magic = p.magic;
@@ -254,8 +357,13 @@ __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const Trac
 						sx = __fmul_rn(sx, inv); sy = __fmul_rn(sy, inv); sz = __fmul_rn(sz, inv);
 						const uint32_t oi = 7u - ((sx < 0.0f ? 1u : 0u) | (sy < 0.0f ? 2u : 0u) | (sz < 0.0f ? 4u : 0u));
 						const uint32_t slot = lane_addr + (lane_addr & 0xffu) + kWarpStack; // region + stack + 16 * lane
-						sts128(slot, r0);
-						sts128(slot + 512u, make_float4(sx, sy, sz, __uint_as_float(oi)));
+						if (PACKED) { // origin and direction interleaved: the lane that takes the ray gets (ox, dx), (oy, dy), (oz, dz) as register pairs
+							sts128(slot, make_float4(r0.x, sx, r0.y, sy));
+							sts128(slot + 512u, make_float4(r0.z, sz, r0.w, __uint_as_float(oi)));
+						} else {
+							sts128(slot, r0);
+							sts128(slot + 512u, make_float4(sx, sy, sz, __uint_as_float(oi)));
+						}
 						sts128(slot + 1024u, make_float4(__frcp_rn(sx), __frcp_rn(sy), __frcp_rn(sz), 0.0f));
 					}
 					__syncwarp();
@@ -266,8 +374,13 @@ __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const Trac
 					const uint32_t slot = (lane_addr & ~0xffu) + kWarpStack + cand * 16u;
 					const float4 a = lds128(slot), b = lds128(slot + 512u), c = lds128(slot + 1024u);
 					ray_idx = stage_base + cand;
-					ox = a.x; oy = a.y; oz = a.z; tmin = a.w;
-					dx = b.x; dy = b.y; dz = b.z; octinv = __float_as_uint(b.w);
+					if (PACKED) {
+						ox = a.x; dx = a.y; oy = a.z; dy = a.w;
+						oz = b.x; dz = b.y; tmin = b.z; octinv = __float_as_uint(b.w);
+					} else {
+						ox = a.x; oy = a.y; oz = a.z; tmin = a.w;
+						dx = b.x; dy = b.y; dz = b.z; octinv = __float_as_uint(b.w);
+					}
 					idx = c.x; idy = c.y; idz = c.z;
 					hit_t = 1e9f; hit_idx = -1; hit_u = 0.0f; hit_v = 0.0f;
 					ng = make_uint2(0u, 0x80000000u);
@@ -360,7 +473,18 @@ __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const Trac
 					const bool nx = idx < 0.0f, ny = idy < 0.0f, nz = idz < 0.0f;
 					// planes: n2 = (lox.lo, lox.hi, loy.lo, loy.hi) n3 = (loz.lo, loz.hi, hix.lo, hix.hi)
 					//         n4 = (hiy.lo, hiy.hi, hiz.lo, hiz.hi)
-					uint32_t hitmask = test_children4<CVT_PLANES, HM_LUT>(n1.z, octinv4,
+					uint32_t hitmask;
+					if (PACKED) {
+						hitmask = test_children4_packed<CVT_PLANES>(n1.z, octinv4,
+							nx ? n3.z : n2.x, ny ? n4.x : n2.z, nz ? n4.z : n3.x,
+							nx ? n2.x : n3.z, ny ? n2.z : n4.x, nz ? n3.x : n4.z,
+							aix, aiy, aiz, aox, aoy, aoz, tmin, hit_t, magic);
+						hitmask |= test_children4_packed<CVT_PLANES>(n1.w, octinv4,
+							nx ? n3.w : n2.y, ny ? n4.y : n2.w, nz ? n4.w : n3.y,
+							nx ? n2.y : n3.w, ny ? n2.w : n4.y, nz ? n3.y : n4.w,
+							aix, aiy, aiz, aox, aoy, aoz, tmin, hit_t, magic);
+					} else {
+					hitmask = test_children4<CVT_PLANES, HM_LUT>(n1.z, octinv4,
 						nx ? n3.z : n2.x, ny ? n4.x : n2.z, nz ? n4.z : n3.x,
 						nx ? n2.x : n3.z, ny ? n2.z : n4.x, nz ? n3.x : n4.z,
 						aix, aiy, aiz, aox, aoy, aoz, tmin, hit_t, magic, s_hm_lut);
@@ -368,6 +492,7 @@ __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const Trac
 						nx ? n3.w : n2.y, ny ? n4.y : n2.w, nz ? n4.w : n3.y,
 						nx ? n2.y : n3.w, ny ? n2.w : n4.y, nz ? n3.y : n4.w,
 						aix, aiy, aiz, aox, aoy, aoz, tmin, hit_t, magic, s_hm_lut);
+					}
 					ng.y = (hitmask & 0xff000000u) | (n0.w >> 24);
 					tg.y = hitmask & 0x00ffffffu;
 				}
@@ -388,29 +513,15 @@ __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const Trac
 #define ADYPT_WOOP_TEST(TR, M0, M1, M2) \
 	do { \
 		if (STATS) ++st_tris; \
-		const float toz = __fsub_rn(M0.w, dot3_fma(ox, oy, oz, M0)); \
-		const float tidz = __frcp_rn(dot3_fma(dx, dy, dz, M0)); \
-		const float tt = __fmul_rn(toz, tidz); \
-		const float tox = __fadd_rn(M1.w, dot3_fma(ox, oy, oz, M1)); \
-		const float tu = __fmaf_rn(tt, dot3_fma(dx, dy, dz, M1), tox); \
-		const float toy = __fadd_rn(M2.w, dot3_fma(ox, oy, oz, M2)); \
-		const float tv = __fmaf_rn(tt, dot3_fma(dx, dy, dz, M2), toy); \
+		float tt, tu, tv; \
+		woop_eval<PACKED>(ox, oy, oz, dx, dy, dz, M0, M1, M2, tt, tu, tv); \
 		if (tt > tmin && tt < hit_t && tu >= 0.0f && tu <= 1.0f && tv >= 0.0f && __fadd_rn(tu, tv) <= 1.0f) { \
 			hit_t = tt; \
 			if (ANY) finished = true; /* :480-483 */ \
 			else { hit_u = tu; hit_v = tv; hit_idx = (int32_t)(TR); } \
 		} \
 	} while (0)
-#define ADYPT_WOOP_EVAL(M0, M1, M2, TT, TU, TV) \
-	do { \
-		const float toz = __fsub_rn(M0.w, dot3_fma(ox, oy, oz, M0)); \
-		const float tidz = __frcp_rn(dot3_fma(dx, dy, dz, M0)); \
-		TT = __fmul_rn(toz, tidz); \
-		const float tox = __fadd_rn(M1.w, dot3_fma(ox, oy, oz, M1)); \
-		TU = __fmaf_rn(TT, dot3_fma(dx, dy, dz, M1), tox); \
-		const float toy = __fadd_rn(M2.w, dot3_fma(ox, oy, oz, M2)); \
-		TV = __fmaf_rn(TT, dot3_fma(dx, dy, dz, M2), toy); \
-	} while (0)
+#define ADYPT_WOOP_EVAL(M0, M1, M2, TT, TU, TV) woop_eval<PACKED>(ox, oy, oz, dx, dy, dz, M0, M1, M2, TT, TU, TV)
 #define ADYPT_WOOP_ACCEPT(TR, TT, TU, TV) \
 	do { \
 		if (STATS) ++st_tris; \
