@@ -91,6 +91,29 @@ __global__ void build_woop_kernel(const uint8_t *__restrict__ tris, const int32_
 	woop[3 * (size_t)i + 2] = make_float4(inv[1][0], inv[1][1], inv[1][2], inv[1][3]);
 }
 
+// Wide nodes (traverse.cuh, MODE 2): the reference's 80-byte node re-laid as one 128-byte line with each child's hit-mask contribution as a word
+__global__ void build_wide_nodes(const uint4 *__restrict__ nodes, uint32_t n_nodes, uint4 *__restrict__ wide)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_nodes) return;
+	const uint4 n0 = nodes[(size_t)i * 5u], n1 = nodes[(size_t)i * 5u + 1];
+	uint32_t c[8];
+#pragma unroll
+	for (int k = 0; k < 8; ++k) {
+		const uint32_t b = ((k < 4 ? n1.z : n1.w) >> (8 * (k & 3))) & 0xffu;
+		c[k] = (b >> 5) << (b & 31u);
+	}
+	uint4 *o = wide + (size_t)i * 8u;
+	o[0] = make_uint4(n0.x, n0.y, n0.z, n0.w >> 24);
+	o[1] = make_uint4((n0.w & 0xffu) << 23, ((n0.w >> 8) & 0xffu) << 23, ((n0.w >> 16) & 0xffu) << 23, n1.x);
+	o[2] = nodes[(size_t)i * 5u + 2];
+	o[3] = nodes[(size_t)i * 5u + 3];
+	o[4] = nodes[(size_t)i * 5u + 4];
+	o[5] = make_uint4(c[0], c[1], c[2], c[3]);
+	o[6] = make_uint4(c[4], c[5], c[6], c[7]);
+	o[7] = make_uint4(n1.y, 0u, 0u, 0u);
+}
+
 // Shading records: the wavefront's shading stage gathers one Triangle per segment. The reference's record is
 // 100 bytes at a 100-byte stride (Shape.hpp:70-88) -- 25 scalar loads over 4 or 5 sectors; here it is copied, unchanged, to
 // the start of a 128-byte line (7 vector loads, exactly one L2 line). The shading branch its material selects
@@ -135,9 +158,12 @@ TraceKernel trace_kernel_for(bool any, bool stats, int variant)
 	case 5: return trace_kernel<true, false, 4, 8, 2>;
 	case 8: return trace_kernel<true, false, 4, 8, 12, false>;
 	case 9: return trace_kernel<true, false, 4, 8, 12, true, true>;
-	case 13: return trace_kernel<true, false, 4, 8, 12, true, false, true>;
-	case 14: return trace_kernel<true, false, 3, 8, 12, true, false, true>;
-	case 15: return trace_kernel<true, false, 2, 8, 12, true, false, true>;
+	case 13: return trace_kernel<true, false, 4, 8, 12, true, false, 1>;
+	case 14: return trace_kernel<true, false, 3, 8, 12, true, false, 1>;
+	case 15: return trace_kernel<true, false, 2, 8, 12, true, false, 1>;
+	case 16: return trace_kernel<true, false, 4, 8, 12, true, false, 2>;
+	case 17: return trace_kernel<true, false, 3, 8, 12, true, false, 2>;
+	case 18: return trace_kernel<true, false, 2, 8, 12, true, false, 2>;
 	default: return trace_kernel<true>;
 	}
 	switch (variant) {
@@ -152,9 +178,12 @@ TraceKernel trace_kernel_for(bool any, bool stats, int variant)
 	case 9: return trace_kernel<false, false, 4, 8, 12, true, true>; // hit-mask contributions from a shared-memory table
 	case 10: return trace_kernel<false, false, 3, 8, 12, true, true>;
 	case 11: return trace_kernel<false, false, 5, 8, 12, true, true>;
-	case 13: return trace_kernel<false, false, 4, 8, 12, true, false, true>; // slab evaluations as packed FFMA2 / FADD2
-	case 14: return trace_kernel<false, false, 3, 8, 12, true, false, true>;
-	case 15: return trace_kernel<false, false, 2, 8, 12, true, false, true>;
+	case 13: return trace_kernel<false, false, 4, 8, 12, true, false, 1>; // slab evaluations as packed FFMA2 / FADD2
+	case 14: return trace_kernel<false, false, 3, 8, 12, true, false, 1>;
+	case 15: return trace_kernel<false, false, 2, 8, 12, true, false, 1>;
+	case 16: return trace_kernel<false, false, 4, 8, 12, true, false, 2>; // packed + 128-byte nodes with the hit-mask words spelled out
+	case 17: return trace_kernel<false, false, 3, 8, 12, true, false, 2>;
+	case 18: return trace_kernel<false, false, 2, 8, 12, true, false, 2>;
 	default: return trace_kernel<false>;
 	}
 }
@@ -167,6 +196,7 @@ int launch_trace(adypt_scene *s, const float4 *d_rays, uint64_t n, int32_t *d_tr
 	const bool any = d_occ != nullptr;
 	TraceParams p;
 	p.nodes = s->d_nodes;
+	p.nodes_wide = s->d_nodes_wide;
 	p.woop = s->d_woop;
 	p.tri_indices = s->d_tri_indices;
 	p.rays = d_rays;
@@ -233,6 +263,7 @@ static void free_scene(adypt_scene *s)
 {
 	DeviceGuard g(s->device);
 	cudaFree(s->d_nodes);
+	cudaFree(s->d_nodes_wide);
 	cudaFree(s->d_woop);
 	cudaFree(s->d_tri_indices);
 	cudaFree(s->d_tris);
@@ -354,6 +385,14 @@ int adypt_scene_create(const adypt_scene_desc *d, adypt_scene **out)
 		return rc;                                                                   \
 	}
 	UP(s->d_nodes, d->nodes, (size_t)d->n_nodes * 80u);
+	if (d->n_nodes) {
+		if (cudaMalloc((void **)&s->d_nodes_wide, (size_t)d->n_nodes * 128u) != cudaSuccess) { free_scene(s); return fail(ADYPT_ENOMEM, "cudaMalloc wide nodes"); }
+		s->device_bytes += (size_t)d->n_nodes * 128u;
+		build_wide_nodes<<<(d->n_nodes + 127) / 128, 128>>>(s->d_nodes, d->n_nodes, s->d_nodes_wide);
+		count_launch();
+		cudaError_t e = cudaDeviceSynchronize();
+		if (e != cudaSuccess) { free_scene(s); return fail(ADYPT_ECUDA, std::string("build_wide_nodes: ") + cudaGetErrorString(e)); }
+	}
 	UP(s->d_tri_indices, d->tri_indices, (size_t)d->n_refs * 4u);
 	UP(s->d_tris, d->triangles, (size_t)d->n_tris * 100u);
 	UP(s->d_mats, d->materials, (size_t)d->n_mats * 64u);
@@ -462,7 +501,7 @@ int adypt_trace_configure(adypt_scene *s, int ctas_per_sm, int refill_threshold,
 {
 	return guarded([&]() -> int {
 	if (!s) return fail(ADYPT_EINVAL, "scene is NULL");
-	if (ctas_per_sm < 0 || refill_threshold < 0 || refill_threshold > 32 || variant < 0 || variant > 15) return fail(ADYPT_EINVAL, "bad tuning value");
+	if (ctas_per_sm < 0 || refill_threshold < 0 || refill_threshold > 32 || variant < 0 || variant > 18) return fail(ADYPT_EINVAL, "bad tuning value");
 	if (variant == 12 && !getenv("ADYPT_EXPERIMENTAL"))
 		return fail(ADYPT_EINVAL, "variant 12 (shared-memory ray pool) is an experiment without a deep-stack path: set ADYPT_EXPERIMENTAL=1 to select it");
 	s->ctas_per_sm = ctas_per_sm;
