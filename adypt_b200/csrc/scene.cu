@@ -91,27 +91,16 @@ __global__ void build_woop_kernel(const uint8_t *__restrict__ tris, const int32_
 	woop[3 * (size_t)i + 2] = make_float4(inv[1][0], inv[1][1], inv[1][2], inv[1][3]);
 }
 
-// Wide nodes (traverse.cuh, MODE 2): the reference's 80-byte node re-laid as one 128-byte line with each child's hit-mask contribution as a word
+// Wide nodes (traverse.cuh, MODE 2): the reference's 80-byte node followed by its three plane scales as floats, at a 96-byte stride
 __global__ void build_wide_nodes(const uint4 *__restrict__ nodes, uint32_t n_nodes, uint4 *__restrict__ wide)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n_nodes) return;
-	const uint4 n0 = nodes[(size_t)i * 5u], n1 = nodes[(size_t)i * 5u + 1];
-	uint32_t c[8];
+	uint4 *o = wide + (size_t)i * 6u;
 #pragma unroll
-	for (int k = 0; k < 8; ++k) {
-		const uint32_t b = ((k < 4 ? n1.z : n1.w) >> (8 * (k & 3))) & 0xffu;
-		c[k] = (b >> 5) << (b & 31u);
-	}
-	uint4 *o = wide + (size_t)i * 8u;
-	o[0] = make_uint4(n0.x, n0.y, n0.z, n0.w >> 24);
-	o[1] = make_uint4((n0.w & 0xffu) << 23, ((n0.w >> 8) & 0xffu) << 23, ((n0.w >> 16) & 0xffu) << 23, n1.x);
-	o[2] = nodes[(size_t)i * 5u + 2];
-	o[3] = nodes[(size_t)i * 5u + 3];
-	o[4] = nodes[(size_t)i * 5u + 4];
-	o[5] = make_uint4(c[0], c[1], c[2], c[3]);
-	o[6] = make_uint4(c[4], c[5], c[6], c[7]);
-	o[7] = make_uint4(n1.y, 0u, 0u, 0u);
+	for (int k = 0; k < 5; ++k) o[k] = nodes[(size_t)i * 5u + k];
+	const uint32_t w = nodes[(size_t)i * 5u].w;
+	o[5] = make_uint4((w & 0xffu) << 23, ((w >> 8) & 0xffu) << 23, ((w >> 16) & 0xffu) << 23, 0u);
 }
 
 // Shading records: the wavefront's shading stage gathers one Triangle per segment. The reference's record is
@@ -147,8 +136,9 @@ __global__ void build_shade_records(const uint8_t *__restrict__ tris, const Mate
 
 // ------------------------------------------------------------------------------------------------
 // The kernel a launch uses. Variants are code-generation variants of the same algorithm (identical results; tuning and
-// A/B measurements only); 0 = tuned default: 4 conversion planes on the I2F pipe, 8 CTAs/SM, triangle batch 2 with both
-// fetches up front, staged ray set-up. `stats` selects the instrumented build (work counters; slower).
+// A/B measurements only); 0 = tuned default: packed slab / Woop evaluations on 96-byte nodes (MODE 2), 3 conversion planes on the I2F
+// pipe, 8 CTAs/SM, triangle batch 2 with both fetches up front, staged ray set-up. 19 = the product kernel of round 1 and most of round 2
+// (scalar evaluations, the reference's 80-byte nodes). `stats` selects the instrumented build (work counters; slower).
 TraceKernel trace_kernel_for(bool any, bool stats, int variant)
 {
 	if (stats) return any ? trace_kernel<true, true> : trace_kernel<false, true>;
@@ -164,7 +154,8 @@ TraceKernel trace_kernel_for(bool any, bool stats, int variant)
 	case 16: return trace_kernel<true, false, 4, 8, 12, true, false, 2>;
 	case 17: return trace_kernel<true, false, 3, 8, 12, true, false, 2>;
 	case 18: return trace_kernel<true, false, 2, 8, 12, true, false, 2>;
-	default: return trace_kernel<true>;
+	case 19: return trace_kernel<true>;
+	default: return trace_kernel<true, false, 3, 8, 12, true, false, 2>;
 	}
 	switch (variant) {
 	case 1: return trace_kernel<false, false, 2, 8, 0>; // unbounded triangle loop
@@ -181,10 +172,11 @@ TraceKernel trace_kernel_for(bool any, bool stats, int variant)
 	case 13: return trace_kernel<false, false, 4, 8, 12, true, false, 1>; // slab evaluations as packed FFMA2 / FADD2
 	case 14: return trace_kernel<false, false, 3, 8, 12, true, false, 1>;
 	case 15: return trace_kernel<false, false, 2, 8, 12, true, false, 1>;
-	case 16: return trace_kernel<false, false, 4, 8, 12, true, false, 2>; // packed + 128-byte nodes with the hit-mask words spelled out
+	case 16: return trace_kernel<false, false, 4, 8, 12, true, false, 2>; // packed + 96-byte nodes fetched with three 256-bit loads
 	case 17: return trace_kernel<false, false, 3, 8, 12, true, false, 2>;
 	case 18: return trace_kernel<false, false, 2, 8, 12, true, false, 2>;
-	default: return trace_kernel<false>;
+	case 19: return trace_kernel<false>; // scalar evaluations, 80-byte nodes
+	default: return trace_kernel<false, false, 3, 8, 12, true, false, 2>;
 	}
 }
 
@@ -386,8 +378,8 @@ int adypt_scene_create(const adypt_scene_desc *d, adypt_scene **out)
 	}
 	UP(s->d_nodes, d->nodes, (size_t)d->n_nodes * 80u);
 	if (d->n_nodes) {
-		if (cudaMalloc((void **)&s->d_nodes_wide, (size_t)d->n_nodes * 128u) != cudaSuccess) { free_scene(s); return fail(ADYPT_ENOMEM, "cudaMalloc wide nodes"); }
-		s->device_bytes += (size_t)d->n_nodes * 128u;
+		if (cudaMalloc((void **)&s->d_nodes_wide, (size_t)d->n_nodes * 96u) != cudaSuccess) { free_scene(s); return fail(ADYPT_ENOMEM, "cudaMalloc wide nodes"); }
+		s->device_bytes += (size_t)d->n_nodes * 96u;
 		build_wide_nodes<<<(d->n_nodes + 127) / 128, 128>>>(s->d_nodes, d->n_nodes, s->d_nodes_wide);
 		count_launch();
 		cudaError_t e = cudaDeviceSynchronize();
@@ -501,7 +493,7 @@ int adypt_trace_configure(adypt_scene *s, int ctas_per_sm, int refill_threshold,
 {
 	return guarded([&]() -> int {
 	if (!s) return fail(ADYPT_EINVAL, "scene is NULL");
-	if (ctas_per_sm < 0 || refill_threshold < 0 || refill_threshold > 32 || variant < 0 || variant > 18) return fail(ADYPT_EINVAL, "bad tuning value");
+	if (ctas_per_sm < 0 || refill_threshold < 0 || refill_threshold > 32 || variant < 0 || variant > 19) return fail(ADYPT_EINVAL, "bad tuning value");
 	if (variant == 12 && !getenv("ADYPT_EXPERIMENTAL"))
 		return fail(ADYPT_EINVAL, "variant 12 (shared-memory ray pool) is an experiment without a deep-stack path: set ADYPT_EXPERIMENTAL=1 to select it");
 	s->ctas_per_sm = ctas_per_sm;

@@ -19,7 +19,7 @@ struct adypt_scene {
 	int sm_count = 0;
 	uint32_t n_nodes = 0, n_refs = 0, n_tris = 0, n_mats = 0;
 	uint4 *d_nodes = nullptr;          // n_nodes * 5
-	uint4 *d_nodes_wide = nullptr;     // n_nodes * 8: derived 128-byte layout (build_wide_nodes)
+	uint4 *d_nodes_wide = nullptr;     // n_nodes * 6: derived 96-byte layout (build_wide_nodes)
 	float4 *d_woop = nullptr;          // n_refs * 3
 	int32_t *d_tri_indices = nullptr;  // n_refs
 	uint8_t *d_tris = nullptr;         // n_tris * 100

@@ -23,7 +23,7 @@ namespace adypt {
 
 struct TraceParams {
 	const uint4 *__restrict__ nodes;        // 5 per node
-	const uint4 *__restrict__ nodes_wide;   // 8 per node: the derived 128-byte layout (scene.cu build_wide_nodes), MODE 2 kernels
+	const uint4 *__restrict__ nodes_wide;   // the derived 96-byte layout (scene.cu build_wide_nodes), MODE 2 kernels
 	const float4 *__restrict__ woop;        // 3 per leaf reference
 	const int32_t *__restrict__ tri_indices;
 	const float4 *__restrict__ rays;        // origin + tmin of ray r at rays[r * ray_stride]
@@ -248,41 +248,17 @@ __device__ __forceinline__ uint32_t test_children4_packed(uint32_t meta4, uint32
 	       test_child_pair<2, CVT_PLANES>(meta_oct4, s_lox, s_loy, s_loz, s_hix, s_hiy, s_hiz, aix, aiy, aiz, aox, aoy, aoz, tmin, hit_t, magic);
 }
 
-// Wide nodes (MODE 2). The reference's 80-byte node makes the traversal derive, for each of the eight children and at every visit, what
-// a hit adds to the hit mask: extract the meta byte, XOR an inner child's slot with the ray's octant, split count bits and bit index,
-// shift (~55 of a node step's ~220 instructions). Those words do not depend on the ray except for the octant, so the scene keeps a
-// 128-byte copy of every node (one L2 line) that spells them out:
-//   row 0: px py pz | imask         row 1: 2^ex 2^ey 2^ez (floats) | child_base      rows 2-4: the six quantised planes, unchanged
-//   rows 5-6: c[0..7], c[k] = (meta[k] >> 5) << (meta[k] & 31): a leaf's unary triangle bits at its offset, an inner child's bit 24 + slot
-//   row 7: tri_base
-// A hit child ORs its word in; the octant is applied ONCE per visit, to the assembled byte of inner hits: slot w moves to w ^ octinv,
-// three delta swaps. Same hit mask, bit for bit.
-template <int K, int CVT_PLANES>
-__device__ __forceinline__ uint32_t test_child_pair_wide(uint32_t c0, uint32_t c1, uint32_t s_lox, uint32_t s_loy, uint32_t s_loz, uint32_t s_hix,
-                                                         uint32_t s_hiy, uint32_t s_hiz, float aix, float aiy, float aiz, float aox, float aoy, float aoz,
-                                                         float tmin, float hit_t, uint32_t magic)
+// Wide nodes (MODE 2): the scene keeps a 96-byte, 32-byte aligned copy of every node -- the reference's 80 bytes followed by the three
+// plane scales 2^ex, 2^ey, 2^ez as floats -- so that a visit fetches it with THREE 256-bit loads (Blackwell's ld.global.v8.b32) instead of
+// five 128-bit ones, and does not rebuild the scales from their exponent bytes. Divergent lanes cost the L1 a tag look-up per lane and
+// LOAD, and the L1 is the kernel's second-busiest unit (63 %) after instruction issue.
+struct Words8 { uint32_t v[8]; };
+__device__ __forceinline__ Words8 ldg256(const void *p)
 {
-	float x0, x1, y0, y1, z0, z1, X0, X1, Y0, Y1, Z0, Z1;
-	plane2<K, (CVT_PLANES > 0)>(s_lox, magic, aix, aox, x0, x1);
-	plane2<K, (CVT_PLANES > 2)>(s_loy, magic, aiy, aoy, y0, y1);
-	plane2<K, (CVT_PLANES > 4)>(s_loz, magic, aiz, aoz, z0, z1);
-	plane2<K, (CVT_PLANES > 1)>(s_hix, magic, aix, aox, X0, X1);
-	plane2<K, (CVT_PLANES > 3)>(s_hiy, magic, aiy, aoy, Y0, Y1);
-	plane2<K, (CVT_PLANES > 5)>(s_hiz, magic, aiz, aoz, Z0, Z1);
-	const float lo0 = fmaxf(fmaxf(x0, y0), fmaxf(z0, tmin)), hi0 = fminf(fminf(X0, Y0), fminf(Z0, hit_t));
-	const float lo1 = fmaxf(fmaxf(x1, y1), fmaxf(z1, tmin)), hi1 = fminf(fminf(X1, Y1), fminf(Z1, hit_t));
-	return (lo0 <= hi0 ? c0 : 0u) | (lo1 <= hi1 ? c1 : 0u);
-}
-__device__ __forceinline__ uint32_t permute_inner_slots(uint32_t h, uint32_t octinv)
-{
-#pragma unroll
-	for (uint32_t j = 1u; j <= 4u; j <<= 1) {
-		const uint32_t sh = octinv & j; // 0 or j: a delta swap by 0 is the identity
-		const uint32_t m = (j == 1u ? 0x55u : j == 2u ? 0x33u : 0x0fu) << 24;
-		const uint32_t t = ((h >> sh) ^ h) & m;
-		h ^= t | (t << sh);
-	}
-	return h;
+	Words8 r;
+	asm("ld.global.nc.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+	    : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]) : "l"(p));
+	return r;
 }
 
 // TRI_BATCH: 0 = a lane tests all triangles of its group before the warp moves on (the GLSL's loop shape);
@@ -299,7 +275,7 @@ template <bool ANY, bool STATS = false, int CVT_PLANES = 4, int MIN_CTAS = 8, in
 __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const TraceParams p)
 {
 	constexpr bool PACKED = MODE >= 1; // slab and Woop evaluations as packed fp32 pairs
-	constexpr bool WIDE = MODE >= 2;   // 128-byte nodes with the children's hit-mask contributions spelled out
+	constexpr bool WIDE = MODE >= 2;   // 96-byte nodes fetched with three 256-bit loads
 
 	const uint32_t magic = p.magic;
 	constexpr int NODE_REPS = ANY ? 2 : 1;
@@ -498,35 +474,25 @@ __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const Trac
 					if (STATS) ++st_nodes;
 					const uint32_t slot = (bit - 24u) ^ octinv;
 					const uint32_t rel = (uint32_t)__popc(imask & ~(0xffffffffu << slot));
+					uint4 n0, n1, n2, n3, n4;
+					float scx, scy, scz; // 2^ex, 2^ey, 2^ez
 					if (WIDE) {
-						const uint4 *np = nodes_base + (size_t)(base + rel) * 8u;
-						const uint4 w0 = __ldg(np), w1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4), ca = __ldg(np + 5), cb = __ldg(np + 6);
-						const uint32_t tri_base = __ldg(reinterpret_cast<const uint32_t *>(np + 7));
-						const float aix = __fmul_rn(__uint_as_float(w1.x), idx);
-						const float aiy = __fmul_rn(__uint_as_float(w1.y), idy);
-						const float aiz = __fmul_rn(__uint_as_float(w1.z), idz);
-						const float aox = __fmul_rn(__fsub_rn(__uint_as_float(w0.x), ox), idx);
-						const float aoy = __fmul_rn(__fsub_rn(__uint_as_float(w0.y), oy), idy);
-						const float aoz = __fmul_rn(__fsub_rn(__uint_as_float(w0.z), oz), idz);
-						ng.x = w1.w;
-						tg.x = tri_base;
-						const bool nx = idx < 0.0f, ny = idy < 0.0f, nz = idz < 0.0f;
-						const uint32_t lx0 = nx ? n3.z : n2.x, ly0 = ny ? n4.x : n2.z, lz0 = nz ? n4.z : n3.x, hx0 = nx ? n2.x : n3.z, hy0 = ny ? n2.z : n4.x, hz0 = nz ? n3.x : n4.z;
-						const uint32_t lx1 = nx ? n3.w : n2.y, ly1 = ny ? n4.y : n2.w, lz1 = nz ? n4.w : n3.y, hx1 = nx ? n2.y : n3.w, hy1 = ny ? n2.w : n4.y, hz1 = nz ? n3.y : n4.w;
-						uint32_t hitmask = test_child_pair_wide<0, CVT_PLANES>(ca.x, ca.y, lx0, ly0, lz0, hx0, hy0, hz0, aix, aiy, aiz, aox, aoy, aoz, tmin, hit_t, magic);
-						hitmask |= test_child_pair_wide<2, CVT_PLANES>(ca.z, ca.w, lx0, ly0, lz0, hx0, hy0, hz0, aix, aiy, aiz, aox, aoy, aoz, tmin, hit_t, magic);
-						hitmask |= test_child_pair_wide<0, CVT_PLANES>(cb.x, cb.y, lx1, ly1, lz1, hx1, hy1, hz1, aix, aiy, aiz, aox, aoy, aoz, tmin, hit_t, magic);
-						hitmask |= test_child_pair_wide<2, CVT_PLANES>(cb.z, cb.w, lx1, ly1, lz1, hx1, hy1, hz1, aix, aiy, aiz, aox, aoy, aoz, tmin, hit_t, magic);
-						hitmask = permute_inner_slots(hitmask, octinv);
-						ng.y = (hitmask & 0xff000000u) | w0.w;
-						tg.y = hitmask & 0x00ffffffu;
+						const uint8_t *np = reinterpret_cast<const uint8_t *>(nodes_base) + (size_t)(base + rel) * 96u;
+						const Words8 a = ldg256(np), b = ldg256(np + 32), c = ldg256(np + 64);
+						n0 = make_uint4(a.v[0], a.v[1], a.v[2], a.v[3]); n1 = make_uint4(a.v[4], a.v[5], a.v[6], a.v[7]);
+						n2 = make_uint4(b.v[0], b.v[1], b.v[2], b.v[3]); n3 = make_uint4(b.v[4], b.v[5], b.v[6], b.v[7]);
+						n4 = make_uint4(c.v[0], c.v[1], c.v[2], c.v[3]);
+						scx = __uint_as_float(c.v[4]); scy = __uint_as_float(c.v[5]); scz = __uint_as_float(c.v[6]);
 					} else {
-					const uint4 *np = nodes_base + (size_t)(base + rel) * 5u;
-					const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
-
-					const float aix = __fmul_rn(__uint_as_float((n0.w & 0xffu) << 23), idx);
-					const float aiy = __fmul_rn(__uint_as_float(((n0.w >> 8) & 0xffu) << 23), idy);
-					const float aiz = __fmul_rn(__uint_as_float(((n0.w >> 16) & 0xffu) << 23), idz);
+						const uint4 *np = nodes_base + (size_t)(base + rel) * 5u;
+						n0 = __ldg(np); n1 = __ldg(np + 1); n2 = __ldg(np + 2); n3 = __ldg(np + 3); n4 = __ldg(np + 4);
+						scx = __uint_as_float((n0.w & 0xffu) << 23);
+						scy = __uint_as_float(((n0.w >> 8) & 0xffu) << 23);
+						scz = __uint_as_float(((n0.w >> 16) & 0xffu) << 23);
+					}
+					const float aix = __fmul_rn(scx, idx);
+					const float aiy = __fmul_rn(scy, idy);
+					const float aiz = __fmul_rn(scz, idz);
 					const float aox = __fmul_rn(__fsub_rn(__uint_as_float(n0.x), ox), idx);
 					const float aoy = __fmul_rn(__fsub_rn(__uint_as_float(n0.y), oy), idy);
 					const float aoz = __fmul_rn(__fsub_rn(__uint_as_float(n0.z), oz), idz);
@@ -559,7 +525,6 @@ __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const Trac
 					}
 					ng.y = (hitmask & 0xff000000u) | (n0.w >> 24);
 					tg.y = hitmask & 0x00ffffffu;
-					}
 				}
 				// The GLSL's else branch (:207-211, "G is a triangle group": tg = ng, ng = 0) cannot be reached: ng.y is
 				// above 0x00ffffff at ray start and after every pop (only groups with inner hits are pushed), and a

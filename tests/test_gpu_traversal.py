@@ -83,6 +83,22 @@ def test_empty_and_ragged_batches(A, cpu):
     assert r["t"] is None and r["uv"] is None and np.array_equal(r["tri"], o["tri"][:100])
 
 
+def test_kernel_variants_agree_bit_for_bit(A, cpu):
+    """Every code-generation variant of the traversal kernel (scene.cu trace_kernel_for) -- the scalar kernel on the reference's 80-byte
+    nodes (19), packed FFMA2 evaluations (13-15), packed on 96-byte nodes fetched with 256-bit loads (0 = the product, 16-18), the older
+    tuning variants -- returns the oracle's ids, t and uv bits and any-hit flags."""
+    for name in ("city12", "tiny_deep"):
+        g = load_golden(name)
+        sc = A.Scene(g.nodes, g.tri_indices, g.woop)
+        rays = g.extra["rays"]
+        want = cpu.trace_closest(g.nodes, g.tri_indices, g.woop, rays)
+        want_any = cpu.trace_any(g.nodes, g.woop, rays)
+        for variant in (0, 19, 13, 14, 15, 16, 17, 18, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11):
+            sc.configure(0, 0, variant)
+            assert_same_hits(sc.trace_closest(rays), want)
+            assert np.array_equal(sc.trace_any(rays), want_any), (name, variant)
+
+
 def test_host_array_call_equals_device_call_across_its_chunk_schedule(A):
     """The host-array call cuts the batch into chunks with short first and last ones (scene.cu trace_host); sizes around the point
     where that schedule switches on, and odd ones that put chunk boundaries at odd ray indices, against ONE device launch."""
@@ -254,7 +270,7 @@ def test_c2_incoherent_rays(A, cpu, c2):
     assert torch.equal(p_tri, d_tri[perm]) and torch.equal(p_t.view(torch.int32), d_t[perm].view(torch.int32))
     assert torch.equal(p_uv.view(torch.int32), d_uv[perm].view(torch.int32))
     # the structure-of-arrays entry the wavefront uses (origins and directions as two arrays) is the same kernel with another stride
-    for variant in (0, 9):  # product kernel; hit-mask table variant
+    for variant in (0, 19, 13, 9):  # product kernel; the scalar kernel on 80-byte nodes; packed on 80-byte nodes; hit-mask table variant
         sc.configure(0, 0, variant)
         sc.trace_closest(d_rays[:1_000_000], again[:1_000_000], None, None, stream=st)
         torch.cuda.synchronize()

@@ -22,8 +22,9 @@ def _cuobjdump():
 def test_traversal_kernels_fit_eight_ctas_per_sm():
     out = subprocess.run([_cuobjdump(), "-res-usage", adypt_b200.LIB_PATH], capture_output=True, text=True, check=True).stdout
     usage = dict(re.findall(r"Function (\S+):\s*\n\s*(REG:.*)", out))
-    # the product kernels: closest-hit and any-hit with the default tuning (CVT planes 4, 8 CTAs/SM, triangle batch 12, staged)
-    names = [n for n in usage if re.match(r"_ZN5adypt12trace_kernelILb[01]ELb0ELi4ELi8ELi12ELb1ELb0EEE", n)]
+    # the product kernels: closest-hit and any-hit with the default tuning (CVT planes 3, 8 CTAs/SM, triangle batch 12, staged, packed
+    # evaluations on 96-byte nodes)
+    names = [n for n in usage if re.match(r"_ZN5adypt12trace_kernelILb[01]ELb0ELi3ELi8ELi12ELb1ELb0ELi2EEE", n)]
     assert len(names) == 2, sorted(usage)
     for n in names:
         f = {k: int(v) for k, v in re.findall(r"([A-Z]+):(\d+)", usage[n])}
