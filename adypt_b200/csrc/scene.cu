@@ -103,6 +103,29 @@ __global__ void build_wide_nodes(const uint4 *__restrict__ nodes, uint32_t n_nod
 	o[5] = make_uint4((w & 0xffu) << 23, ((w >> 8) & 0xffu) << 23, ((w >> 16) & 0xffu) << 23, 0u);
 }
 
+// EXPERIMENT (traverse.cuh, MODE 3): 128-byte nodes with the children's hit-mask words
+__global__ void build_wide_nodes128(const uint4 *__restrict__ nodes, uint32_t n_nodes, uint4 *__restrict__ wide)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_nodes) return;
+	const uint4 n0 = nodes[(size_t)i * 5u], n1 = nodes[(size_t)i * 5u + 1], n2 = nodes[(size_t)i * 5u + 2], n3 = nodes[(size_t)i * 5u + 3], n4 = nodes[(size_t)i * 5u + 4];
+	uint32_t c[8];
+#pragma unroll
+	for (int k = 0; k < 8; ++k) {
+		const uint32_t b = ((k < 4 ? n1.z : n1.w) >> (8 * (k & 3))) & 0xffu;
+		c[k] = (b >> 5) << (b & 31u);
+	}
+	uint4 *o = wide + (size_t)i * 8u;
+	o[0] = make_uint4(n0.x, n0.y, n0.z, n0.w >> 24);
+	o[1] = make_uint4((n0.w & 0xffu) << 23, ((n0.w >> 8) & 0xffu) << 23, ((n0.w >> 16) & 0xffu) << 23, n1.x);
+	o[2] = n2;
+	o[3] = n3;
+	o[4] = n4;
+	o[5] = make_uint4(c[0], c[1], c[2], c[3]);
+	o[6] = make_uint4(c[4], c[5], c[6], c[7]);
+	o[7] = make_uint4(n1.y, 0u, 0u, 0u);
+}
+
 // Shading records: the wavefront's shading stage gathers one Triangle per segment. The reference's record is
 // 100 bytes at a 100-byte stride (Shape.hpp:70-88) -- 25 scalar loads over 4 or 5 sectors; here it is copied, unchanged, to
 // the start of a 128-byte line (7 vector loads, exactly one L2 line). The shading branch its material selects
@@ -155,6 +178,8 @@ TraceKernel trace_kernel_for(bool any, bool stats, int variant)
 	case 17: return trace_kernel<true, false, 3, 8, 12, true, false, 2>;
 	case 18: return trace_kernel<true, false, 2, 8, 12, true, false, 2>;
 	case 19: return trace_kernel<true>;
+	case 20: return trace_kernel<true, false, 3, 8, 12, true, false, 3>;
+	case 21: return trace_kernel<true, false, 4, 8, 12, true, false, 3>;
 	default: return trace_kernel<true, false, 3, 8, 12, true, false, 2>;
 	}
 	switch (variant) {
@@ -176,6 +201,8 @@ TraceKernel trace_kernel_for(bool any, bool stats, int variant)
 	case 17: return trace_kernel<false, false, 3, 8, 12, true, false, 2>;
 	case 18: return trace_kernel<false, false, 2, 8, 12, true, false, 2>;
 	case 19: return trace_kernel<false>; // scalar evaluations, 80-byte nodes
+	case 20: return trace_kernel<false, false, 3, 8, 12, true, false, 3>; // experiment: 128-byte nodes with hit-mask words
+	case 21: return trace_kernel<false, false, 4, 8, 12, true, false, 3>;
 	default: return trace_kernel<false, false, 3, 8, 12, true, false, 2>;
 	}
 }
@@ -189,6 +216,7 @@ int launch_trace(adypt_scene *s, const float4 *d_rays, uint64_t n, int32_t *d_tr
 	TraceParams p;
 	p.nodes = s->d_nodes;
 	p.nodes_wide = s->d_nodes_wide;
+	p.nodes_wide128 = s->d_nodes_wide128;
 	p.woop = s->d_woop;
 	p.tri_indices = s->d_tri_indices;
 	p.rays = d_rays;
@@ -256,6 +284,7 @@ static void free_scene(adypt_scene *s)
 	DeviceGuard g(s->device);
 	cudaFree(s->d_nodes);
 	cudaFree(s->d_nodes_wide);
+	cudaFree(s->d_nodes_wide128);
 	cudaFree(s->d_woop);
 	cudaFree(s->d_tri_indices);
 	cudaFree(s->d_tris);
@@ -493,9 +522,15 @@ int adypt_trace_configure(adypt_scene *s, int ctas_per_sm, int refill_threshold,
 {
 	return guarded([&]() -> int {
 	if (!s) return fail(ADYPT_EINVAL, "scene is NULL");
-	if (ctas_per_sm < 0 || refill_threshold < 0 || refill_threshold > 32 || variant < 0 || variant > 19) return fail(ADYPT_EINVAL, "bad tuning value");
+	if (ctas_per_sm < 0 || refill_threshold < 0 || refill_threshold > 32 || variant < 0 || variant > 21) return fail(ADYPT_EINVAL, "bad tuning value");
 	if (variant == 12 && !getenv("ADYPT_EXPERIMENTAL"))
 		return fail(ADYPT_EINVAL, "variant 12 (shared-memory ray pool) is an experiment without a deep-stack path: set ADYPT_EXPERIMENTAL=1 to select it");
+	if ((variant == 20 || variant == 21) && !s->d_nodes_wide128 && s->n_nodes) { // the experiment's node copy is built when it is first asked for
+		DeviceGuard g(s->device);
+		ADYPT_CUDA(cudaMalloc((void **)&s->d_nodes_wide128, (size_t)s->n_nodes * 128u));
+		build_wide_nodes128<<<(s->n_nodes + 127) / 128, 128>>>(s->d_nodes, s->n_nodes, s->d_nodes_wide128);
+		ADYPT_CUDA(cudaDeviceSynchronize());
+	}
 	s->ctas_per_sm = ctas_per_sm;
 	s->refill_threshold = refill_threshold;
 	s->variant = variant;

@@ -24,6 +24,7 @@ namespace adypt {
 struct TraceParams {
 	const uint4 *__restrict__ nodes;        // 5 per node
 	const uint4 *__restrict__ nodes_wide;   // the derived 96-byte layout (scene.cu build_wide_nodes), MODE 2 kernels
+	const uint4 *__restrict__ nodes_wide128; // experiment (MODE 3), built on demand
 	const float4 *__restrict__ woop;        // 3 per leaf reference
 	const int32_t *__restrict__ tri_indices;
 	const float4 *__restrict__ rays;        // origin + tmin of ray r at rays[r * ray_stride]
@@ -261,6 +262,37 @@ __device__ __forceinline__ Words8 ldg256(const void *p)
 	return r;
 }
 
+// EXPERIMENT (MODE 3): 128-byte nodes that also spell out what each child adds to the hit mask (c[k] = (meta[k] >> 5) << (meta[k] & 31)),
+// so a visit ORs words in and applies the octant once (three delta swaps on the byte of inner hits) instead of decoding eight meta bytes
+// (~55 -> ~25 instructions). Rows of 32 bytes: [p, imask | scales, child_base] [lox loy loz hix] [hiy hiz | c0..c3] [c4..c7 | tri_base].
+template <int K, int CVT_PLANES>
+__device__ __forceinline__ uint32_t test_child_pair_wide(uint32_t c0, uint32_t c1, uint32_t s_lox, uint32_t s_loy, uint32_t s_loz, uint32_t s_hix,
+                                                         uint32_t s_hiy, uint32_t s_hiz, float aix, float aiy, float aiz, float aox, float aoy, float aoz,
+                                                         float tmin, float hit_t, uint32_t magic)
+{
+	float x0, x1, y0, y1, z0, z1, X0, X1, Y0, Y1, Z0, Z1;
+	plane2<K, (CVT_PLANES > 0)>(s_lox, magic, aix, aox, x0, x1);
+	plane2<K, (CVT_PLANES > 2)>(s_loy, magic, aiy, aoy, y0, y1);
+	plane2<K, (CVT_PLANES > 4)>(s_loz, magic, aiz, aoz, z0, z1);
+	plane2<K, (CVT_PLANES > 1)>(s_hix, magic, aix, aox, X0, X1);
+	plane2<K, (CVT_PLANES > 3)>(s_hiy, magic, aiy, aoy, Y0, Y1);
+	plane2<K, (CVT_PLANES > 5)>(s_hiz, magic, aiz, aoz, Z0, Z1);
+	const float lo0 = fmaxf(fmaxf(x0, y0), fmaxf(z0, tmin)), hi0 = fminf(fminf(X0, Y0), fminf(Z0, hit_t));
+	const float lo1 = fmaxf(fmaxf(x1, y1), fmaxf(z1, tmin)), hi1 = fminf(fminf(X1, Y1), fminf(Z1, hit_t));
+	return (lo0 <= hi0 ? c0 : 0u) | (lo1 <= hi1 ? c1 : 0u);
+}
+__device__ __forceinline__ uint32_t permute_inner_slots(uint32_t h, uint32_t octinv)
+{
+#pragma unroll
+	for (uint32_t j = 1u; j <= 4u; j <<= 1) {
+		const uint32_t sh = octinv & j; // 0 or j: a delta swap by 0 is the identity
+		const uint32_t m = (j == 1u ? 0x55u : j == 2u ? 0x33u : 0x0fu) << 24;
+		const uint32_t t = ((h >> sh) ^ h) & m;
+		h ^= t | (t << sh);
+	}
+	return h;
+}
+
 // TRI_BATCH: 0 = a lane tests all triangles of its group before the warp moves on (the GLSL's loop shape);
 // K > 0 = at most K triangle tests per lane and round, lanes with triangles left skip their next node step until
 // the group is empty; 12 = K 2 with both triangles' rows fetched before the first test. Only the warp-level
@@ -275,7 +307,8 @@ template <bool ANY, bool STATS = false, int CVT_PLANES = 4, int MIN_CTAS = 8, in
 __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const TraceParams p)
 {
 	constexpr bool PACKED = MODE >= 1; // slab and Woop evaluations as packed fp32 pairs
-	constexpr bool WIDE = MODE >= 2;   // 96-byte nodes fetched with three 256-bit loads
+	constexpr bool WIDE = MODE == 2;   // 96-byte nodes fetched with three 256-bit loads
+	constexpr bool WIDE128 = MODE == 3; // experiment: 128-byte nodes with hit-mask words, four 256-bit loads
 
 	const uint32_t magic = p.magic;
 	constexpr int NODE_REPS = ANY ? 2 : 1;
@@ -298,7 +331,7 @@ __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const Trac
 	const unsigned lane = (lane_addr >> 3) & 31u;
 	const unsigned lt_mask = ~(0xffffffffu << lane);
 	const unsigned long long n_rays = p.n_ptr ? *p.n_ptr : p.n;
-	const uint4 *nodes_base = WIDE ? p.nodes_wide : p.nodes;
+	const uint4 *nodes_base = WIDE ? p.nodes_wide : WIDE128 ? p.nodes_wide128 : p.nodes;
 	const float4 *woop_base = p.woop;
 #ifdef ADYPT_PTR_REGS
 	asm volatile("mov.u64 %0, %0;" : "+l"(nodes_base));
@@ -474,6 +507,31 @@ __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const Trac
 					if (STATS) ++st_nodes;
 					const uint32_t slot = (bit - 24u) ^ octinv;
 					const uint32_t rel = (uint32_t)__popc(imask & ~(0xffffffffu << slot));
+					if (WIDE128) {
+						const uint8_t *np = reinterpret_cast<const uint8_t *>(nodes_base) + (size_t)(base + rel) * 128u;
+						const Words8 a = ldg256(np), b = ldg256(np + 32), c = ldg256(np + 64), d = ldg256(np + 96);
+						const float aix = __fmul_rn(__uint_as_float(a.v[4]), idx);
+						const float aiy = __fmul_rn(__uint_as_float(a.v[5]), idy);
+						const float aiz = __fmul_rn(__uint_as_float(a.v[6]), idz);
+						const float aox = __fmul_rn(__fsub_rn(__uint_as_float(a.v[0]), ox), idx);
+						const float aoy = __fmul_rn(__fsub_rn(__uint_as_float(a.v[1]), oy), idy);
+						const float aoz = __fmul_rn(__fsub_rn(__uint_as_float(a.v[2]), oz), idz);
+						ng.x = a.v[7];
+						tg.x = d.v[4];
+						const bool nx = idx < 0.0f, ny = idy < 0.0f, nz = idz < 0.0f;
+						// planes: b = (lox.lo, lox.hi, loy.lo, loy.hi, loz.lo, loz.hi, hix.lo, hix.hi), c.v[0..3] = (hiy.lo, hiy.hi, hiz.lo, hiz.hi)
+						const uint32_t lx0 = nx ? b.v[6] : b.v[0], ly0 = ny ? c.v[0] : b.v[2], lz0 = nz ? c.v[2] : b.v[4];
+						const uint32_t hx0 = nx ? b.v[0] : b.v[6], hy0 = ny ? b.v[2] : c.v[0], hz0 = nz ? b.v[4] : c.v[2];
+						const uint32_t lx1 = nx ? b.v[7] : b.v[1], ly1 = ny ? c.v[1] : b.v[3], lz1 = nz ? c.v[3] : b.v[5];
+						const uint32_t hx1 = nx ? b.v[1] : b.v[7], hy1 = ny ? b.v[3] : c.v[1], hz1 = nz ? b.v[5] : c.v[3];
+						uint32_t hitmask = test_child_pair_wide<0, CVT_PLANES>(c.v[4], c.v[5], lx0, ly0, lz0, hx0, hy0, hz0, aix, aiy, aiz, aox, aoy, aoz, tmin, hit_t, magic);
+						hitmask |= test_child_pair_wide<2, CVT_PLANES>(c.v[6], c.v[7], lx0, ly0, lz0, hx0, hy0, hz0, aix, aiy, aiz, aox, aoy, aoz, tmin, hit_t, magic);
+						hitmask |= test_child_pair_wide<0, CVT_PLANES>(d.v[0], d.v[1], lx1, ly1, lz1, hx1, hy1, hz1, aix, aiy, aiz, aox, aoy, aoz, tmin, hit_t, magic);
+						hitmask |= test_child_pair_wide<2, CVT_PLANES>(d.v[2], d.v[3], lx1, ly1, lz1, hx1, hy1, hz1, aix, aiy, aiz, aox, aoy, aoz, tmin, hit_t, magic);
+						hitmask = permute_inner_slots(hitmask, octinv);
+						ng.y = (hitmask & 0xff000000u) | a.v[3];
+						tg.y = hitmask & 0x00ffffffu;
+					} else {
 					uint4 n0, n1, n2, n3, n4;
 					float scx, scy, scz; // 2^ex, 2^ey, 2^ez
 					if (WIDE) {
@@ -525,6 +583,7 @@ __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const Trac
 					}
 					ng.y = (hitmask & 0xff000000u) | (n0.w >> 24);
 					tg.y = hitmask & 0x00ffffffu;
+					}
 				}
 				// The GLSL's else branch (:207-211, "G is a triangle group": tg = ng, ng = 0) cannot be reached: ng.y is
 				// above 0x00ffffff at ray start and after every pop (only groups with inner hits are pushed), and a
