@@ -1,0 +1,11 @@
+#!/bin/bash
+# round 2, evidence for the packed / 96-byte-node traversal kernel: full gpu test suite, ncu --set full of the closest-hit launch on C2 and C4
+# (DRAM bytes per launch for bench.py's roofline.traffic), C3 launch list, bench + reference arm, smoke()
+O=gpurun_out/r2ao; mkdir -p $O
+timeout 1500 python -m pytest tests -m gpu -q > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -2 $O/pytest_gpu.log
+timeout 600 ncu --set full --import-source on --clock-control none -k regex:trace_kernel -s 3 -c 1 -o $O/prof_trace_c2 -f python tools/profile_variant.py 0 5 > $O/ncu_trace_c2.log 2>&1; echo "ncu c2 rc=$?"
+timeout 900 ncu --set full --import-source on --clock-control none -k regex:trace_kernel -s 3 -c 1 -o $O/prof_trace_c4 -f python tools/profile_c4.py > $O/ncu_trace_c4.log 2>&1; echo "ncu c4 rc=$?"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/launches_c3.csv python tools/pt_time.py > $O/pt_time_ncu.log 2>&1; echo "launch list c3 rc=$?"
+timeout 900 python bench.py --impl reference --steps 20 --warmup 5 > $O/bench_reference.json 2> $O/bench_reference.err; echo "ref rc=$?"
+timeout 900 python bench.py --steps 20 --warmup 5 > $O/bench.json 2> $O/bench.err; echo "bench rc=$?"; tail -3 $O/bench.err
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
