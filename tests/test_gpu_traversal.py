@@ -92,7 +92,7 @@ def test_kernel_variants_agree_bit_for_bit(A, cpu):
         sc = A.Scene(g.nodes, g.tri_indices, g.woop)
         rays = g.extra["rays"]
         want = cpu.trace_closest(g.nodes, g.tri_indices, g.woop, rays)
-        want_any = cpu.trace_any(g.nodes, g.woop, rays)
+        want_any = cpu.trace_any(g.nodes, g.woop, rays)["occluded"]
         for variant in (0, 19, 13, 14, 15, 16, 17, 18, 20, 21, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11):
             sc.configure(0, 0, variant)
             assert_same_hits(sc.trace_closest(rays), want)
