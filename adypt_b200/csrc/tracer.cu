@@ -455,7 +455,7 @@ enum { kClassMiss = 0, kClassDiffuse = 1, kClassGlossy = 2, kClassMirror = 3, kC
 // is *sure_base + sure_idx (*sure_base is kNoBase until the reservation has come back).
 constexpr unsigned kNoBase = 0xffffffffu;
 __device__ __forceinline__ void shade_queue_entry(const ShadeBuffers &B, const PTArgs &A, int b, float tmin, bool last, int dims, unsigned q,
-                                                  int32_t tri_idx, int32_t mat_idx, const volatile unsigned *sure_base = nullptr, unsigned sure_idx = 0u)
+                                                  int32_t tri_idx, int32_t mat_idx, const unsigned *sure_base = nullptr, unsigned sure_idx = 0u)
 {
 	const bool sure = sure_base != nullptr;
 	bool keep = false, conn = false;
@@ -502,10 +502,14 @@ __device__ __forceinline__ void shade_queue_entry(const ShadeBuffers &B, const P
 		}
 	}
 	unsigned long long slot = queue_append(keep && !sure, B.out_count, A.zero);
-	if (sure) {
-		unsigned base;
-		while ((base = *sure_base) == kNoBase) {}
-		slot = base + sure_idx; // queue positions fit 32 bits (alloc_wavefront)
+	const unsigned sure_m = __ballot_sync(kFullMask, sure);
+	if (sure_m != 0u) { // warp-uniform. One lane waits for the block's reservation (an atomic read: the flag is written with an atomic too)
+		const unsigned leader = (unsigned)__ffs((int)sure_m) - 1u;
+		unsigned base = 0u;
+		if ((threadIdx.x & 31u) == leader)
+			while ((base = atomicOr(const_cast<unsigned *>(sure_base), 0u)) == kNoBase) {}
+		base = __shfl_sync(kFullMask, base, (int)leader);
+		if (sure) slot = base + sure_idx; // queue positions fit 32 bits (alloc_wavefront)
 	}
 	if (keep) {
 		B.out_org[slot] = make_float4(origin.x, origin.y, origin.z, tmin);
@@ -710,7 +714,7 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) k_shade_bounce_multi(Shad
 			if (threadIdx.x == 9u) s_base[buf ^ 1u] = kNoBase;
 		}
 		__syncthreads();
-		if (block_slots && threadIdx.x == 0u) *(volatile unsigned *)&s_base[buf] = reserved; // whoever needs a slot before this waits for it
+		if (block_slots && threadIdx.x == 0u) atomicExch(&s_base[buf], reserved); // whoever needs a slot before this waits for it (shade_queue_entry)
 		const unsigned n_valid = q0 >= total ? 0u : (total - q0 < kN ? total - q0 : kN);
 		const unsigned n_chunks = (n_valid + 31u) / 32u;
 		const unsigned n_miss = s_total[buf][kClassMiss], n_glossy = s_total[buf][kClassGlossy]; // the regions in front of the sure ones
@@ -724,7 +728,7 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) k_shade_bounce_multi(Shad
 			const unsigned cls = w >> 24;
 			const bool sure = block_slots && (cls == (unsigned)kClassDiffuse || cls == (unsigned)kClassMirror || cls == (unsigned)kClassGlass || cls == (unsigned)kClassOther);
 			shade_queue_entry(B, A, b, tmin, last, dims, q0 + s_order[buf][p], s_tri[buf][p], (w & 0x00ffffffu) != 0x00ffffffu ? (int32_t)(w & 0x00ffffffu) : -1,
-			                  sure ? (const volatile unsigned *)&s_base[buf] : nullptr, p - n_miss - (cls > (unsigned)kClassGlossy ? n_glossy : 0u));
+			                  sure ? &s_base[buf] : nullptr, p - n_miss - (cls > (unsigned)kClassGlossy ? n_glossy : 0u));
 		}
 	}
 }

@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const Trac
 	constexpr bool WIDE128 = MODE == 3; // experiment: 128-byte nodes with hit-mask words, four 256-bit loads
 
 	const uint32_t magic = p.magic;
-	constexpr int NODE_REPS = ANY ? 2 : 1;
+	constexpr int NODE_REPS = (ANY && TRI_BATCH > 0) ? 2 : 1; // the unbounded triangle loop (TRI_BATCH 0) has no "triangles left over" state to skip a node step with
 	// Shared memory, one region per warp: [stack: kSmemStack entries x 32 lanes x 8 B][stage: 3 rows x 32 entries x 16 B].
 	// Every address is formed from ONE register, lane_addr = region + 8 * lane (stack entry sp of this lane is at
 	// lane_addr + 256 * sp; 8-byte accesses of a warp are conflict-free), and so are the lane number and its lt-mask:
