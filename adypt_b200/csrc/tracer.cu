@@ -450,14 +450,13 @@ enum { kClassMiss = 0, kClassDiffuse = 1, kClassGlossy = 2, kClassMirror = 3, kC
 
 // One queue entry of bounce b: everything of Render's loop body after the intersection (pathtracer.glsl:130-201) and the hand-over
 // to the next queue. Called by all 32 lanes of a warp together (the queue appends are warp-collective); tri_idx == -2 = no entry.
-// sure_base != nullptr: the caller knows from the entry's class that the path goes on (diffuse, mirror, dielectric, pass-through; not the
+// sure: the caller knows from the entry's class that the path goes on (diffuse, mirror, dielectric, pass-through; not the
 // last bounce, no Russian roulette) and its block has reserved the slots of all such entries of the round with ONE atomic: the entry's slot
 // is *sure_base + sure_idx (*sure_base is kNoBase until the reservation has come back).
 constexpr unsigned kNoBase = 0xffffffffu;
 __device__ __forceinline__ void shade_queue_entry(const ShadeBuffers &B, const PTArgs &A, int b, float tmin, bool last, int dims, unsigned q,
-                                                  int32_t tri_idx, int32_t mat_idx, const unsigned *sure_base = nullptr, unsigned sure_idx = 0u)
+                                                  int32_t tri_idx, int32_t mat_idx, bool sure = false, unsigned *sure_base = nullptr, unsigned sure_idx = 0u)
 {
-	const bool sure = sure_base != nullptr;
 	bool keep = false, conn = false;
 	V3 origin = v3(0, 0, 0), dir = v3(0, 0, 0), color = v3(0, 0, 0);
 	unsigned id = 0, bias_bits = 0;
@@ -507,7 +506,7 @@ __device__ __forceinline__ void shade_queue_entry(const ShadeBuffers &B, const P
 		const unsigned leader = (unsigned)__ffs((int)sure_m) - 1u;
 		unsigned base = 0u;
 		if ((threadIdx.x & 31u) == leader)
-			while ((base = atomicOr(const_cast<unsigned *>(sure_base), 0u)) == kNoBase) {}
+			while ((base = atomicOr(sure_base, 0u)) == kNoBase) {}
 		base = __shfl_sync(kFullMask, base, (int)leader);
 		if (sure) slot = base + sure_idx; // queue positions fit 32 bits (alloc_wavefront)
 	}
@@ -726,9 +725,11 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) k_shade_bounce_multi(Shad
 			const unsigned p = c * 32u + lane;
 			const unsigned w = (unsigned)s_mat[buf][p]; // class << 24 | material id
 			const unsigned cls = w >> 24;
-			const bool sure = block_slots && (cls == (unsigned)kClassDiffuse || cls == (unsigned)kClassMirror || cls == (unsigned)kClassGlass || cls == (unsigned)kClassOther);
-			shade_queue_entry(B, A, b, tmin, last, dims, q0 + s_order[buf][p], s_tri[buf][p], (w & 0x00ffffffu) != 0x00ffffffu ? (int32_t)(w & 0x00ffffffu) : -1,
-			                  sure ? &s_base[buf] : nullptr, p - n_miss - (cls > (unsigned)kClassGlossy ? n_glossy : 0u));
+			constexpr unsigned kSureClasses = (1u << kClassDiffuse) | (1u << kClassMirror) | (1u << kClassGlass) | (1u << kClassOther);
+			const bool sure = block_slots && ((kSureClasses >> cls) & 1u) != 0u;
+			const unsigned mat = w & 0x00ffffffu;
+			shade_queue_entry(B, A, b, tmin, last, dims, q0 + s_order[buf][p], s_tri[buf][p], mat != 0x00ffffffu ? (int32_t)mat : -1, sure, &s_base[buf],
+			                  p - n_miss - (cls > (unsigned)kClassGlossy ? n_glossy : 0u));
 		}
 	}
 }
