@@ -604,17 +604,19 @@ __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const Trac
 		if (STATS) ++st_tris; \
 		float tt, tu, tv; \
 		woop_eval<PACKED>(ox, oy, oz, dx, dy, dz, M0, M1, M2, tt, tu, tv); \
-		if (tt > tmin && tt < hit_t && tu >= 0.0f && tu <= 1.0f && tv >= 0.0f && __fadd_rn(tu, tv) <= 1.0f) { \
+		if (tt > tmin && tt < hit_t && tu >= 0.0f && tv >= 0.0f && __fadd_rn(tu, tv) <= 1.0f) { /* u <= 1 is implied, see below */ \
 			hit_t = tt; \
 			if (ANY) finished = true; /* :480-483 */ \
 			else { hit_u = tu; hit_v = tv; hit_idx = (int32_t)(TR); } \
 		} \
 	} while (0)
 #define ADYPT_WOOP_EVAL(M0, M1, M2, TT, TU, TV) woop_eval<PACKED>(ox, oy, oz, dx, dy, dz, M0, M1, M2, TT, TU, TV)
+	// The reference also tests u <= 1 (traversal.glsl:235). It is implied by the others for every input -- v >= 0 makes u + v >= u, rounding is
+	// monotonic, so u <= fl(u + v) <= 1, and a NaN u already fails u >= 0 -- so the acceptance below leaves it out (same results, one compare less).
 #define ADYPT_WOOP_ACCEPT(TR, TT, TU, TV) \
 	do { \
 		if (STATS) ++st_tris; \
-		if (TT > tmin && TT < hit_t && TU >= 0.0f && TU <= 1.0f && TV >= 0.0f && __fadd_rn(TU, TV) <= 1.0f) { \
+		if (TT > tmin && TT < hit_t && TU >= 0.0f && TV >= 0.0f && __fadd_rn(TU, TV) <= 1.0f) { \
 			hit_t = TT; \
 			if (ANY) finished = true; /* :480-483 */ \
 			else { hit_u = TU; hit_v = TV; hit_idx = (int32_t)(TR); } \

@@ -52,6 +52,8 @@ def main():
         mn, md = timed(lambda: sc.trace_any(d_rays, occ, stream=st))
         print(f'any-hit 8M variant {v}: {mn:.3f} ms {n/mn/1e3:.0f} Mrays/s')
     sc.configure(0, best[1], best[0])
+    if os.environ.get('TUNE_NO_PT'):
+        return
     # path tracer, C3-like
     mesh3 = W.city(183, 1, mixed_materials=True)
     hs3 = host.build_scene(mesh3); sc3 = hs3.upload(0); sc3.configure(0, best[1], best[0])
