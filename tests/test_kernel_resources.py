@@ -38,3 +38,19 @@ def test_traversal_kernels_fit_eight_ctas_per_sm():
         if "k_shade_primaryILi4E" in n or "k_shade_primary_sorted" in n:  # bounce 0 (default: class-sorted, 128 threads x 8 CTAs per
             assert f["REG"] <= 64 and f["STACK"] <= 384, (n, f)  # SM): local memory = the parked chunk (8 x 2 float4) + a few spills
             assert f["SHARED"] <= 12288, (n, f)                   # 8 CTAs x 12 KB of sort buffers fit beside the L1
+
+
+@pytest.mark.skipif(_cuobjdump() is None, reason="cuobjdump not found")
+def test_product_traversal_kernel_uses_packed_fp32_and_256_bit_node_loads():
+    """The SASS of the product kernels must hold what DESIGN.md 4.1 says they are built from: packed FFMA2 / FADD2 / FMUL2 for the slab and
+    Woop evaluations, and exactly three 256-bit loads (the 96-byte node) -- a silent fall-back to the scalar form would still pass every
+    parity test."""
+    for any_hit in (0, 1):
+        fn = f"_ZN5adypt12trace_kernelILb{any_hit}ELb0ELi3ELi8ELi12ELb1ELb0ELi2EEEvNS_11TraceParamsE"
+        sass = subprocess.run([_cuobjdump(), "-sass", "-fun", fn, adypt_b200.LIB_PATH], capture_output=True, text=True).stdout
+        ops = re.findall(r"^\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_.]+)", sass, flags=re.M)
+        assert len(ops) > 500, (fn, len(ops))
+        count = lambda prefix: sum(1 for o in ops if o.startswith(prefix))
+        assert count("FFMA2") >= 36 and count("FADD2") >= 12 and count("FMUL2") >= 6, (fn, count("FFMA2"), count("FADD2"), count("FMUL2"))
+        assert count("LDG.E.ENL2.256") == 3, (fn, count("LDG.E.ENL2.256"))
+        assert count("I2F.U8") == 24, (fn, count("I2F.U8"))  # three of the six planes on the conversion pipe
