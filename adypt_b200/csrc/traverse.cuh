@@ -9,9 +9,11 @@
 //
 // FP policy: IEEE fp32, round-to-nearest, no implicit contraction (explicit __f*_rn
 // intrinsics), with fused multiply-add exactly where the oracle has fmaf(): the 48 slab evaluations per
-// node and the Woop dot chains.
+// node and the Woop dot chains. The product kernel (MODE 2) issues those two at a time with Blackwell's packed
+// fp32 instructions (fma / sub / mul .rn.f32x2 -> FFMA2 / FADD2 / FMUL2): each half is the scalar IEEE operation.
 //
-// Memory: node = 5 x LDG.128 and Woop = 3 x LDG.128 through the read-only path (L1 + L2; C1/C2 BVHs are
+// Memory: node = 3 x 256-bit loads of the scene's 96-byte node copy (MODE 2; 5 x LDG.128 of the reference's
+// 80-byte node in the older variants) and Woop = 3 x LDG.128 through the read-only path (L1 + L2; C1/C2 BVHs are
 // L2-resident on B200), traversal stack = kSmemStack entries per lane in shared memory (per warp [entry][lane],
 // so a warp's 8-byte accesses are conflict-free) with a local-memory overflow that real scenes never reach.
 #pragma once
