@@ -126,6 +126,17 @@ __global__ void build_wide_nodes128(const uint4 *__restrict__ nodes, uint32_t n_
 	o[7] = make_uint4(n1.y, 0u, 0u, 0u);
 }
 
+// EXPERIMENT (traverse.cuh, MODE 5): Woop rows at a 64-byte stride
+__global__ void build_woop64(const float4 *__restrict__ woop, uint32_t n_refs, float4 *__restrict__ out)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_refs) return;
+	out[(size_t)i * 4u] = woop[(size_t)i * 3u];
+	out[(size_t)i * 4u + 1] = woop[(size_t)i * 3u + 1];
+	out[(size_t)i * 4u + 2] = woop[(size_t)i * 3u + 2];
+	out[(size_t)i * 4u + 3] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
 // Shading records: the wavefront's shading stage gathers one Triangle per segment. The reference's record is
 // 100 bytes at a 100-byte stride (Shape.hpp:70-88) -- 25 scalar loads over 4 or 5 sectors; here it is copied, unchanged, to
 // the start of a 128-byte line (7 vector loads, exactly one L2 line). The shading branch its material selects
@@ -180,6 +191,7 @@ TraceKernel trace_kernel_for(bool any, bool stats, int variant)
 	case 19: return trace_kernel<true>;
 	case 20: return trace_kernel<true, false, 3, 8, 12, true, false, 3>;
 	case 21: return trace_kernel<true, false, 4, 8, 12, true, false, 3>;
+	case 22: return trace_kernel<true, false, 3, 8, 12, true, false, 5>;
 	default: return trace_kernel<true, false, 3, 8, 12, true, false, 2>;
 	}
 	switch (variant) {
@@ -203,6 +215,7 @@ TraceKernel trace_kernel_for(bool any, bool stats, int variant)
 	case 19: return trace_kernel<false>; // scalar evaluations, 80-byte nodes
 	case 20: return trace_kernel<false, false, 3, 8, 12, true, false, 3>; // experiment: 128-byte nodes with hit-mask words
 	case 21: return trace_kernel<false, false, 4, 8, 12, true, false, 3>;
+	case 22: return trace_kernel<false, false, 3, 8, 12, true, false, 5>; // experiment: the product kernel with 64-byte Woop rows, two 256-bit loads per test
 	default: return trace_kernel<false, false, 3, 8, 12, true, false, 2>;
 	}
 }
@@ -217,6 +230,7 @@ int launch_trace(adypt_scene *s, const float4 *d_rays, uint64_t n, int32_t *d_tr
 	p.nodes = s->d_nodes;
 	p.nodes_wide = s->d_nodes_wide;
 	p.nodes_wide128 = s->d_nodes_wide128;
+	p.woop64 = s->d_woop64;
 	p.woop = s->d_woop;
 	p.tri_indices = s->d_tri_indices;
 	p.rays = d_rays;
@@ -285,6 +299,7 @@ static void free_scene(adypt_scene *s)
 	cudaFree(s->d_nodes);
 	cudaFree(s->d_nodes_wide);
 	cudaFree(s->d_nodes_wide128);
+	cudaFree(s->d_woop64);
 	cudaFree(s->d_woop);
 	cudaFree(s->d_tri_indices);
 	cudaFree(s->d_tris);
@@ -522,13 +537,19 @@ int adypt_trace_configure(adypt_scene *s, int ctas_per_sm, int refill_threshold,
 {
 	return guarded([&]() -> int {
 	if (!s) return fail(ADYPT_EINVAL, "scene is NULL");
-	if (ctas_per_sm < 0 || refill_threshold < 0 || refill_threshold > 32 || variant < 0 || variant > 21) return fail(ADYPT_EINVAL, "bad tuning value");
+	if (ctas_per_sm < 0 || refill_threshold < 0 || refill_threshold > 32 || variant < 0 || variant > 22) return fail(ADYPT_EINVAL, "bad tuning value");
 	if (variant == 12 && !getenv("ADYPT_EXPERIMENTAL"))
 		return fail(ADYPT_EINVAL, "variant 12 (shared-memory ray pool) is an experiment without a deep-stack path: set ADYPT_EXPERIMENTAL=1 to select it");
 	if ((variant == 20 || variant == 21) && !s->d_nodes_wide128 && s->n_nodes) { // the experiment's node copy is built when it is first asked for
 		DeviceGuard g(s->device);
 		ADYPT_CUDA(cudaMalloc((void **)&s->d_nodes_wide128, (size_t)s->n_nodes * 128u));
 		build_wide_nodes128<<<(s->n_nodes + 127) / 128, 128>>>(s->d_nodes, s->n_nodes, s->d_nodes_wide128);
+		ADYPT_CUDA(cudaDeviceSynchronize());
+	}
+	if (variant == 22 && !s->d_woop64 && s->n_refs) { // the experiment's Woop copy is built when it is first asked for
+		DeviceGuard g(s->device);
+		ADYPT_CUDA(cudaMalloc((void **)&s->d_woop64, (size_t)s->n_refs * 64u));
+		build_woop64<<<(s->n_refs + 255) / 256, 256>>>(s->d_woop, s->n_refs, s->d_woop64);
 		ADYPT_CUDA(cudaDeviceSynchronize());
 	}
 	s->ctas_per_sm = ctas_per_sm;

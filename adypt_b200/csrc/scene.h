@@ -21,6 +21,7 @@ struct adypt_scene {
 	uint4 *d_nodes = nullptr;          // n_nodes * 5
 	uint4 *d_nodes_wide = nullptr;     // n_nodes * 6: derived 96-byte layout (build_wide_nodes)
 	uint4 *d_nodes_wide128 = nullptr;  // experiment (variants 20, 21): n_nodes * 8, built on demand
+	float4 *d_woop64 = nullptr;        // experiment (variant 22): n_refs * 4, built on demand
 	float4 *d_woop = nullptr;          // n_refs * 3
 	int32_t *d_tri_indices = nullptr;  // n_refs
 	uint8_t *d_tris = nullptr;         // n_tris * 100

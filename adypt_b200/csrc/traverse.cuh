@@ -27,6 +27,7 @@ struct TraceParams {
 	const uint4 *__restrict__ nodes;        // 5 per node
 	const uint4 *__restrict__ nodes_wide;   // the derived 96-byte layout (scene.cu build_wide_nodes), MODE 2 kernels
 	const uint4 *__restrict__ nodes_wide128; // experiment (MODE 3), built on demand
+	const float4 *__restrict__ woop64;       // experiment (MODE 5), built on demand: 64-byte rows (48 bytes of Woop + 16 spare), 4 float4 per reference
 	const float4 *__restrict__ woop;        // 3 per leaf reference
 	const int32_t *__restrict__ tri_indices;
 	const float4 *__restrict__ rays;        // origin + tmin of ray r at rays[r * ray_stride]
@@ -309,7 +310,8 @@ template <bool ANY, bool STATS = false, int CVT_PLANES = 4, int MIN_CTAS = 8, in
 __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const TraceParams p)
 {
 	constexpr bool PACKED = MODE >= 1; // slab and Woop evaluations as packed fp32 pairs
-	constexpr bool WIDE = MODE == 2;   // 96-byte nodes fetched with three 256-bit loads
+	constexpr bool WIDE = MODE == 2 || MODE == 5; // 96-byte nodes fetched with three 256-bit loads
+	constexpr bool WOOP64 = MODE == 5; // experiment: 64-byte Woop rows fetched with two 256-bit loads
 	constexpr bool WIDE128 = MODE == 3; // experiment: 128-byte nodes with hit-mask words, four 256-bit loads
 
 	const uint32_t magic = p.magic;
@@ -334,7 +336,7 @@ __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const Trac
 	const unsigned lt_mask = ~(0xffffffffu << lane);
 	const unsigned long long n_rays = p.n_ptr ? *p.n_ptr : p.n;
 	const uint4 *nodes_base = WIDE ? p.nodes_wide : WIDE128 ? p.nodes_wide128 : p.nodes;
-	const float4 *woop_base = p.woop;
+	const float4 *woop_base = WOOP64 ? p.woop64 : p.woop;
 #ifdef ADYPT_PTR_REGS
 	asm volatile("mov.u64 %0, %0;" : "+l"(nodes_base));
 #if ADYPT_PTR_REGS > 1
@@ -632,10 +634,23 @@ __global__ void __launch_bounds__(kTraceBlock, MIN_CTAS) trace_kernel(const Trac
 						const bool two = tg.y != 0u;
 						const uint32_t tr1 = tg.x + (uint32_t)(__ffs((int)tg.y) - 1);
 						tg.y &= tg.y - 1u; // no-op on 0
-						const float4 *wa = woop_base + (size_t)tr0 * 3u;
-						const float4 *wb = woop_base + (size_t)(two ? tr1 : tr0) * 3u;
-						const float4 a0 = __ldg(wa), a1 = __ldg(wa + 1), a2 = __ldg(wa + 2);
-						const float4 b0 = __ldg(wb), b1 = __ldg(wb + 1), b2 = __ldg(wb + 2);
+						float4 a0, a1, a2, b0, b1, b2;
+						if (WOOP64) {
+							const float4 *wa = woop_base + (size_t)tr0 * 4u;
+							const float4 *wb = woop_base + (size_t)(two ? tr1 : tr0) * 4u;
+							const Words8 pa = ldg256(wa), qa = ldg256(wa + 2), pb = ldg256(wb), qb = ldg256(wb + 2);
+							a0 = make_float4(__uint_as_float(pa.v[0]), __uint_as_float(pa.v[1]), __uint_as_float(pa.v[2]), __uint_as_float(pa.v[3]));
+							a1 = make_float4(__uint_as_float(pa.v[4]), __uint_as_float(pa.v[5]), __uint_as_float(pa.v[6]), __uint_as_float(pa.v[7]));
+							a2 = make_float4(__uint_as_float(qa.v[0]), __uint_as_float(qa.v[1]), __uint_as_float(qa.v[2]), __uint_as_float(qa.v[3]));
+							b0 = make_float4(__uint_as_float(pb.v[0]), __uint_as_float(pb.v[1]), __uint_as_float(pb.v[2]), __uint_as_float(pb.v[3]));
+							b1 = make_float4(__uint_as_float(pb.v[4]), __uint_as_float(pb.v[5]), __uint_as_float(pb.v[6]), __uint_as_float(pb.v[7]));
+							b2 = make_float4(__uint_as_float(qb.v[0]), __uint_as_float(qb.v[1]), __uint_as_float(qb.v[2]), __uint_as_float(qb.v[3]));
+						} else {
+							const float4 *wa = woop_base + (size_t)tr0 * 3u;
+							const float4 *wb = woop_base + (size_t)(two ? tr1 : tr0) * 3u;
+							a0 = __ldg(wa); a1 = __ldg(wa + 1); a2 = __ldg(wa + 2);
+							b0 = __ldg(wb); b1 = __ldg(wb + 1); b2 = __ldg(wb + 2);
+						}
 						if (!ANY) {
 							// both triangles' t, u, v first (they do not depend on hit_t, so ptxas can interleave the two chains;
 							// a lane with one triangle evaluates it twice, wb == wa), then the acceptance tests in the reference's

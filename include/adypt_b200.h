@@ -114,7 +114,7 @@ int adypt_trace_stats(adypt_scene *scene, const float *rays, uint64_t n, int mem
 /* number of kernel launches adypt_* calls have issued so far on this scene's device (bench accounting) */
 int adypt_launch_count(uint64_t *launches);
 /* tuning knobs of the persistent traversal kernel (0 = default): CTAs per SM, the refill threshold, and a
- * variant of the traversal kernels (0..21, see trace_kernel_for / launch_trace in csrc/scene.cu: 0 = the product kernel, the rest are the
+ * variant of the traversal kernels (0..22, see trace_kernel_for / launch_trace in csrc/scene.cu: 0 = the product kernel, the rest are the
  * measured alternatives kept for A/B runs, e.g. 9-11 the shared-memory hit-mask table, 12 the shared-memory ray pool; identical results) */
 int adypt_trace_configure(adypt_scene *scene, int ctas_per_sm, int refill_threshold, int variant);
 
